@@ -1,0 +1,287 @@
+"""Benchmark of the RCGAN training hot path (BASELINE.json metric: RCGAN G+D train images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference-equivalent CPU path (oracle)
+
+A "step" is one full training iteration of the reference hot loop (mnist/model.py:335-372): 1 discriminator
+step + 2 generator(+confusion) steps; images/sec = real images consumed per second = B / t_iter.
+Workload at N=1 (and per GPU for N>1, weak scaling): BASELINE configs[1], MNIST DCGAN RCGAN-U (learned confusion
+matrix + permutation regulariser), batch 1024, bf16, synthetic 28x28x1.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'mnist_rcganu_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=True)),
+    'mnist_rcgan_b64': dict(batch=64, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False)),
+    'mnist_rcgany_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False,
+                                                      concat_y=True, concat_y_layers=[1])),
+}
+METRIC = 'RCGAN G+D train images/sec'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+def synthetic(B, seed=0):
+    """Config-2 inputs: X~U[0,1) 28x28x1, one-hot labels from randint (the label sampler is not in the step)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    eye = torch.eye(10)
+    lab = lambda: eye[torch.randint(0, 10, (B,), generator=g)]
+    d = dict(batch_images=torch.rand(B, 28, 28, 1, generator=g), batch_z=torch.rand(B, 100, generator=g) * 2 - 1,
+             batch_labels_real=lab(), batch_labels_gen=lab(), batch_labels_fake=lab(), batch_labels_real_weights=lab())
+    return {k: v.contiguous().pin_memory() if torch.cuda.is_available() else v for k, v in d.items()}
+
+
+def oracle_iteration_timer(B, flags, threads):
+    """The reference-equivalent CPU path: the oracle restatement (PyTorch-CPU fp32, literal reference graph incl.
+    its 10 label-wise discriminator calls) -- TensorFlow 1.5 itself cannot be installed here."""
+    import torch
+    from oracle import mnist as OM, sampler as OS
+    torch.set_num_threads(threads)
+    cfg = OM.default_config(batch_size=B, alpha=0.5, perm_regularizer=True, **flags)
+    P = OM.init_params(cfg, 0, torch.float32)
+    C = OS.one_coin_confusion(0.5)
+    b = OM.synthetic_batch(B, 0, torch.float32, C, cfg)
+    tr = OM.Trainer(P, cfg, C)
+
+    def step():
+        t = time.perf_counter()
+        tr.iteration(b)
+        return time.perf_counter() - t
+    return step
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    B = 128                                  # bounded sample: one iteration at 1/8 of the workload batch
+    step = oracle_iteration_timer(B, wl['flags'], cores)
+    for _ in range(min(args.warmup, 2)):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = B / t
+    sample = 'oracle iteration (1 D + 2 G steps, literal reference graph) at batch %d, fp32, %d threads' % (B, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_step': B},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def op_profile(model, reps=5):
+    """Per-op device time (CUDA events on the launching stream, L2 flushed between reps) of both programs; returns
+    the dominant op with its algorithmic work for the roofline entry."""
+    import torch
+    from robust_conditional_gan_b200 import nnops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    rows = []
+    for prog in (model.d_prog, model.g_prog):
+        prog.run_forward(); prog.run_backward()
+        for op in prog.ops:
+            for direction in ('forward', 'backward'):
+                fn = getattr(op, direction)
+                ts = []
+                for _ in range(reps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); fn(prog); e1.record(); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms = sorted(ts)[len(ts) // 2]
+                flops = 0
+                if isinstance(op, (nnops.ConvOp, nnops.DeconvOp)):
+                    d = op.desc
+                    f1 = 2.0 * d.n * d.ho * d.wo * d.cout * d.kh * d.kw * d.cin
+                    if direction == 'forward':
+                        flops = f1
+                    else:
+                        flops = f1 * (int(op.need[0]) + int(op.need[1])) if any(op.need) else 0
+                rows.append(dict(prog=prog.name, op=type(op).__name__, shape=str(tuple(op.outputs[0].shape)) if op.outputs else '',
+                                 dir=direction, ms=ms, flops=flops))
+    return rows
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from robust_conditional_gan_b200 import _C
+    from robust_conditional_gan_b200.model import DCGAN, default_flags
+    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    B = wl['batch']
+    flags = default_flags(batch_size=B, alpha=0.5, **wl['flags'])
+    lib = _C.load()
+    model = DCGAN(batch_size=B, algorithm=flags.algorithm, estimate_confuse=flags.estimate_confuse, perm_regularizer=True,
+                  alpha=0.5, disc_type=flags.disc_type, config=flags, precision=args.precision, world_size=world, rank=rank,
+                  seed=0)
+    feeds = synthetic(B, seed=rank)
+    # launches per iteration: count once with eager (uncaptured) launches
+    model.use_cuda_graph = False
+    n0 = lib.rcgan_launch_count()
+    model.train_iteration(**feeds)
+    launches_per_iter = lib.rcgan_launch_count() - n0
+    model.use_cuda_graph = True
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        model.train_iteration(**feeds)
+    # ---- leg 1: inputs resident in HBM, device-timed
+    model.feed(**feeds)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model.train_iteration(fetch_losses=False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- leg 2: end to end through the public API: pinned-host inputs copied every step, losses read back
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = model.train_iteration(fetch_losses=True, **feeds)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    h2d = sum(v.numel() * 4 for v in feeds.values()) + sum(feeds[k].numel() * 4 for k in ('batch_z', 'batch_labels_gen', 'batch_labels_fake'))
+    d2h = 4 * (len(model.d_prog.loss_names) + len(model.g_prog.loss_names))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms / args.steps
+    value = world * B / (ms_step / 1e3)
+    result = {
+        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': world * B, 'step': '1 D step + 2 G(+C) steps',
+                   'parallelism': 'dp%d' % world,
+                   'l2': 'no explicit flush: one iteration touches ~1.5 GB of activations/gradients, >> 126 MB L2'},
+        'clocks': clk,
+        'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': launches_per_iter * args.steps,
+        'losses': {k: round(v, 5) for k, v in out.items()},
+    }
+    if world == 1:
+        # roofline of the dominant op (timed live, CUDA events, L2 flushed) ...
+        rows = op_profile(model)
+        tot = sum(r['ms'] for r in rows)
+        top = max(rows, key=lambda r: r['ms'])
+        if top['flops'] > 0:
+            ach = top['flops'] / (top['ms'] * 1e-3) / 1e12
+            result['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s',
+                                  'frac': ach / pk['tf_burst'], 'traffic': None, 'peak_source': pk['src'] + ' bf16 burst',
+                                  'kernel': '%s %s %s %s' % (top['prog'], top['op'], top['shape'], top['dir']),
+                                  'share_of_step': top['ms'] / tot}
+        else:
+            result['roofline'] = {'bound': 'hbm', 'achieved': None, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': None,
+                                  'traffic': None, 'kernel': '%s %s %s' % (top['prog'], top['op'], top['dir'])}
+        result['op_profile_top'] = [dict(r, ms=round(r['ms'], 4)) for r in sorted(rows, key=lambda r: -r['ms'])[:8]]
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
+            json.dump(rows, f, indent=1)
+        # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            step = oracle_iteration_timer(B, wl['flags'], cores)
+            step()
+            t = step()
+            result['cpu_baseline'] = {'value': B / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                      'sample': '1 warm-up + 1 timed oracle iteration (1 D + 2 G steps) at batch %d, fp32' % B}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='mnist_rcganu_b1024', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

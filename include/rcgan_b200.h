@@ -1,0 +1,209 @@
+/* rcgan_b200 -- C ABI of the B200-native RCGAN training hot path.
+ *
+ * One shared object, `librcgan_b200.so`, `extern "C"`, plain pointers and sizes.
+ * The reference (tkkiran/Robust-Conditional-GAN) is pure Python over TensorFlow 1.5
+ * and has no FFI of its own: the "interface each entry replaces" is the TensorFlow
+ * op the reference's wrapper calls, cited per entry as reference file:line.
+ *
+ * Conventions:
+ *   - every entry returns 0 on success or a negative rcgan_status; the message of the
+ *     last failure on the calling thread is available from rcgan_last_error();
+ *   - never allocates device memory, never synchronises, never throws; all pointers are
+ *     DEVICE pointers to caller-owned buffers unless the name says host;
+ *   - kernels are enqueued on the caller's stream (`void* stream` is a cudaStream_t),
+ *     so they can be captured into a CUDA graph by the caller;
+ *   - activations are NHWC ("rows x channels", channels fastest) with an explicit
+ *     channel stride `ld` (elements per pixel, >= channels) so padded concat buffers
+ *     can be consumed in place;  `dtype` selects the activation storage type;
+ *   - parameters, gradients of parameters, statistics and optimizer state are fp32.
+ */
+#ifndef RCGAN_B200_H
+#define RCGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum rcgan_status { RCGAN_OK = 0, RCGAN_EBADSHAPE = -1, RCGAN_EUNSUPPORTED = -2, RCGAN_ECUDA = -3 };
+enum rcgan_dtype { RCGAN_F32 = 0, RCGAN_BF16 = 1 };
+enum rcgan_act { RCGAN_ACT_NONE = 0, RCGAN_ACT_RELU = 1, RCGAN_ACT_LRELU = 2, RCGAN_ACT_SIGMOID = 3, RCGAN_ACT_TANH = 4 };
+/* GAN loss link functions: mnist/model.py:135-147, cifar10/gan_resnet.py:604-606,751 */
+enum rcgan_loss_mode {
+  RCGAN_HINGE_D_REAL = 0, /* relu(1-l) */ RCGAN_HINGE_D_FAKE = 1, /* relu(1+l) */ RCGAN_HINGE_G = 2, /* -l */
+  RCGAN_CE_D_REAL = 3, /* sCE(l,1) */ RCGAN_CE_D_FAKE = 4, /* sCE(l,0) */ RCGAN_CE_G = 5 /* sCE(l,1) */
+};
+
+const char* rcgan_last_error(void);
+int rcgan_abi_version(void);
+/* number of kernels this library has launched in this process (captured graph replays are not re-counted) */
+long rcgan_launch_count(void);
+/* 1 when the library was built for sm_100a and the current device is compute capability 10.x */
+int rcgan_device_ok(void);
+
+/* ---------------------------------------------------------------- convolution family
+ * Replaces tf.nn.conv2d (mnist/ops.py:62, cifar10/common/ops/conv2d.py:181-187) and its
+ * autodiff dgrad/wgrad; tf.nn.conv2d_transpose (mnist/ops.py:78) is the dgrad entry used
+ * as a forward op; tf.matmul linears (mnist/ops.py:114-116, cifar10/common/ops/linear.py:
+ * 163-173) are the 1x1, h=w=1 case.  Filter layout HWIO [kh,kw,cin,cout] fp32. */
+typedef struct {
+  int n, h, w, cin;     /* conv input  x  [n,h,w,cin]   */
+  int ho, wo, cout;     /* conv output y  [n,ho,wo,cout] */
+  int kh, kw, stride;   /* square stride */
+  int pad_t, pad_l;     /* TF SAME pad_before (top, left) */
+  int ldx, ldy;         /* channel strides of the x-side and y-side buffers (elements) */
+  int dtype;            /* rcgan_dtype of x/y/dx/dy */
+} rcgan_conv_desc;
+
+/* bytes of the bf16 tensor-core weight pack for this shape, 0 if the shape runs on the
+ * CUDA-core path (tiny channel counts: cin or cout not a multiple of 8, K < 64 ...). */
+size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d);
+/* w_f32 (optionally scaled by *scale_dev, e.g. 1/sigma) -> bf16 pack (both GEMM layouts) */
+int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scale_dev, void* pack, void* stream);
+
+/* y = act(conv(x, w) + bias)        bias may be NULL.  out_dtype: storage type of y -- d->dtype, or RCGAN_F32
+ * for a bf16 conv whose output feeds a batch norm (kept fp32: the norm's backward cancels catastrophically on
+ * bf16-rounded inputs). */
+int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
+                       const float* bias, void* y, int out_dtype, int act, float leak, void* stream);
+/* dx (=|+=) act(conv_dgrad(dy, w) + bias): the backward-data op; with bias/act it is the
+ * forward of deconv2d (mnist/ops.py:69-92).  bias may be NULL. */
+int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, const float* w, const void* wpack,
+                       const float* bias, void* dx, int out_dtype, int act, float leak, int accumulate, void* stream);
+/* dw (=|+=) x^T * dy ;  ws: caller workspace of rcgan_conv2d_wgrad_workspace() bytes */
+size_t rcgan_conv2d_wgrad_workspace(const rcgan_conv_desc* d);
+int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- rows x channels helpers */
+/* db[c] (=|+=) sum_r dy[r,c]   (bias gradients of conv / deconv / linear) */
+int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream);
+/* y = act(x + bias) and dx = dy * act'(y)  (standalone activations: lrelu/relu/sigmoid/tanh) */
+int rcgan_bias_act_fwd(const void* x, const float* bias, void* y, long rows, int c, int ldx, int ldy, int dtype,
+                       int act, float leak, void* stream);
+int rcgan_act_bwd(const void* dy, const void* y, void* dx, long rows, int c, int ld_dy, int ld_y, int ld_dx,
+                  int dtype, int act, float leak, int accumulate, void* stream);
+/* out[r, 0:c1] = a[r,:], out[r, c1:c1+c2] = yb[r / rows_per_sample, :], out[r, c1+c2:ldo] = 0
+ * (ops.conv_cond_concat mnist/ops.py:46-51 and the z|y, h|y concats of mnist/model.py:714-728);
+ * yb is fp32 [samples, c2].  Backward: da (=|+=) dout[:, 0:c1]. */
+int rcgan_concat_label_fwd(const void* a, int lda, const float* yb, void* out, int ldo, long rows, int rows_per_sample,
+                           int c1, int c2, int dtype, void* stream);
+int rcgan_slice_bwd(const void* dout, int ldo, void* da, int lda, long rows, int c1, int dtype, int accumulate,
+                    void* stream);
+/* y[s,c] = mean over hw of x[s,hw,c]  (tf.reduce_mean(h3, axis=(1,2)) mnist/model.py:678; gan_resnet.py:407),
+ * with optional relu applied to x first (gan_resnet.py:405).  Backward broadcasts dy/hw (times relu mask). */
+int rcgan_meanhw_fwd(const void* x, void* y, int samples, int hw, int c, int dtype, int relu, void* stream);
+int rcgan_meanhw_bwd(const void* dy, const void* x, void* dx, int samples, int hw, int c, int dtype, int relu,
+                     int accumulate, void* stream);
+/* 2x2 mean pool / nearest-neighbour 2x upsample and residual add (cifar10/gan_resnet.py:231-272, 328) */
+int rcgan_avgpool2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream);
+int rcgan_avgpool2_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dtype, int accumulate, void* stream);
+int rcgan_upsample2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream);
+int rcgan_upsample2_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dtype, int accumulate, void* stream);
+int rcgan_add(const void* a, const void* b, void* out, long numel, int dtype, void* stream);
+/* dst (=|+=) src */
+int rcgan_copy_acc(const void* src, void* dst, long numel, int dtype, int accumulate, void* stream);
+/* fp32 -> activation dtype cast (feeding inputs), and back */
+int rcgan_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long numel, void* stream);
+
+/* ---------------------------------------------------------------- (conditional) batch norm
+ * tf.contrib.layers.batch_norm (mnist/ops.py:30-44) when labels == NULL (tables have one row);
+ * cond_batchnorm (cifar10/common/ops/normalization.py:27-59) when labels != NULL.
+ * x is [samples*hw, c] of type xdtype; y, dy and dx are of type ydtype (xdtype f32 with ydtype bf16 is the
+ * bf16-mode layout); stats are over all rows, biased variance, eps inside rsqrt.
+ * save[2*c] receives (mean, invstd).  moving_mean/var (may be NULL) are updated with `decay`
+ * (Bessel-corrected variance).  train == 0 normalises with the moving statistics instead. */
+size_t rcgan_bn_workspace(int samples, int hw, int c);
+int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale, const float* offset,
+                 const int* labels, float eps, int act, float leak, int train, float decay, float* moving_mean,
+                 float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream);
+/* dx (=|+=) ; dscale/doffset [n_labels, c] (=|+=).  y is the activated forward output. */
+int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype, int ydtype,
+                 const float* scale, const int* labels, int n_labels, const float* save, int act, float leak,
+                 float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* ---------------------------------------------------------------- spectral norm
+ * spectral_normed_weight (mnist/sn.py:17-75 == cifar10/common/ops/sn.py), one power iteration.
+ * W [m,c] fp32, u [c].  Outputs: w_bar [m,c] fp32 (may be NULL), u_new [c], and `save`
+ * (rcgan_sn_save_floats(m,c) floats: sigma, 1/sigma, na, n, a[m], b[c], t[m] ...) for backward.
+ * The gradient flows THROUGH the power iteration. */
+size_t rcgan_sn_save_floats(int m, int c);
+size_t rcgan_sn_workspace(int m, int c);
+int rcgan_sn_fwd(const float* W, const float* u, int m, int c, float* w_bar, float* u_new, float* save, void* ws,
+                 size_t ws_bytes, void* stream);
+/* dW (=|+=) from G = dL/dW_bar */
+int rcgan_sn_bwd(const float* W, const float* u, const float* G, int m, int c, const float* save, float* dW,
+                 int accumulate, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- losses
+ * Unified noisy-channel projection loss (mnist/model.py:150-207,679-686;
+ * cifar10/gan_resnet.py:588-606,649-685,751-760):
+ *   l[b,j] = psi[b] + <h[b,:], V[j,:]>,   L = scale * sum_b sum_j wgt[b,j] * phi_mode(l[b,j])
+ * h [B,d] (activation dtype, ld = d), psi [B] fp32, V [k,d] fp32, wgt [B,k] fp32.
+ * Outputs (any may be NULL): loss_acc[0] += L; logits [B,k] fp32; dh (=|+=) [B,d] activation dtype;
+ * dpsi [B] fp32 (=); dV [k,d] fp32 (+=); dwgt [B,k] fp32 (=). */
+int rcgan_channel_loss(const void* h, const float* psi, const float* V, const float* wgt, int B, int d, int k,
+                       int dtype, int mode, float scale, float* loss_acc, float* logits, void* dh, int accumulate_dh,
+                       float* dpsi, float* dV, float* dwgt, void* stream);
+/* mean sigmoid cross entropy (perm regulariser, mnist/model.py:214-224; gan_resnet.py:486-490,687-695):
+ * loss_acc[0] += scale * sum sCE(logits, targets);  dlogits = scale * (sigmoid(l) - t).  fp32 [B,k]. */
+int rcgan_sigmoid_ce(const float* logits, const float* targets, long numel, float scale, float* loss_acc,
+                     float* dlogits, void* stream);
+/* Scalar-logit GAN loss (vanilla discriminator, mnist/model.py:687-703 + :135-147):
+ * loss_acc[0] += scale * sum_b phi_mode(l[b]);  dl[b] = scale * phi'(l[b]).  fp32 [B]. */
+int rcgan_logit_loss(const float* logits, long B, int mode, float scale, float* loss_acc, float* dlogits, void* stream);
+/* Row softmax of the confusion logits and its backward (mnist/model.py:106; gan_resnet.py:522):
+ * C = softmax(L); dL = C * (dC - <dC, C>_row).  [k,k] fp32. */
+int rcgan_softmax_rows_fwd(const float* logits, float* C, int rows, int k, void* stream);
+int rcgan_softmax_rows_bwd(const float* C, const float* dC, float* dlogits, int rows, int k, int accumulate,
+                           void* stream);
+/* wgt[b,:] = C[y[b],:] (tensordot(onehot(y), C)); backward dC[y[b],:] += dwgt[b,:] (dC zeroed by the call when !accumulate) */
+int rcgan_gather_rows_fwd(const float* C, const int* y, float* wgt, int B, int k, void* stream);
+int rcgan_gather_rows_bwd(const float* dwgt, const int* y, float* dC, int B, int k, int rows, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * tf.train.AdamOptimizer (mnist/model.py:250-262; gan_resnet.py:802-817) over one flat arena:
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr_t * m / (sqrt(v) + eps),
+ * lr_t = lr * sqrt(1-b2^t)/(1-b1^t) is computed by the caller; when lr_t_dev != NULL it is read from that
+ * device float instead (so a captured CUDA graph can be replayed with a new step count).  grad_scale multiplies g first
+ * (1/world_size after an allreduce-sum).  Elements in [clip_lo[i], clip_hi[i]) (n_clip <= 8 ranges)
+ * are clipped to [-1,1] after the update (max-norm variable constraint, mnist/ops.py:101-111). */
+int rcgan_adam_tf(float* p, const float* g, float* m, float* v, long numel, float lr_t, const float* lr_t_dev, float b1,
+                  float b2, float eps, float grad_scale, const long* clip_lo, const long* clip_hi, int n_clip,
+                  void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on the caller's stream (zeroing gradient arenas / loss slots inside a captured step) */
+int rcgan_zero(void* ptr, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------- label-noise sampler
+ * numpy legacy RandomState stream on the device (mnist/model.py:795-834, :293-333;
+ * cifar10/common/data/cifar10.py:29-38).  `state` is 625 uint32 (624 MT19937 words + position).
+ * `table` (device, doubles) comes from rcgan_sampler_table_host(): per confusion-matrix row and
+ * class index the binomial-inversion constants, computed on the HOST with libm exactly as numpy does. */
+#define RCGAN_MT_STATE_WORDS 625
+#define RCGAN_SAMPLER_TABLE_DOUBLES(k) ((k) * ((k) - 1) * 4)
+void rcgan_sampler_table_host(const double* C, int k, double* table);
+int rcgan_mt_seed(uint32_t* state, uint32_t seed, void* stream);
+/* Fisher-Yates permutation exactly as np.random.shuffle draws it; perm[n] int32 */
+int rcgan_mt_shuffle_perm(uint32_t* state, int32_t* perm, int n, void* stream);
+/* mnist: for each i: real[i] ~ C[y[i]], gen[i] = randint(k) (or real[i] if real_match), fake[i] ~ C[gen[i]] */
+int rcgan_sample_labels_mnist(uint32_t* state, const double* table, int k, const int32_t* y, int n, int real_match,
+                              int32_t* real, int32_t* gen, int32_t* fake, void* stream);
+/* re-noising pass (mnist/model.py:329-333): real2[i] ~ C[real[i]], fake2[i] ~ C[fake[i]] interleaved */
+int rcgan_sample_renoise_mnist(uint32_t* state, const double* table, int k, const int32_t* real, const int32_t* fake,
+                               int n, int32_t* real2, int32_t* fake2, void* stream);
+/* cifar: rnd = randint(k, size=n) first, then per i: labels[i] ~ C[labels[i]] (in place), biased[i] ~ C[rnd[i]] */
+int rcgan_sample_labels_cifar(uint32_t* state, const double* table, int k, int32_t* labels, int n, int32_t* rnd,
+                              int32_t* biased, void* stream);
+/* out[i] = lo + (hi-lo)*random_double()  (np.random.uniform; batch_z mnist/model.py:342), stored as fp32 */
+int rcgan_mt_uniform(uint32_t* state, float* out, long n, double lo, double hi, void* stream);
+/* CIFAR real-data preprocessing (gan_resnet.py:548-552): int32 CHW [n,3072] in [0,255] ->
+ * 2*(v/256 - .5) + noise[n,3072 NHWC-ordered after transpose] (noise may be NULL), NHWC, activation dtype */
+int rcgan_preprocess_cifar(const int32_t* chw, const float* noise, void* out, int n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,124 @@
+"""ctypes binding of librcgan_b200.so (the C ABI declared in include/rcgan_b200.h).
+
+There is NO fallback: if the shared object is missing or a call fails, this raises.
+PyTorch is used by the callers only for device memory and streams; every pointer handed
+to the library is a raw `tensor.data_ptr()` and every launch goes to the caller's stream.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_long, c_size_t, c_uint32, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'librcgan_b200.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
+MT_STATE_WORDS = 625
+
+
+class RcganError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    """rcgan_conv_desc"""
+    _fields_ = [(n, c_int) for n in ('n', 'h', 'w', 'cin', 'ho', 'wo', 'cout', 'kh', 'kw', 'stride', 'pad_t', 'pad_l',
+                                     'ldx', 'ldy', 'dtype')]
+
+
+P = c_void_p
+DP = POINTER(ConvDesc)
+_SIGS = {
+    'rcgan_last_error': (c_char_p, []),
+    'rcgan_abi_version': (c_int, []),
+    'rcgan_launch_count': (c_long, []),
+    'rcgan_device_ok': (c_int, []),
+    'rcgan_conv_wpack_bytes': (c_size_t, [DP]),
+    'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
+    'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
+    'rcgan_conv2d_dgrad': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, c_int, P]),
+    'rcgan_conv2d_wgrad_workspace': (c_size_t, [DP]),
+    'rcgan_conv2d_wgrad': (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),
+    'rcgan_colsum': (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, P]),
+    'rcgan_bias_act_fwd': (c_int, [P, P, P, c_long, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    'rcgan_act_bwd': (c_int, [P, P, P, c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    'rcgan_concat_label_fwd': (c_int, [P, c_int, P, P, c_int, c_long, c_int, c_int, c_int, c_int, P]),
+    'rcgan_slice_bwd': (c_int, [P, c_int, P, c_int, c_long, c_int, c_int, c_int, P]),
+    'rcgan_meanhw_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_meanhw_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_avgpool2_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_avgpool2_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_upsample2_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_upsample2_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_add': (c_int, [P, P, P, c_long, c_int, P]),
+    'rcgan_copy_acc': (c_int, [P, P, c_long, c_int, c_int, P]),
+    'rcgan_cast': (c_int, [P, c_int, P, c_int, c_long, P]),
+    'rcgan_bn_workspace': (c_size_t, [c_int, c_int, c_int]),
+    'rcgan_bn_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_float, c_int, c_float, c_int, c_float, P, P,
+                             P, P, c_size_t, P]),
+    'rcgan_bn_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_int,
+                             c_int, P, c_size_t, P]),
+    'rcgan_sn_save_floats': (c_size_t, [c_int, c_int]),
+    'rcgan_sn_workspace': (c_size_t, [c_int, c_int]),
+    'rcgan_sn_fwd': (c_int, [P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    'rcgan_sn_bwd': (c_int, [P, P, P, c_int, c_int, P, P, c_int, P, c_size_t, P]),
+    'rcgan_channel_loss': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, P, P, P, P]),
+    'rcgan_sigmoid_ce': (c_int, [P, P, c_long, c_float, P, P, P]),
+    'rcgan_logit_loss': (c_int, [P, c_long, c_int, c_float, P, P, P]),
+    'rcgan_softmax_rows_fwd': (c_int, [P, P, c_int, c_int, P]),
+    'rcgan_softmax_rows_bwd': (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    'rcgan_gather_rows_fwd': (c_int, [P, P, P, c_int, c_int, P]),
+    'rcgan_gather_rows_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'rcgan_adam_tf': (c_int, [P, P, P, P, c_long, c_float, P, c_float, c_float, c_float, c_float, POINTER(c_long),
+                              POINTER(c_long), c_int, P]),
+    'rcgan_zero': (c_int, [P, c_size_t, P]),
+    'rcgan_sampler_table_host': (None, [POINTER(c_double), c_int, POINTER(c_double)]),
+    'rcgan_mt_seed': (c_int, [P, c_uint32, P]),
+    'rcgan_mt_shuffle_perm': (c_int, [P, P, c_int, P]),
+    'rcgan_sample_labels_mnist': (c_int, [P, P, c_int, P, c_int, c_int, P, P, P, P]),
+    'rcgan_sample_renoise_mnist': (c_int, [P, P, c_int, P, P, c_int, P, P, P]),
+    'rcgan_sample_labels_cifar': (c_int, [P, P, c_int, P, c_int, P, P, P]),
+    'rcgan_mt_uniform': (c_int, [P, P, c_long, c_double, c_double, P]),
+    'rcgan_preprocess_cifar': (c_int, [P, P, P, c_int, c_int, P]),
+}
+EXPORTS = sorted(_SIGS)
+
+_lib = None
+
+
+def load():
+    """Load the shared object (raises RcganError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RcganError('%s is missing: build it with `python -m robust_conditional_gan_b200.build` or '
+                             '__graft_entry__.build(); there is no CPU or PyTorch fallback' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)       # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().rcgan_last_error().decode()
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise with the library's message on failure."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RcganError('%s failed (%d): %s' % (name, rc, last_error()))
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,31 @@
+// Error reporting and device probing for the C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rcgan_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#include <atomic>
+static std::atomic<long> g_launches{0};
+void rcgan_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long rcgan_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char* rcgan_last_error(void) { return g_err; }
+extern "C" int rcgan_abi_version(void) { return 1; }
+
+extern "C" int rcgan_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { rcgan_set_error("no CUDA device"); return 0; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { rcgan_set_error("cudaGetDeviceProperties failed"); return 0; }
+  if (prop.major != 10) { rcgan_set_error("device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor); return 0; }
+  return 1;
+}

@@ -1,0 +1,357 @@
+// CUDA-core implicit-GEMM convolution family (fprop / dgrad / wgrad), NHWC x HWIO.
+//
+// This is (a) the fp32 "parity mode" path for every conv / deconv / linear of the
+// reference (tf.nn.conv2d mnist/ops.py:62, conv2d.py:181-187; tf.nn.conv2d_transpose
+// mnist/ops.py:78; tf.matmul ops.py:114-116, linear.py:163-173) and (b) the path for
+// the degenerate layers in bf16 mode (cin=1, cout=1, cout=10 ...: arithmetic intensity
+// < 30 flop/B) that do not belong on the tensor pipe.
+//
+// GEMM view (fp32 accumulate, 64x64x16 or 256x16x16 CTA tile, 256 threads):
+//   fprop: M = n*ho*wo, N = cout, K = kh*kw*cin   A = im2col(x)      B = w[K][cout]
+//   dgrad: M = n*h*w,   N = cin,  K = kh*kw*cout  A = col2im^T(dy)   B = w^T
+//   wgrad: M = kh*kw*cin, N = cout, K = n*ho*wo   A = im2col(x)^T    B = dy     (split-K)
+#include "common.cuh"
+
+namespace {
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+constexpr int BK = 16;
+
+struct ConvP {
+  int n, h, w, cin, ho, wo, cout, kh, kw, stride, pad_t, pad_l, ldx, ldy;
+  int M, N, K;
+  const float* bias;
+  int act;
+  float leak;
+  int accumulate;
+  int klen;  // K range per blockIdx.z (wgrad split-K), multiple of BK
+};
+
+template <int MODE, typename T, typename TO, int BM, int BN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p, const T* __restrict__ act_in,  // x (fprop/wgrad) or dy (dgrad)
+                                                        const float* __restrict__ wt,           // weights (fprop/dgrad)
+                                                        const T* __restrict__ dy_in,            // dy (wgrad)
+                                                        void* __restrict__ out_) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int A_PER_T = BM * BK / 256, B_PER_T = BN * BK / 256 > 0 ? BN * BK / 256 : 1;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * p.klen;
+  const int kend = min(p.K, kbeg + p.klen);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  // ---- per-thread A row bookkeeping
+  // fprop/dgrad: k-fast mapping: k_l = t%16, rows m_l = t/16 + 16*i
+  // wgrad     : m-fast mapping: m_l = idx % BM, k_l = idx / BM
+  int rowbase[A_PER_T];  // element offset of (nb, 0, 0, 0) for fprop/dgrad rows
+  int rowy[A_PER_T], rowx[A_PER_T];
+  bool rowok[A_PER_T];
+  if (MODE != MODE_WGRAD) {
+#pragma unroll
+    for (int i = 0; i < A_PER_T; i++) {
+      int m = m0 + (t >> 4) + 16 * i;
+      rowok[i] = m < p.M;
+      int mm = rowok[i] ? m : 0;
+      if (MODE == MODE_FPROP) {
+        int ox = mm % p.wo, r = mm / p.wo, oy = r % p.ho, nb = r / p.ho;
+        rowbase[i] = nb * p.h * p.w;
+        rowy[i] = oy * p.stride - p.pad_t;
+        rowx[i] = ox * p.stride - p.pad_l;
+      } else {
+        int ix = mm % p.w, r = mm / p.w, iy = r % p.h, nb = r / p.h;
+        rowbase[i] = nb * p.ho * p.wo;
+        rowy[i] = iy + p.pad_t;
+        rowx[i] = ix + p.pad_l;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < A_PER_T; i++) {
+      int idx = t + 256 * i;
+      int m = m0 + idx % BM;
+      rowok[i] = m < p.M;
+      int mm = rowok[i] ? m : 0;
+      int ci = mm % p.cin, tap = mm / p.cin;
+      rowbase[i] = ci;
+      rowy[i] = tap / p.kw - p.pad_t;  // ky - pad_t
+      rowx[i] = tap % p.kw - p.pad_l;
+    }
+  }
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ------------------------------------------------ A tile
+    if (MODE == MODE_FPROP) {
+      int k = k0 + (t & 15);
+      bool kok = k < kend;
+      int kk = kok ? k : 0;
+      int ci = kk % p.cin, tap = kk / p.cin;
+      int ky = tap / p.kw, kx = tap % p.kw;
+#pragma unroll
+      for (int i = 0; i < A_PER_T; i++) {
+        int iy = rowy[i] + ky, ix = rowx[i] + kx;
+        float v = 0.f;
+        if (kok && rowok[i] && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
+          v = to_f(act_in[(size_t)(rowbase[i] + iy * p.w + ix) * p.ldx + ci]);
+        As[t & 15][(t >> 4) + 16 * i] = v;
+      }
+    } else if (MODE == MODE_DGRAD) {
+      int k = k0 + (t & 15);
+      bool kok = k < kend;
+      int kk = kok ? k : 0;
+      int co = kk % p.cout, tap = kk / p.cout;
+      int ky = tap / p.kw, kx = tap % p.kw;
+#pragma unroll
+      for (int i = 0; i < A_PER_T; i++) {
+        int ty_ = rowy[i] - ky, tx_ = rowx[i] - kx;
+        float v = 0.f;
+        if (kok && rowok[i] && ty_ >= 0 && tx_ >= 0) {
+          int oy = ty_ / p.stride, ox = tx_ / p.stride;
+          if (oy * p.stride == ty_ && ox * p.stride == tx_ && oy < p.ho && ox < p.wo)
+            v = to_f(act_in[(size_t)(rowbase[i] + oy * p.wo + ox) * p.ldy + co]);
+        }
+        As[t & 15][(t >> 4) + 16 * i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER_T; i++) {
+        int idx = t + 256 * i;
+        int k = k0 + idx / BM;
+        float v = 0.f;
+        if (k < kend && rowok[i]) {
+          int ox = k % p.wo, r = k / p.wo, oy = r % p.ho, nb = r / p.ho;
+          int iy = oy * p.stride + rowy[i], ix = ox * p.stride + rowx[i];
+          if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
+            v = to_f(act_in[(size_t)((nb * p.h + iy) * p.w + ix) * p.ldx + rowbase[i]]);
+        }
+        As[idx / BM][idx % BM] = v;
+      }
+    }
+    // ------------------------------------------------ B tile
+    if (MODE == MODE_FPROP) {
+#pragma unroll
+      for (int i = 0; i < B_PER_T; i++) {
+        int idx = t + 256 * i;
+        if (idx < BN * BK) {
+          int nl = idx % BN, kl = idx / BN;
+          int k = k0 + kl, nn = n0 + nl;
+          Bs[kl][nl] = (k < kend && nn < p.N) ? wt[(size_t)k * p.cout + nn] : 0.f;
+        }
+      }
+    } else if (MODE == MODE_DGRAD) {
+#pragma unroll
+      for (int i = 0; i < B_PER_T; i++) {
+        int idx = t + 256 * i;
+        if (idx < BN * BK) {
+          int kl = idx % BK, nl = idx / BK;
+          int k = k0 + kl, ci = n0 + nl;
+          float v = 0.f;
+          if (k < kend && ci < p.N) {
+            int co = k % p.cout, tap = k / p.cout;
+            v = wt[((size_t)tap * p.cin + ci) * p.cout + co];
+          }
+          Bs[kl][nl] = v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < B_PER_T; i++) {
+        int idx = t + 256 * i;
+        if (idx < BN * BK) {
+          int nl = idx % BN, kl = idx / BN;
+          int k = k0 + kl, nn = n0 + nl;
+          Bs[kl][nl] = (k < kend && nn < p.N) ? to_f(dy_in[(size_t)k * p.ldy + nn]) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; j++) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------ epilogue
+  if (MODE == MODE_WGRAD) {
+    float* out = reinterpret_cast<float*>(out_) + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+      int m = m0 + ty * TM + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; j++) {
+        int nn = n0 + tx * TN + j;
+        if (nn < p.N) out[(size_t)m * p.N + nn] = acc[i][j];
+      }
+    }
+  } else {
+    TO* out = reinterpret_cast<TO*>(out_);
+    const int ld = MODE == MODE_FPROP ? p.ldy : p.ldx;
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+      int m = m0 + ty * TM + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; j++) {
+        int nn = n0 + tx * TN + j;
+        if (nn >= p.N) continue;
+        float v = acc[i][j];
+        if (p.bias) v += p.bias[nn];
+        v = act_fwd(v, p.act, p.leak);
+        size_t o = (size_t)m * ld + nn;
+        if (p.accumulate) v += to_f(out[o]);
+        out[o] = from_f<TO>(v);
+      }
+    }
+  }
+}
+
+// dw (=|+=) sum over splits
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long mn, int nsplit, int accumulate) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mn) return;
+  float s = 0.f;
+  for (int z = 0; z < nsplit; z++) s += ws[(size_t)z * mn + i];
+  dw[i] = accumulate ? dw[i] + s : s;
+}
+
+int check_desc(const rcgan_conv_desc* d, const char* who) {
+  RCGAN_CHECK_ARG(d, "%s: null desc", who);
+  RCGAN_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0 && d->ho > 0 && d->wo > 0,
+                  "%s: non-positive dims", who);
+  RCGAN_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad_t >= 0 && d->pad_l >= 0, "%s: bad filter", who);
+  RCGAN_CHECK_ARG(d->ldx >= d->cin && d->ldy >= d->cout, "%s: ld smaller than channels", who);
+  RCGAN_CHECK_ARG(d->dtype == RCGAN_F32 || d->dtype == RCGAN_BF16, "%s: bad dtype %d", who, d->dtype);
+  RCGAN_CHECK_ARG((long)d->n * d->h * d->w * d->ldx < 2147483647L && (long)d->n * d->ho * d->wo * d->ldy < 2147483647L,
+                  "%s: tensor exceeds 2^31 elements", who);
+  return 0;
+}
+
+ConvP make_p(const rcgan_conv_desc* d) {
+  ConvP p;
+  p.n = d->n; p.h = d->h; p.w = d->w; p.cin = d->cin; p.ho = d->ho; p.wo = d->wo; p.cout = d->cout;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.ldx = d->ldx; p.ldy = d->ldy;
+  p.bias = nullptr; p.act = 0; p.leak = 0.f; p.accumulate = 0; p.klen = 0;
+  p.M = p.N = p.K = 0;
+  return p;
+}
+
+int wgrad_splits(const ConvP& p) {
+  long tiles = (long)ceil_div(p.M, 64) * ceil_div(p.N, 64);
+  long want = (2L * RCGAN_NUM_SMS + tiles - 1) / tiles;
+  long maxs = (p.K + 8 * BK - 1) / (8 * BK);  // at least 128 k per split
+  long s = want < 1 ? 1 : want;
+  if (s > maxs) s = maxs;
+  if (s > 512) s = 512;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+template <int MODE, typename T, typename TO>
+void launch(const ConvP& p, const void* a, const float* w, const void* dy, void* out, int nz, cudaStream_t st) {
+  if (p.N <= 16 && MODE != MODE_WGRAD) {
+    dim3 grid(ceil_div(p.M, 256), ceil_div(p.N, 16), nz);
+    conv_simt_kernel<MODE, T, TO, 256, 16><<<grid, 256, 0, st>>>(p, (const T*)a, w, (const T*)dy, out);
+  } else {
+    dim3 grid(ceil_div(p.M, 64), ceil_div(p.N, 64), nz);
+    conv_simt_kernel<MODE, T, TO, 64, 64><<<grid, 256, 0, st>>>(p, (const T*)a, w, (const T*)dy, out);
+  }
+}
+
+// operand dtype x output dtype: (f32,f32) (bf16,bf16) (bf16,f32 -- tensors that feed a batch norm stay fp32)
+template <int MODE>
+int launch_io(const ConvP& p, int dtype, int out_dtype, const void* a, const float* w, void* out, cudaStream_t st) {
+  if (dtype == RCGAN_F32 && out_dtype == RCGAN_F32) launch<MODE, float, float>(p, a, w, nullptr, out, 1, st);
+  else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_BF16) launch<MODE, bf16, bf16>(p, a, w, nullptr, out, 1, st);
+  else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_F32) launch<MODE, bf16, float>(p, a, w, nullptr, out, 1, st);
+  else { rcgan_set_error("conv: unsupported dtype pair (%d -> %d)", dtype, out_dtype); return RCGAN_EUNSUPPORTED; }
+  return 0;
+}
+
+}  // namespace
+
+// Implemented in conv_tc.cu (tcgen05 path); return 1 when they handled the call.
+int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
+                   int act, float leak, cudaStream_t st, int* handled);
+int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
+                   int act, float leak, int accumulate, cudaStream_t st, int* handled);
+
+extern "C" int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
+                                  const float* bias, void* y, int out_dtype, int act, float leak, void* stream) {
+  if (int e = check_desc(d, "conv2d_fprop")) return e;
+  if (wpack) {
+    int handled = 0;
+    int e = rcgan_tc_fprop(d, x, wpack, bias, y, out_dtype, act, leak, as_stream(stream), &handled);
+    if (e || handled) return e;
+  }
+  RCGAN_CHECK_ARG(w, "conv2d_fprop: null fp32 weights");
+  ConvP p = make_p(d);
+  p.M = d->n * d->ho * d->wo; p.N = d->cout; p.K = d->kh * d->kw * d->cin;
+  p.bias = bias; p.act = act; p.leak = leak; p.klen = ((p.K + BK - 1) / BK) * BK;
+  if (int e = launch_io<MODE_FPROP>(p, d->dtype, out_dtype, x, w, y, as_stream(stream))) return e;
+  RCGAN_LAUNCH_CHECK("conv2d_fprop");
+  return 0;
+}
+
+extern "C" int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, const float* w, const void* wpack,
+                                  const float* bias, void* dx, int out_dtype, int act, float leak, int accumulate,
+                                  void* stream) {
+  if (int e = check_desc(d, "conv2d_dgrad")) return e;
+  if (wpack) {
+    int handled = 0;
+    int e = rcgan_tc_dgrad(d, dy, wpack, bias, dx, out_dtype, act, leak, accumulate, as_stream(stream), &handled);
+    if (e || handled) return e;
+  }
+  RCGAN_CHECK_ARG(w, "conv2d_dgrad: null fp32 weights");
+  ConvP p = make_p(d);
+  p.M = d->n * d->h * d->w; p.N = d->cin; p.K = d->kh * d->kw * d->cout;
+  p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate; p.klen = ((p.K + BK - 1) / BK) * BK;
+  if (int e = launch_io<MODE_DGRAD>(p, d->dtype, out_dtype, dy, w, dx, as_stream(stream))) return e;
+  RCGAN_LAUNCH_CHECK("conv2d_dgrad");
+  return 0;
+}
+
+extern "C" size_t rcgan_conv2d_wgrad_workspace(const rcgan_conv_desc* d) {
+  if (!d) return 0;
+  ConvP p = make_p(d);
+  p.M = d->kh * d->kw * d->cin; p.N = d->cout; p.K = d->n * d->ho * d->wo;
+  return (size_t)wgrad_splits(p) * p.M * p.N * sizeof(float);
+}
+
+extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  if (int e = check_desc(d, "conv2d_wgrad")) return e;
+  ConvP p = make_p(d);
+  p.M = d->kh * d->kw * d->cin; p.N = d->cout; p.K = d->n * d->ho * d->wo;
+  int ns = wgrad_splits(p);
+  RCGAN_CHECK_ARG(ws && ws_bytes >= (size_t)ns * p.M * p.N * sizeof(float), "conv2d_wgrad: workspace too small");
+  int klen = (p.K + ns - 1) / ns;
+  klen = ((klen + BK - 1) / BK) * BK;
+  ns = (p.K + klen - 1) / klen;
+  p.klen = klen;
+  if (d->dtype == RCGAN_F32) launch<MODE_WGRAD, float, float>(p, x, nullptr, dy, ws, ns, as_stream(stream));
+  else launch<MODE_WGRAD, bf16, float>(p, x, nullptr, dy, ws, ns, as_stream(stream));
+  RCGAN_LAUNCH_CHECK("conv2d_wgrad");
+  long mn = (long)p.M * p.N;
+  splitk_reduce_kernel<<<ceil_div(mn, 256), 256, 0, as_stream(stream)>>>((const float*)ws, dw, mn, ns, accumulate);
+  RCGAN_LAUNCH_CHECK("conv2d_wgrad_reduce");
+  return 0;
+}

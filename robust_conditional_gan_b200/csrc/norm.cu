@@ -1,0 +1,360 @@
+// Batch norm (tf.contrib.layers.batch_norm, mnist/ops.py:30-44) and conditional batch norm
+// (cond_batchnorm, cifar10/common/ops/normalization.py:27-59) with the following activation fused.
+// x is [rows = samples*hw, c] channels-last.  HBM-bound; ideal traffic fwd = 2 reads + 1 write of x
+// (stats pass + apply pass; the stats pass of a tensor that fits the 126 MB L2 is served from L2),
+// bwd = reads of dy, x, y for the reduction + dy, x, y again for dx.
+//
+// Types: x is TX, y/dy/dx are TY.  (f32,f32) is parity mode, (bf16,bf16) plain bf16, and (f32,bf16)
+// the bf16 training layout: the tensor feeding a norm is kept in fp32 because the norm's backward
+// dx = istd*(scale*g - mean(scale*g) - xhat*mean(scale*g*xhat)) cancels catastrophically and amplifies
+// the bf16 rounding of x ~50x (measured on the reference's discriminator at initialisation).
+//
+//   stats   : per row-chunk shifted sums (pivot = first row of the chunk) -> (mean, M2) partials,
+//             merged with Chan's formula in the finalize kernel (no E[x^2]-E[x]^2 cancellation)
+//   apply   : y = act((x-mean)*invstd*scale[label] + offset[label]), 4-element vectors
+//   bwd     : g = dy*act'(y); partial sums of g and g*xhat per chunk; finalize folds them into
+//             dscale/doffset[label] and the two per-channel projections; dx elementwise.
+#include "common.cuh"
+
+namespace {
+
+template <typename T, int V> __device__ __forceinline__ void load_vec(const T* p, float* out) {
+  if (V == 1) { out[0] = to_f(*p); return; }
+  if (sizeof(T) == 4) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+  }
+}
+template <typename T, int V> __device__ __forceinline__ void store_vec(T* p, const float* in) {
+  if (V == 1) { *p = from_f<T>(in[0]); return; }
+  if (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+  } else {
+    uint2 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+    h[0] = __floats2bfloat162_rn(in[0], in[1]);
+    h[1] = __floats2bfloat162_rn(in[2], in[3]);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+}
+
+struct Geo {
+  int rows, c, hw;
+  int V;           // channels per thread-vector (4 or 1)
+  int cg;          // channel vectors = c / V
+  int LC, LR;      // thread layout: LC channel lanes x LR row lanes = 256
+  int gx;          // ceil(cg / LC)
+  int chunk_rows, nchunk;
+};
+
+Geo make_geo(int samples, int hw, int c, bool per_sample) {
+  Geo g;
+  g.rows = samples * hw; g.c = c; g.hw = hw;
+  g.V = (c % 4 == 0) ? 4 : 1;
+  g.cg = c / g.V;
+  int lc = 1;
+  while (lc < 32 && lc * 2 <= g.cg) lc *= 2;
+  g.LC = lc; g.LR = 256 / lc;
+  g.gx = (g.cg + lc - 1) / lc;
+  long want = (2L * RCGAN_NUM_SMS + g.gx - 1) / g.gx;  // chunks wanted for ~2 waves
+  if (per_sample) {
+    // chunks never straddle a sample: chunk_rows = hw / 2^j
+    int cr = hw;
+    while ((long)samples * (hw / cr) < want && cr % 2 == 0 && cr / 2 >= 16) cr /= 2;
+    g.chunk_rows = cr;
+  } else {
+    long cr = (g.rows + want - 1) / want;
+    if (cr < 32) cr = 32;
+    if (cr > g.rows) cr = g.rows;
+    g.chunk_rows = (int)cr;
+  }
+  g.nchunk = (g.rows + g.chunk_rows - 1) / g.chunk_rows;
+  return g;
+}
+
+// ws layout (floats): [0, nchunk*c) = P1 ; [nchunk*c, 2*nchunk*c) = P2 ; then 2*c floats (A, B) for bwd
+template <typename TX, int V>
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const TX* __restrict__ x, Geo g, float* __restrict__ ws) {
+  extern __shared__ float sh[];  // [LR][LC*V] x 2
+  const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
+  const int cv = blockIdx.x * g.LC + lc;
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * g.chunk_rows, r1 = min(g.rows, r0 + g.chunk_rows);
+  float piv[V], s[V], ss[V];
+#pragma unroll
+  for (int i = 0; i < V; i++) { s[i] = 0.f; ss[i] = 0.f; piv[i] = 0.f; }
+  if (cv < g.cg) {
+    const TX* base = x + (size_t)cv * V;
+    load_vec<TX, V>(base + (size_t)r0 * g.c, piv);
+    for (int r = r0 + lr; r < r1; r += g.LR) {
+      float v[V];
+      load_vec<TX, V>(base + (size_t)r * g.c, v);
+#pragma unroll
+      for (int i = 0; i < V; i++) { float d = v[i] - piv[i]; s[i] += d; ss[i] = fmaf(d, d, ss[i]); }
+    }
+  }
+  float* S = sh;
+  float* SS = sh + 256 * V;
+#pragma unroll
+  for (int i = 0; i < V; i++) { S[(lr * g.LC + lc) * V + i] = s[i]; SS[(lr * g.LC + lc) * V + i] = ss[i]; }
+  __syncthreads();
+  if (lr == 0 && cv < g.cg) {
+    float n = (float)(r1 - r0);
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < g.LR; k++) { a += S[(k * g.LC + lc) * V + i]; b += SS[(k * g.LC + lc) * V + i]; }
+      int ch = cv * V + i;
+      ws[(size_t)chunk * g.c + ch] = piv[i] + a / n;                          // chunk mean
+      ws[(size_t)(g.nchunk + chunk) * g.c + ch] = fmaxf(b - a * a / n, 0.f);  // chunk M2
+    }
+  }
+}
+
+__global__ void bn_stats_finalize_kernel(Geo g, const float* __restrict__ ws, float eps, float decay, float* mm, float* mv,
+                                         float* __restrict__ save) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= g.c) return;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int k = 0; k < g.nchunk; k++) {
+    int r0 = k * g.chunk_rows;
+    float nb = (float)(min(g.rows, r0 + g.chunk_rows) - r0);
+    float mb = ws[(size_t)k * g.c + ch], m2b = ws[(size_t)(g.nchunk + k) * g.c + ch];
+    float nt = n + nb, delta = mb - mean;
+    mean += delta * (nb / nt);
+    m2 += m2b + delta * delta * (n * nb / nt);
+    n = nt;
+  }
+  float var = m2 / n;
+  save[ch] = mean;
+  save[g.c + ch] = rsqrtf(var + eps);
+  if (mm) {
+    float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
+    mm[ch] = decay * mm[ch] + (1.f - decay) * mean;
+    mv[ch] = decay * mv[ch] + (1.f - decay) * unbiased;
+  }
+}
+
+__global__ void bn_infer_stats_kernel(int c, const float* __restrict__ mm, const float* __restrict__ mv, float eps,
+                                      float* __restrict__ save) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  save[ch] = mm[ch];
+  save[c + ch] = rsqrtf(mv[ch] + eps);
+}
+
+template <typename TX, typename TY, int V>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, Geo g,
+                                                       const float* __restrict__ scale, const float* __restrict__ offset,
+                                                       const int* __restrict__ labels, const float* __restrict__ save,
+                                                       int act, float leak) {
+  long total = (long)g.rows * g.cg;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / g.cg;
+    int ch = (int)(i - r * g.cg) * V;
+    int lab = labels ? labels[r / g.hw] : 0;
+    float v[V], o[V];
+    load_vec<TX, V>(x + r * g.c + ch, v);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float xh = (v[k] - save[ch + k]) * save[g.c + ch + k];
+      o[k] = act_fwd(fmaf(xh, scale[(size_t)lab * g.c + ch + k], offset[(size_t)lab * g.c + ch + k]), act, leak);
+    }
+    store_vec<TY, V>(y + r * g.c + ch, o);
+  }
+}
+
+template <typename TX, typename TY, int V>
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
+                                                             const TY* __restrict__ y, Geo g, const float* __restrict__ save,
+                                                             int act, float leak, float* __restrict__ ws) {
+  extern __shared__ float sh[];
+  const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
+  const int cv = blockIdx.x * g.LC + lc;
+  const int chunk = blockIdx.y;
+  const int r0 = chunk * g.chunk_rows, r1 = min(g.rows, r0 + g.chunk_rows);
+  float s1[V], s2[V], mean[V], istd[V];
+#pragma unroll
+  for (int i = 0; i < V; i++) { s1[i] = 0.f; s2[i] = 0.f; mean[i] = 0.f; istd[i] = 0.f; }
+  if (cv < g.cg) {
+#pragma unroll
+    for (int i = 0; i < V; i++) { mean[i] = save[cv * V + i]; istd[i] = save[g.c + cv * V + i]; }
+    for (int r = r0 + lr; r < r1; r += g.LR) {
+      float vd[V], vx[V], vy[V];
+      size_t o = (size_t)r * g.c + (size_t)cv * V;
+      load_vec<TY, V>(dy + o, vd);
+      load_vec<TX, V>(x + o, vx);
+      if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + o, vy);
+#pragma unroll
+      for (int i = 0; i < V; i++) {
+        float gg = vd[i];
+        if (act != RCGAN_ACT_NONE) gg *= act_bwd_from_y(vy[i], act, leak);
+        s1[i] += gg;
+        s2[i] = fmaf(gg, (vx[i] - mean[i]) * istd[i], s2[i]);
+      }
+    }
+  }
+  float* S = sh;
+  float* SS = sh + 256 * V;
+#pragma unroll
+  for (int i = 0; i < V; i++) { S[(lr * g.LC + lc) * V + i] = s1[i]; SS[(lr * g.LC + lc) * V + i] = s2[i]; }
+  __syncthreads();
+  if (lr == 0 && cv < g.cg) {
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < g.LR; k++) { a += S[(k * g.LC + lc) * V + i]; b += SS[(k * g.LC + lc) * V + i]; }
+      int ch = cv * V + i;
+      ws[(size_t)chunk * g.c + ch] = a;
+      ws[(size_t)(g.nchunk + chunk) * g.c + ch] = b;
+    }
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(Geo g, float* __restrict__ ws, const float* __restrict__ scale,
+                                       const int* __restrict__ labels, int n_labels, float* __restrict__ dscale,
+                                       float* __restrict__ doffset, int accumulate_param) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= g.c) return;
+  if (!accumulate_param)
+    for (int l = 0; l < n_labels; l++) { dscale[(size_t)l * g.c + ch] = 0.f; doffset[(size_t)l * g.c + ch] = 0.f; }
+  float A = 0.f, B = 0.f;
+  for (int k = 0; k < g.nchunk; k++) {
+    int lab = labels ? labels[((long)k * g.chunk_rows) / g.hw] : 0;
+    float p1 = ws[(size_t)k * g.c + ch], p2 = ws[(size_t)(g.nchunk + k) * g.c + ch];
+    float sc = scale[(size_t)lab * g.c + ch];
+    A = fmaf(sc, p1, A);
+    B = fmaf(sc, p2, B);
+    doffset[(size_t)lab * g.c + ch] += p1;
+    dscale[(size_t)lab * g.c + ch] += p2;
+  }
+  float inv = 1.f / (float)g.rows;
+  float* AB = ws + (size_t)2 * g.nchunk * g.c;
+  AB[ch] = A * inv;
+  AB[g.c + ch] = B * inv;
+}
+
+template <typename TX, typename TY, int V>
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
+                                                        const TY* __restrict__ y, TY* __restrict__ dx, Geo g,
+                                                        const float* __restrict__ scale, const int* __restrict__ labels,
+                                                        const float* __restrict__ save, const float* __restrict__ AB,
+                                                        int act, float leak, int accumulate) {
+  long total = (long)g.rows * g.cg;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / g.cg;
+    int ch = (int)(i - r * g.cg) * V;
+    int lab = labels ? labels[r / g.hw] : 0;
+    float vd[V], vx[V], vy[V], o[V];
+    size_t off = (size_t)r * g.c + ch;
+    load_vec<TY, V>(dy + off, vd);
+    load_vec<TX, V>(x + off, vx);
+    if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + off, vy);
+    if (accumulate) load_vec<TY, V>(dx + off, o);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float gg = vd[k];
+      if (act != RCGAN_ACT_NONE) gg *= act_bwd_from_y(vy[k], act, leak);
+      float istd = save[g.c + ch + k];
+      float xh = (vx[k] - save[ch + k]) * istd;
+      float v = istd * (scale[(size_t)lab * g.c + ch + k] * gg - AB[ch + k] - xh * AB[g.c + ch + k]);
+      o[k] = accumulate ? o[k] + v : v;
+    }
+    store_vec<TY, V>(dx + off, o);
+  }
+}
+
+inline int ew_grid(long work) {
+  long gsz = (work + 255) / 256;
+  long cap = (long)RCGAN_NUM_SMS * 16;
+  return (int)(gsz < 1 ? 1 : (gsz > cap ? cap : gsz));
+}
+
+inline int check_types(int xd, int yd, const char* who) {
+  bool ok = (xd == RCGAN_F32 && yd == RCGAN_F32) || (xd == RCGAN_BF16 && yd == RCGAN_BF16) ||
+            (xd == RCGAN_F32 && yd == RCGAN_BF16);
+  if (!ok) { rcgan_set_error("%s: unsupported dtype pair x=%d y=%d", who, xd, yd); return RCGAN_EUNSUPPORTED; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
+  Geo a = make_geo(samples, hw, c, false), b = make_geo(samples, hw, c, true);
+  int nc = a.nchunk > b.nchunk ? a.nchunk : b.nchunk;
+  return ((size_t)2 * nc * c + 2 * c) * sizeof(float);
+}
+
+// expands `...` with TX, TY, VV bound for the (xdtype, ydtype, V) triple
+#define BN_DISPATCH(xd, yd, V, ...)                                                                      \
+  if ((xd) == RCGAN_F32 && (yd) == RCGAN_F32) {                                                          \
+    typedef float TX; typedef float TY;                                                                  \
+    if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
+  } else if ((xd) == RCGAN_BF16) {                                                                       \
+    typedef bf16 TX; typedef bf16 TY;                                                                    \
+    if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
+  } else {                                                                                               \
+    typedef float TX; typedef bf16 TY;                                                                   \
+    if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
+  }
+
+extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
+                            const float* offset, const int* labels, float eps, int act, float leak, int train,
+                            float decay, float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes,
+                            void* stream) {
+  RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "bn_fwd: bad shape");
+  if (int e = check_types(xdtype, ydtype, "bn_fwd")) return e;
+  RCGAN_CHECK_ARG(x && y && scale && offset && save, "bn_fwd: null pointer");
+  RCGAN_CHECK_ARG((long)samples * hw * c < 2147483647L, "bn_fwd: too large");
+  cudaStream_t st = as_stream(stream);
+  Geo g = make_geo(samples, hw, c, labels != nullptr);
+  if (train) {
+    RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_fwd: workspace too small");
+    dim3 grid(g.gx, g.nchunk);
+    size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
+    BN_DISPATCH(xdtype, ydtype, g.V, bn_stats_partial_kernel<TX, VV><<<grid, 256, shb, st>>>((const TX*)x, g, (float*)ws));
+    RCGAN_LAUNCH_CHECK("bn_stats_partial");
+    bn_stats_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(g, (const float*)ws, eps, decay, moving_mean, moving_var, save);
+    RCGAN_LAUNCH_CHECK("bn_stats_finalize");
+  } else {
+    RCGAN_CHECK_ARG(moving_mean && moving_var, "bn_fwd: inference needs moving statistics");
+    bn_infer_stats_kernel<<<ceil_div(c, 128), 128, 0, st>>>(c, moving_mean, moving_var, eps, save);
+    RCGAN_LAUNCH_CHECK("bn_infer_stats");
+  }
+  BN_DISPATCH(xdtype, ydtype, g.V, bn_apply_kernel<TX, TY, VV><<<ew_grid((long)g.rows * g.cg), 256, 0, st>>>(
+                                       (const TX*)x, (TY*)y, g, scale, offset, labels, save, act, leak));
+  RCGAN_LAUNCH_CHECK("bn_apply");
+  return 0;
+}
+
+extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
+                            int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
+                            float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
+                            size_t ws_bytes, void* stream) {
+  RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0 && n_labels > 0, "bn_bwd: bad shape");
+  if (int e = check_types(xdtype, ydtype, "bn_bwd")) return e;
+  RCGAN_CHECK_ARG(dy && x && dx && scale && save && dscale && doffset, "bn_bwd: null pointer");
+  RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y, "bn_bwd: activation needs y");
+  cudaStream_t st = as_stream(stream);
+  Geo g = make_geo(samples, hw, c, labels != nullptr);
+  RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
+  dim3 grid(g.gx, g.nchunk);
+  size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
+  BN_DISPATCH(xdtype, ydtype, g.V, bn_bwd_partial_kernel<TX, TY, VV><<<grid, 256, shb, st>>>(
+                                       (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws));
+  RCGAN_LAUNCH_CHECK("bn_bwd_partial");
+  bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(g, (float*)ws, scale, labels, n_labels, dscale, doffset,
+                                                            accumulate_param);
+  RCGAN_LAUNCH_CHECK("bn_bwd_finalize");
+  const float* AB = (const float*)ws + (size_t)2 * g.nchunk * c;
+  BN_DISPATCH(xdtype, ydtype, g.V, bn_bwd_dx_kernel<TX, TY, VV><<<ew_grid((long)g.rows * g.cg), 256, 0, st>>>(
+                                       (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, g, scale, labels, save, AB, act,
+                                       leak, accumulate_dx));
+  RCGAN_LAUNCH_CHECK("bn_bwd_dx");
+  return 0;
+}

@@ -1,0 +1,620 @@
+"""Op classes of the static program: each maps one reference op (cited per class) onto
+forward/backward launches of librcgan_b200.so.  See graph.py for the planning protocol."""
+import torch
+
+from . import _C
+from ._C import ConvDesc, call, stream_ptr
+from .graph import Op, Tensor, cur, needs, round_up, same_pad
+
+ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
+       'tanh': _C.ACT_TANH}
+
+
+def dp(t):
+    """device pointer of a graph tensor's data (None -> NULL)"""
+    return None if t is None else t.data.data_ptr()
+
+
+def gp(t):
+    return None if t is None or t.grad is None else t.grad.data_ptr()
+
+
+def spatial(t):
+    """(n, h, w) of a 2-D [n,c] or 4-D [n,h,w,c] tensor"""
+    if len(t.shape) == 2:
+        return t.shape[0], 1, 1
+    assert len(t.shape) == 4, t.shape
+    return t.shape[0], t.shape[1], t.shape[2]
+
+
+class ConvOp(Op):
+    """y = act(conv2d_SAME(x, w, stride) + b).  tf.nn.conv2d + bias_add (mnist/ops.py:53-67;
+    cifar10/common/ops/conv2d.py:181-216); with a 2-D x it is tf.matmul + bias
+    (mnist/ops.py:97-116; cifar10/common/ops/linear.py:161-180).  w: [kh,kw,cin,cout] or [cin,cout]."""
+
+    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False):
+        """pre_norm: the output feeds a batch norm -> stored in fp32 even in bf16 mode (gradient stays bf16)."""
+        prog = cur()
+        n, h, wd = spatial(x)
+        if len(w.shape) == 2:
+            kh = kw = 1
+            cin, cout = w.shape
+        else:
+            kh, kw, cin, cout = w.shape
+        assert cin == x.c, 'conv: weight cin %d != input channels %d' % (cin, x.c)
+        ho, pt = same_pad(h, kh, stride)
+        wo, pl = same_pad(wd, kw, stride)
+        self.x, self.w, self.b = x, w, b
+        self.act, self.leak = ACT[act], leak
+        oshape = (n, cout) if len(x.shape) == 2 else (n, ho, wo, cout)
+        assert not (pre_norm and self.act != _C.ACT_NONE)
+        self.y = prog.new(oshape, _C.F32 if pre_norm else x.dtype, grad_dtype=x.dtype)
+        self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
+        self.inputs, self.outputs = (x, w, b), (self.y,)
+        prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        nx, nw, nb = self.need
+        self.acc_x = self.claim(self.x) if nx else 0
+        self.acc_w = self.claim(self.w) if nw else 0
+        self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
+
+    def forward(self, prog):
+        call('rcgan_conv2d_fprop', self.desc, dp(self.x), dp(self.w), None, dp(self.b), dp(self.y), self.y.dtype, self.act,
+             self.leak, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y):
+            return
+        nx, nw, nb = self.need
+        st = stream_ptr()
+        y, dy = self.y, gp(self.y)
+        if self.act != _C.ACT_NONE:
+            call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        if nx:
+            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None, None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0,
+                 self.acc_x, st)
+        if nw:
+            call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+        if nb and self.b is not None:
+            call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
+
+
+class DeconvOp(Op):
+    """y = act(conv2d_transpose_SAME(x, w, stride) + b), w: [kh,kw,cout,cin] (mnist/ops.py:69-92).
+    Forward = the dgrad of the conv (cin_conv = cout, cout_conv = cin) whose input is y."""
+
+    def __init__(self, x, w, b, out_hw, stride=2, act=None, leak=0.2, pre_norm=False):
+        prog = cur()
+        n, h, wd = spatial(x)
+        kh, kw, cout, cin = w.shape
+        assert cin == x.c
+        oh, ow = out_hw
+        ho, pt = same_pad(oh, kh, stride)
+        wo, pl = same_pad(ow, kw, stride)
+        assert (ho, wo) == (h, wd), 'deconv2d: output_shape inconsistent with SAME/stride'
+        self.x, self.w, self.b = x, w, b
+        self.act, self.leak = ACT[act], leak
+        assert not (pre_norm and self.act != _C.ACT_NONE)
+        self.y = prog.new((n, oh, ow, cout), _C.F32 if pre_norm else x.dtype, grad_dtype=x.dtype)
+        # the conv being transposed: input = y [n,oh,ow,cout], output = x [n,h,w,cin]
+        self.desc = ConvDesc(n, oh, ow, cout, h, wd, cin, kh, kw, stride, pt, pl, self.y.ld, x.ld, x.dtype)
+        self.inputs, self.outputs = (x, w, b), (self.y,)
+        prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        nx, nw, nb = self.need
+        self.acc_x = self.claim(self.x) if nx else 0
+        assert self.acc_x == 0, 'deconv input gradient must have a single writer'
+        self.acc_w = self.claim(self.w) if nw else 0
+        self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
+
+    def forward(self, prog):
+        call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), None, dp(self.b), dp(self.y), self.y.dtype, self.act,
+             self.leak, 0, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y):
+            return
+        nx, nw, nb = self.need
+        st = stream_ptr()
+        y, dy = self.y, gp(self.y)
+        if self.act != _C.ACT_NONE:
+            call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        if nx:
+            call('rcgan_conv2d_fprop', self.desc, dy, dp(self.w), None, None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, st)
+        if nw:
+            call('rcgan_conv2d_wgrad', self.desc, dy, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+        if nb and self.b is not None:
+            call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
+
+
+class BatchNormOp(Op):
+    """y = act(BN(x)).  labels None: tf.contrib.layers.batch_norm (mnist/ops.py:30-44), scale/offset [c];
+    labels int32 [n]: cond_batchnorm (cifar10/common/ops/normalization.py:27-59), tables [n_labels,c]."""
+
+    def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2):
+        prog = cur()
+        n, h, w = spatial(x)
+        self.x, self.scale, self.offset, self.labels = x, scale, offset, labels
+        self.samples, self.hw, self.c = n, h * w, x.c
+        assert x.ld == x.c
+        self.n_labels = scale.numel() // x.c
+        self.moving, self.train, self.eps, self.decay = moving, train, eps, decay
+        self.act, self.leak = ACT[act], leak
+        assert x.grad_dtype == prog.act_dtype or x.dtype == x.grad_dtype
+        self.y = prog.new(x.shape, x.grad_dtype)
+        self.save = torch.zeros(2 * x.c, dtype=torch.float32, device=prog.device)
+        self.inputs, self.outputs = (x, scale, offset), (self.y,)
+        self.ws_bytes = _C.load().rcgan_bn_workspace(self.samples, self.hw, self.c)
+        prog.ws.request(self.ws_bytes)
+        self.dummy = None
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        nx, ns, no = self.need
+        self.acc_x = self.claim(self.x) if nx else 0
+        if ns or no:
+            self.claim(self.scale), self.claim(self.offset)
+        elif needs(self.y):
+            self.dummy = torch.zeros(2 * self.n_labels * self.c, dtype=torch.float32, device=prog.device)
+
+    def forward(self, prog):
+        mm = mv = None
+        if self.moving is not None:
+            mm, mv = dp(self.moving[0]), dp(self.moving[1])
+        call('rcgan_bn_fwd', dp(self.x), dp(self.y), self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale),
+             dp(self.offset), dp(self.labels), self.eps, self.act, self.leak, 1 if self.train else 0, self.decay, mm, mv,
+             self.save.data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y):
+            return
+        nx, ns, no = self.need
+        assert self.train, 'backward through inference-mode batch norm is not part of the training path'
+        if self.dummy is not None:
+            dsc, dof = self.dummy.data_ptr(), self.dummy.data_ptr() + 4 * self.n_labels * self.c
+            accp = 0
+        else:
+            dsc, dof, accp = gp(self.scale), gp(self.offset), 1
+        if not nx:
+            # only parameter gradients wanted: dx still has to go somewhere -> reuse y.grad in place
+            dxp, accx = gp(self.y), 0
+        else:
+            dxp, accx = gp(self.x), self.acc_x
+        call('rcgan_bn_bwd', gp(self.y), dp(self.x), dp(self.y), dxp, self.samples, self.hw, self.c, self.x.dtype, self.y.dtype,
+             dp(self.scale), dp(self.labels), self.n_labels, self.save.data_ptr(), self.act, self.leak, dsc, dof, accx,
+             accp, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+
+
+class ActOp(Op):
+    """Standalone activation (lrelu mnist/ops.py:94-95; relu/tanh/sigmoid)."""
+
+    def __init__(self, x, act, leak=0.2):
+        prog = cur()
+        self.x, self.act, self.leak = x, ACT[act], leak
+        self.y = prog.new(x.shape, x.dtype)
+        self.inputs, self.outputs = (x,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_x = self.claim(self.x) if self.need[0] else 0
+
+    def forward(self, prog):
+        x, y = self.x, self.y
+        call('rcgan_bias_act_fwd', dp(x), None, dp(y), x.rows, x.c, x.ld, y.ld, x.dtype, self.act, self.leak, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        x, y = self.x, self.y
+        call('rcgan_act_bwd', gp(y), dp(y), gp(x), y.rows, y.c, y.ld, y.ld, x.ld, y.dtype, self.act, self.leak, self.acc_x,
+             stream_ptr())
+
+
+class ConcatLabelOp(Op):
+    """concat([a, y broadcast over H,W], channel axis): conv_cond_concat (mnist/ops.py:46-51) and the
+    z|y / h|y concats of the generator (mnist/model.py:714-728).  Output channel stride is padded to a
+    multiple of 8 (zero filled) so 16-byte vector / TMA loads stay aligned."""
+
+    def __init__(self, a, y):
+        prog = cur()
+        n, h, w = spatial(a)
+        self.a, self.yb = a, y
+        assert y.dtype == _C.F32 and y.shape[0] == n
+        c = a.c + y.c
+        oshape = (n, c) if len(a.shape) == 2 else (n, h, w, c)
+        self.out = prog.new(oshape, a.dtype, ld=round_up(c, 8))
+        self.rps = h * w
+        self.inputs, self.outputs = (a, y), (self.out,)
+        prog.add(self)
+
+    def plan(self, prog):
+        self.out.base.needs_grad = needs(self.a)   # labels are data, never differentiated
+
+    def plan_bwd(self, prog):
+        self.acc_a = self.claim(self.a) if self.need[0] else 0
+
+    def forward(self, prog):
+        a, o = self.a, self.out
+        call('rcgan_concat_label_fwd', dp(a), a.ld, dp(self.yb), dp(o), o.ld, o.rows, self.rps, a.c, self.yb.c, a.dtype,
+             stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.out) or not self.need[0]:
+            return
+        a, o = self.a, self.out
+        call('rcgan_slice_bwd', gp(o), o.ld, gp(a), a.ld, o.rows, a.c, a.dtype, self.acc_a, stream_ptr())
+
+
+class MeanHWOp(Op):
+    """tf.reduce_mean(x, axis=(1,2)), optionally of relu(x) (mnist/model.py:678; gan_resnet.py:405-407)."""
+
+    def __init__(self, x, relu=False):
+        prog = cur()
+        n, h, w = spatial(x)
+        assert x.ld == x.c
+        self.x, self.relu, self.hw = x, int(relu), h * w
+        self.y = prog.new((n, x.c), x.dtype)
+        self.inputs, self.outputs = (x,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_x = self.claim(self.x) if self.need[0] else 0
+
+    def forward(self, prog):
+        call('rcgan_meanhw_fwd', dp(self.x), dp(self.y), self.x.shape[0], self.hw, self.x.c, self.x.dtype, self.relu,
+             stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        call('rcgan_meanhw_bwd', gp(self.y), dp(self.x), gp(self.x), self.x.shape[0], self.hw, self.x.c, self.x.dtype,
+             self.relu, self.acc_x, stream_ptr())
+
+
+class CastOp(Op):
+    """dtype boundary between the bf16 trunk and the fp32 head / inputs."""
+
+    def __init__(self, x, dtype):
+        prog = cur()
+        assert x.ld == x.c
+        self.x = x
+        self.y = prog.new(x.shape, dtype)
+        self.inputs, self.outputs = (x,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_x = self.claim(self.x) if self.need[0] else 0
+        if self.acc_x:
+            from .graph import TORCH_DTYPE
+            self.tmp = torch.zeros(self.x.data.numel(), dtype=TORCH_DTYPE[self.x.grad_dtype], device=prog.device)
+
+    def forward(self, prog):
+        call('rcgan_cast', dp(self.x), self.x.dtype, dp(self.y), self.y.dtype, self.x.numel(), stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        st = stream_ptr()
+        if self.acc_x:
+            call('rcgan_cast', gp(self.y), self.y.grad_dtype, self.tmp.data_ptr(), self.x.grad_dtype, self.x.numel(), st)
+            call('rcgan_copy_acc', self.tmp.data_ptr(), gp(self.x), self.x.numel(), self.x.grad_dtype, 1, st)
+        else:
+            call('rcgan_cast', gp(self.y), self.y.grad_dtype, gp(self.x), self.x.grad_dtype, self.x.numel(), st)
+
+
+class SpectralNormOp(Op):
+    """W_bar = W / sigma(W, u) with one power iteration and the gradient THROUGH it
+    (spectral_normed_weight, mnist/sn.py:17-75).  u_new is assigned to u after the step
+    unless update_collection == NO_OPS."""
+
+    def __init__(self, W, u, update=True):
+        prog = cur()
+        self.W, self.u = W, u
+        self.c = W.shape[-1]
+        self.m = W.numel() // self.c
+        lib = _C.load()
+        self.wbar = prog.new(W.shape, _C.F32)
+        self.u_new = prog.new((1, self.c), _C.F32)
+        self.save = torch.zeros(lib.rcgan_sn_save_floats(self.m, self.c), dtype=torch.float32, device=prog.device)
+        prog.ws.request(lib.rcgan_sn_workspace(self.m, self.c))
+        self.inputs, self.outputs = (W,), (self.wbar,)
+        prog.add(self)
+        if update:
+            prog.add_update(u, self.u_new)
+
+    def plan_bwd(self, prog):
+        self.acc_w = self.claim(self.W) if self.need[0] else 0
+
+    def forward(self, prog):
+        call('rcgan_sn_fwd', dp(self.W), dp(self.u), self.m, self.c, dp(self.wbar), dp(self.u_new), self.save.data_ptr(),
+             prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.wbar) or not self.need[0]:
+            return
+        call('rcgan_sn_bwd', dp(self.W), dp(self.u), gp(self.wbar), self.m, self.c, self.save.data_ptr(), gp(self.W),
+             self.acc_w, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+
+
+class ChannelLossOp(Op):
+    """L = coef * mean_b sum_j wgt[b,j] * phi(psi[b] + <h[b], V[j]>)   (SURVEY appendix B).
+    The value stored in the program's loss slot is the un-weighted mean (coef applies to gradients)."""
+
+    def __init__(self, h, psi, V, wgt, mode, name, coef=1.0):
+        prog = cur()
+        self.h, self.psi, self.V, self.wgt = h, psi, V, wgt
+        self.B, self.d, self.k = h.shape[0], h.c, V.shape[0]
+        assert h.ld == h.c and V.c == h.c and wgt.shape == (self.B, self.k)
+        assert psi is None or psi.numel() == self.B
+        self.mode, self.coef = mode, coef
+        self.slot = prog.loss_slot(name)
+        self.logits = prog.new((self.B, self.k), _C.F32)
+        self.inputs, self.outputs = (h, psi, V, wgt), ()
+        prog.add(self)
+
+    def plan(self, prog):
+        pass
+
+    def plan_bwd(self, prog):
+        nh, np_, nv, nw = self.need
+        self.acc_h = self.claim(self.h) if nh else 0
+        if np_:
+            assert self.claim(self.psi) == 0, 'psi gradient must have a single writer'
+        self.zero_v = False
+        if nv:
+            self.zero_v = (self.claim(self.V) == 0) and not self.V.is_variable
+        if nw:
+            assert self.claim(self.wgt) == 0, 'weight-matrix gradient must have a single writer'
+
+    def forward(self, prog):
+        call('rcgan_channel_loss', dp(self.h), dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k, self.h.dtype,
+             self.mode, 1.0 / self.B, prog.losses.data_ptr() + 4 * self.slot, dp(self.logits), None, 0, None, None, None,
+             stream_ptr())
+
+    def backward(self, prog):
+        nh, np_, nv, nw = self.need
+        if not (nh or np_ or nv or nw):
+            return
+        st = stream_ptr()
+        if nv and self.zero_v:
+            call('rcgan_zero', gp(self.V), self.V.grad.numel() * 4, st)
+        call('rcgan_channel_loss', dp(self.h), dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k, self.h.dtype,
+             self.mode, self.coef / self.B, None, None, gp(self.h) if nh else None, self.acc_h,
+             gp(self.psi) if np_ else None, gp(self.V) if nv else None, gp(self.wgt) if nw else None, st)
+
+
+class SigmoidCEOp(Op):
+    """coef * mean(sigmoid_cross_entropy_with_logits(logits, targets)) over all B*k elements
+    (perm regulariser: mnist/model.py:214-224; cifar10/gan_resnet.py:687-695, 780-784)."""
+
+    def __init__(self, logits, targets, name, coef=1.0):
+        prog = cur()
+        assert logits.dtype == _C.F32 and targets.dtype == _C.F32 and logits.ld == logits.c
+        self.logits, self.targets, self.coef = logits, targets, coef
+        self.slot = prog.loss_slot(name)
+        self.inputs, self.outputs = (logits,), ()
+        prog.add(self)
+
+    def plan(self, prog):
+        pass
+
+    def plan_bwd(self, prog):
+        if self.need[0]:
+            assert self.claim(self.logits) == 0, 'classifier logits gradient must have a single writer'
+
+    def forward(self, prog):
+        n = self.logits.numel()
+        call('rcgan_sigmoid_ce', dp(self.logits), dp(self.targets), n, 1.0 / n, prog.losses.data_ptr() + 4 * self.slot, None,
+             stream_ptr())
+
+    def backward(self, prog):
+        if not self.need[0]:
+            return
+        n = self.logits.numel()
+        call('rcgan_sigmoid_ce', dp(self.logits), dp(self.targets), n, self.coef / n, None, gp(self.logits), stream_ptr())
+
+
+class LogitLossOp(Op):
+    """coef * mean_b phi(l[b]) on a scalar logit per sample (vanilla discriminator, mnist/model.py:687-703)."""
+
+    def __init__(self, logits, mode, name, coef=1.0):
+        prog = cur()
+        assert logits.dtype == _C.F32 and logits.ld == logits.c
+        self.logits, self.mode, self.coef = logits, mode, coef
+        self.slot = prog.loss_slot(name)
+        self.inputs, self.outputs = (logits,), ()
+        prog.add(self)
+
+    def plan(self, prog):
+        pass
+
+    def plan_bwd(self, prog):
+        if self.need[0]:
+            assert self.claim(self.logits) == 0, 'logit gradient must have a single writer'
+
+    def forward(self, prog):
+        n = self.logits.numel()
+        call('rcgan_logit_loss', dp(self.logits), n, self.mode, 1.0 / n, prog.losses.data_ptr() + 4 * self.slot, None,
+             stream_ptr())
+
+    def backward(self, prog):
+        if not self.need[0]:
+            return
+        n = self.logits.numel()
+        call('rcgan_logit_loss', dp(self.logits), n, self.mode, self.coef / n, None, gp(self.logits), stream_ptr())
+
+
+class SoftmaxRowsOp(Op):
+    """confusion_matrix = softmax(confusion_logits, -1) (mnist/model.py:106; gan_resnet.py:522)."""
+
+    def __init__(self, logits):
+        prog = cur()
+        self.x = logits
+        self.rows, self.k = logits.shape
+        self.y = prog.new(logits.shape, _C.F32)
+        self.inputs, self.outputs = (logits,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc = self.claim(self.x) if self.need[0] else 0
+
+    def forward(self, prog):
+        call('rcgan_softmax_rows_fwd', dp(self.x), dp(self.y), self.rows, self.k, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        call('rcgan_softmax_rows_bwd', dp(self.y), gp(self.y), gp(self.x), self.rows, self.k, self.acc, stream_ptr())
+
+
+class GatherRowsOp(Op):
+    """wgt[b,:] = C[y[b],:]  == tensordot(one_hot(y), C) (cifar10/gan_resnet.py:682-683, 757)."""
+
+    def __init__(self, C, y):
+        prog = cur()
+        self.C, self.yidx = C, y
+        self.B, self.k = y.numel(), C.shape[1]
+        self.out = prog.new((self.B, self.k), _C.F32)
+        self.inputs, self.outputs = (C,), (self.out,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc = self.claim(self.C) if self.need[0] else 0
+
+    def forward(self, prog):
+        call('rcgan_gather_rows_fwd', dp(self.C), dp(self.yidx), dp(self.out), self.B, self.k, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.out) or not self.need[0]:
+            return
+        call('rcgan_gather_rows_bwd', gp(self.out), dp(self.yidx), gp(self.C), self.B, self.k, self.C.shape[0], self.acc,
+             stream_ptr())
+
+
+class Pool2Op(Op):
+    """2x2 mean pool as add_n of four strided slices / 4 (cifar10/gan_resnet.py:239-240, 248-249)."""
+
+    def __init__(self, x):
+        prog = cur()
+        n, h, w = spatial(x)
+        assert x.ld == x.c
+        self.x = x
+        self.y = prog.new((n, h // 2, w // 2, x.c), x.dtype)
+        self.inputs, self.outputs = (x,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc = self.claim(self.x) if self.need[0] else 0
+
+    def forward(self, prog):
+        n, h, w = spatial(self.x)
+        call('rcgan_avgpool2_fwd', dp(self.x), dp(self.y), n, h, w, self.x.c, self.x.dtype, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        n, h, w = spatial(self.x)
+        call('rcgan_avgpool2_bwd', gp(self.y), gp(self.x), n, h, w, self.x.c, self.x.dtype, self.acc, stream_ptr())
+
+
+class Upsample2Op(Op):
+    """concat x4 + depth_to_space == nearest-neighbour 2x upsample (cifar10/gan_resnet.py:263-264)."""
+
+    def __init__(self, x):
+        prog = cur()
+        n, h, w = spatial(x)
+        assert x.ld == x.c
+        self.x = x
+        self.y = prog.new((n, 2 * h, 2 * w, x.c), x.dtype)
+        self.inputs, self.outputs = (x,), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc = self.claim(self.x) if self.need[0] else 0
+
+    def forward(self, prog):
+        n, h, w = spatial(self.x)
+        call('rcgan_upsample2_fwd', dp(self.x), dp(self.y), n, h, w, self.x.c, self.x.dtype, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y) or not self.need[0]:
+            return
+        n, h, w = spatial(self.x)
+        call('rcgan_upsample2_bwd', gp(self.y), gp(self.x), n, h, w, self.x.c, self.x.dtype, self.acc, stream_ptr())
+
+
+class AddOp(Op):
+    """shortcut + output (cifar10/gan_resnet.py:328, 353)."""
+
+    def __init__(self, a, b):
+        prog = cur()
+        assert a.shape == b.shape and a.ld == a.c and b.ld == b.c
+        self.a, self.b = a, b
+        self.y = prog.new(a.shape, a.dtype)
+        self.inputs, self.outputs = (a, b), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_a = self.claim(self.a) if self.need[0] else 0
+        self.acc_b = self.claim(self.b) if self.need[1] else 0
+
+    def forward(self, prog):
+        call('rcgan_add', dp(self.a), dp(self.b), dp(self.y), self.a.numel(), self.a.dtype, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.y):
+            return
+        st = stream_ptr()
+        if self.need[0]:
+            call('rcgan_copy_acc', gp(self.y), gp(self.a), self.a.numel(), self.a.dtype, self.acc_a, st)
+        if self.need[1]:
+            call('rcgan_copy_acc', gp(self.y), gp(self.b), self.b.numel(), self.b.dtype, self.acc_b, st)
+
+
+class ConcatRowsOp(Op):
+    """tf.concat([a, b], axis=0) of two dense tensors (cifar10/gan_resnet.py:563-578: D on [real; fake])."""
+
+    def __init__(self, a, b):
+        prog = cur()
+        assert a.shape[1:] == b.shape[1:] and a.ld == a.c and b.ld == b.c and a.dtype == b.dtype
+        self.a, self.b = a, b
+        self.y = prog.new((a.shape[0] + b.shape[0],) + tuple(a.shape[1:]), a.dtype)
+        self.inputs, self.outputs = (a, b), (self.y,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_a = self.claim(self.a) if self.need[0] else 0
+        self.acc_b = self.claim(self.b) if self.need[1] else 0
+
+    def _esz(self):
+        return 4 if self.a.dtype == _C.F32 else 2
+
+    def forward(self, prog):
+        st = stream_ptr()
+        call('rcgan_copy_acc', dp(self.a), dp(self.y), self.a.numel(), self.a.dtype, 0, st)
+        call('rcgan_copy_acc', dp(self.b), dp(self.y) + self.a.numel() * self._esz(), self.b.numel(), self.a.dtype, 0, st)
+
+    def backward(self, prog):
+        if not needs(self.y):
+            return
+        st = stream_ptr()
+        if self.need[0]:
+            call('rcgan_copy_acc', gp(self.y), gp(self.a), self.a.numel(), self.a.dtype, self.acc_a, st)
+        if self.need[1]:
+            call('rcgan_copy_acc', gp(self.y) + self.a.numel() * self._esz(), gp(self.b), self.b.numel(), self.a.dtype,
+                 self.acc_b, st)
+
+
+def adam_step(group, lr_t_dev, b1, b2, eps, grad_scale=1.0):
+    """One tf.train.AdamOptimizer update of a whole variable group (one launch)."""
+    import ctypes
+    clip = [(v.offset, v.offset + v.numel()) for v in group.vars if v.clip]
+    assert len(clip) <= 8
+    lo = (ctypes.c_long * 8)(*([c[0] for c in clip] + [0] * (8 - len(clip))))
+    hi = (ctypes.c_long * 8)(*([c[1] for c in clip] + [0] * (8 - len(clip))))
+    call('rcgan_adam_tf', group.params.data_ptr(), group.grads.data_ptr(), group.m.data_ptr(), group.v.data_ptr(),
+         group.numel, 0.0, lr_t_dev.data_ptr(), b1, b2, eps, grad_scale, lo, hi, len(clip), stream_ptr())

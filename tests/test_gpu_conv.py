@@ -1,0 +1,136 @@
+"""CUDA conv/deconv/linear family vs the oracle (oracle/nn.py) on the same seeded inputs."""
+import pytest
+import torch
+
+from oracle import nn as O
+from robust_conditional_gan_b200 import _C
+from robust_conditional_gan_b200._C import ConvDesc, call
+from robust_conditional_gan_b200.graph import same_pad
+from util import keep, TD, TOL, dev, relerr, st
+
+pytestmark = pytest.mark.gpu
+
+# (n, h, w, cin, cout, k, stride, ldx_pad, ldy_pad)
+SHAPES = [
+    (3, 28, 28, 1, 64, 5, 2, 0, 0),      # d_h0_conv
+    (3, 28, 28, 11, 64, 5, 2, 5, 0),     # d_h0_conv with label concat (ld 16)
+    (2, 14, 14, 64, 64, 5, 2, 0, 0),     # d_h1_conv
+    (2, 7, 7, 64, 64, 5, 2, 0, 0),       # d_h2_conv
+    (5, 4, 4, 64, 64, 5, 2, 0, 0),       # d_h3_conv
+    (2, 14, 14, 128, 138, 5, 2, 0, 6),   # g_h2 as the conv it transposes (x: 14x14x128, y: 7x7x138 ld 144)
+    (2, 28, 28, 1, 138, 5, 2, 0, 6),     # g_h3
+    (2, 8, 8, 128, 128, 3, 1, 0, 0),     # CIFAR D 3x3
+    (2, 16, 16, 3, 128, 1, 1, 0, 0),     # CIFAR D shortcut 1x1 cin=3
+    (2, 32, 32, 256, 3, 3, 1, 0, 0),     # G.Output cout=3
+    (7, 1, 1, 110, 1024, 1, 1, 2, 0),    # g_h0_lin (ld 112)
+    (9, 1, 1, 784, 10, 1, 1, 0, 0),      # classifier
+    (33, 1, 1, 64, 1, 1, 1, 0, 0),       # d_h4_lin
+]
+
+
+def make(shape, dtype, seed=0):
+    n, h, w, cin, cout, k, s, px, py = shape
+    g = torch.Generator().manual_seed(seed)
+    ho, pt = same_pad(h, k, s)
+    wo, pl = same_pad(w, k, s)
+    ldx, ldy = cin + px, cout + py
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = torch.randn(k, k, cin, cout, generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(n, ho, wo, cout, generator=g)
+    td = TD[dtype]
+    x, dy = x.to(td).float(), dy.to(td).float()      # quantise inputs so both sides see the same values
+    xbuf = torch.zeros(n, h, w, ldx); xbuf[..., :cin] = x
+    dybuf = torch.zeros(n, ho, wo, ldy); dybuf[..., :cout] = dy
+    d = ConvDesc(n, h, w, cin, ho, wo, cout, k, k, s, pt, pl, ldx, ldy, dtype)
+    return d, x, wt, b, dy, dev(xbuf, td), dev(dybuf, td), (ho, wo, ldx, ldy)
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('shape', SHAPES)
+def test_fprop(lib, shape, dtype):
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, cout = shape[0], shape[4]
+    y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=TD[dtype])
+    call('rcgan_conv2d_fprop', d, xd.data_ptr(), keep(dev(wt)), None, keep(dev(b)), y.data_ptr(), dtype, _C.ACT_LRELU,
+         0.2, st())
+    ref = O.lrelu(O.conv2d(x.double(), wt.double(), shape[6]) + b.double())
+    assert relerr(y[..., :cout].float(), ref) < TOL[dtype]
+    if ldy > cout:
+        assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0     # padding untouched
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('shape', SHAPES)
+def test_dgrad_and_deconv(lib, shape, dtype):
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, h, w, cin, cout, k, s = shape[:7]
+    xr = x.double().requires_grad_(True)
+    O.conv2d(xr, wt.double(), s).backward(dy.double())
+    dx = torch.zeros(n, h, w, ldx, device='cuda', dtype=TD[dtype])
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), keep(dev(wt)), None, None, dx.data_ptr(), dtype, _C.ACT_NONE, 0.0, 0, st())
+    assert relerr(dx[..., :cin].float(), xr.grad) < TOL[dtype]
+    # accumulate
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), keep(dev(wt)), None, None, dx.data_ptr(), dtype, _C.ACT_NONE, 0.0, 1, st())
+    assert relerr(dx[..., :cin].float(), 2 * xr.grad) < 2 * TOL[dtype]
+    # as the forward of deconv2d: conv2d_transpose(dy, w[kh,kw,cin(out),cout(in)]) + bias, sigmoid
+    if s == 2:
+        bias = torch.randn(cin, generator=torch.Generator().manual_seed(5))
+        out = torch.zeros(n, h, w, ldx, device='cuda', dtype=TD[dtype])
+        call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), keep(dev(wt)), None, keep(dev(bias)), out.data_ptr(),
+             dtype, _C.ACT_SIGMOID, 0.0, 0, st())
+        ref = torch.sigmoid(O.conv2d_transpose(dy.double(), wt.double(), (h, w), s) + bias.double())
+        assert relerr(out[..., :cin].float(), ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('shape', SHAPES)
+def test_wgrad(lib, shape, dtype):
+    d, x, wt, b, dy, xd, dyd, _ = make(shape, dtype)
+    s = shape[6]
+    wr = wt.double().requires_grad_(True)
+    O.conv2d(x.double(), wr, s).backward(dy.double())
+    nb = lib.rcgan_conv2d_wgrad_workspace(d)
+    ws = torch.zeros(max(nb, 4), dtype=torch.uint8, device='cuda')
+    dw = torch.full(wt.shape, 3.0, device='cuda')
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
+    assert relerr(dw, wr.grad) < TOL[dtype]
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
+    assert relerr(dw, 2 * wr.grad) < 2 * TOL[dtype]
+    db = torch.zeros(shape[4], device='cuda')
+    call('rcgan_colsum', dyd.data_ptr(), dyd.numel() // dyd.shape[-1], shape[4], dyd.shape[-1], dtype, db.data_ptr(), 0, st())
+    assert relerr(db, dy.double().sum((0, 1, 2))) < TOL[dtype]
+
+
+@pytest.mark.parametrize('shape', [SHAPES[2], SHAPES[5], SHAPES[10]])
+def test_bf16_operands_fp32_output(lib, shape):
+    """pre-norm layout: bf16 operands, fp32 stored output (conv -> batch norm); must be MORE accurate than bf16 storage"""
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, _C.BF16)
+    n, h, w, cin, cout, k, s = shape[:7]
+    y = torch.zeros(n, ho, wo, ldy, device='cuda', dtype=torch.float32)
+    call('rcgan_conv2d_fprop', d, xd.data_ptr(), keep(dev(wt)), None, keep(dev(b)), y.data_ptr(), _C.F32, _C.ACT_NONE, 0.0, st())
+    ref = O.conv2d(x.double(), wt.double(), s) + b.double()
+    assert relerr(y[..., :cout], ref) < 2e-5
+    if s == 2:
+        out = torch.zeros(n, h, w, ldx, device='cuda', dtype=torch.float32)
+        call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), keep(dev(wt)), None, None, out.data_ptr(), _C.F32, _C.ACT_NONE, 0.0, 0, st())
+        assert relerr(out[..., :cin], O.conv2d_transpose(dy.double(), wt.double(), (h, w), s)) < 2e-5
+
+
+def test_wgrad_large_k_splits(lib):
+    """split-K path: K = n*ho*wo = 50176 (d_h1 at batch 1024 has 50176 output pixels)"""
+    shape = (256, 14, 14, 64, 64, 5, 2, 0, 0)
+    d, x, wt, b, dy, xd, dyd, _ = make(shape, _C.F32)
+    wr = wt.double().requires_grad_(True)
+    O.conv2d(x.double(), wr, 2).backward(dy.double())
+    nb = lib.rcgan_conv2d_wgrad_workspace(d)
+    ws = torch.zeros(nb, dtype=torch.uint8, device='cuda')
+    dw = torch.zeros(wt.shape, device='cuda')
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
+    assert relerr(dw, wr.grad) < 2e-5
+
+
+def test_bad_args_fail_loudly(lib):
+    d = ConvDesc(1, 4, 4, 8, 4, 4, 8, 3, 3, 1, 1, 1, 4, 8, _C.F32)      # ldx < cin
+    with pytest.raises(_C.RcganError, match='ld smaller'):
+        call('rcgan_conv2d_fprop', d, None, None, None, None, None, 0, 0, 0.0, st())

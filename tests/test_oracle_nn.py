@@ -1,0 +1,147 @@
+"""The floating-point oracle is 'parity unpinned' (no TF here); these tests pin the semantic gotchas of
+SURVEY 8c through algebraic identities and closed forms."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mnist as OM, nn as O, sampler as S
+
+D = torch.float64
+
+
+def test_same_padding_table():
+    # k5 s2: 28->14 (1,2), 14->7 (1,2), 7->4 (2,2), 4->2 (1,2); k3 s1: (1,1)
+    assert O.same_pad(28, 5, 2) == (1, 2) and O.same_pad(14, 5, 2) == (1, 2)
+    assert O.same_pad(7, 5, 2) == (2, 2) and O.same_pad(4, 5, 2) == (1, 2) and O.same_pad(32, 3, 1) == (1, 1)
+
+
+@pytest.mark.parametrize('size', [28, 14, 7, 4])
+def test_conv2d_transpose_is_dgrad_of_conv2d(size):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, size, size, 3, generator=g, dtype=D, requires_grad=True)
+    w = torch.randn(5, 5, 3, 4, generator=g, dtype=D)
+    y = O.conv2d(x, w, 2)
+    dy = torch.randn(y.shape, generator=g, dtype=D)
+    gx, = torch.autograd.grad(y, x, dy)
+    assert float((O.conv2d_transpose(dy, w, (size, size)) - gx).abs().max()) < 1e-12
+    # and it is NOT torch's padding=2, output_padding=1 convention
+    t = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), stride=2, padding=2,
+                                             output_padding=1).permute(0, 2, 3, 1)
+    if t.shape == gx.shape:
+        assert float((t - gx).abs().max()) > 1e-3
+
+
+def test_conv2d_direct_definition():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 7, 7, 2, generator=g, dtype=D); w = torch.randn(5, 5, 2, 3, generator=g, dtype=D)
+    y = O.conv2d(x, w, 2)
+    pt, _ = O.same_pad(7, 5, 2)
+    ref = torch.zeros(1, 4, 4, 3, dtype=D)
+    for oy in range(4):
+        for ox in range(4):
+            for ky in range(5):
+                for kx in range(5):
+                    iy, ix = oy * 2 - pt + ky, ox * 2 - pt + kx
+                    if 0 <= iy < 7 and 0 <= ix < 7:
+                        ref[0, oy, ox] += x[0, iy, ix] @ w[ky, kx]
+    assert float((y - ref).abs().max()) < 1e-12
+
+
+def test_sn_closed_form_gradient_equals_autograd_and_differs_from_constant_uv():
+    g = torch.Generator().manual_seed(2)
+    W = torch.randn(3, 3, 128, 128, generator=g, dtype=D, requires_grad=True)
+    u = torch.randn(1, 128, generator=g, dtype=D)
+    Wb, u_new, sigma = O.spectral_normed_weight(W, u)
+    G = torch.randn(Wb.shape, generator=g, dtype=D)
+    gw, = torch.autograd.grad(Wb, W, G)
+    cf = O.sn_grad_closed_form(W.detach(), u, G)
+    assert float((gw - cf).abs().max()) < 1e-12
+    const = G / sigma.detach()
+    assert float((gw - const).norm() / gw.norm()) > 1e-3       # SURVEY: ~3.8e-3
+    assert abs(float(u_new.norm()) - 1) < 1e-12
+
+
+def test_bn_moving_update_uses_bessel_variance():
+    x = torch.arange(12, dtype=D).reshape(4, 3)
+    y, mean, var = O.batch_norm_train(x, torch.ones(3, dtype=D), torch.zeros(3, dtype=D))
+    mm, mv = O.batch_norm_moving_update(torch.zeros(3, dtype=D), torch.ones(3, dtype=D), mean, var, 4)
+    assert torch.allclose(mm, 0.1 * mean) and torch.allclose(mv, 0.9 + 0.1 * var * 4 / 3)
+    assert torch.allclose(y.var(0, unbiased=False), torch.ones(3, dtype=D), atol=1e-4)
+
+
+def test_tf_adam_differs_from_torch_adam_for_tiny_grads():
+    p0 = torch.ones(4, dtype=D); g = torch.tensor([1e-9, 1e-3, -1e-9, 1.0], dtype=D)
+    opt = O.TFAdam(['p'], 2e-4, 0.5)
+    P = {'p': p0.clone()}
+    opt.step(P, {'p': g})
+    tp = torch.nn.Parameter(p0.clone()); to = torch.optim.Adam([tp], 2e-4, betas=(0.5, 0.999), eps=1e-8); tp.grad = g.clone(); to.step()
+    assert abs(float(P["p"][3] - tp[3])) < 1e-9 and abs(float(P['p'][0] - tp.data[0])) > 1e-6
+
+
+def test_collapsed_expectation_equals_ten_discriminator_calls():
+    """The product evaluates the trunk once and takes the label expectation in the channel loss; the oracle
+    follows the reference's 10 calls (mnist/model.py:183-204).  Same numbers."""
+    cfg = OM.default_config(batch_size=6, algorithm='rcgan', disc_type='projection', estimate_confuse=True, alpha=0.5)
+    P = OM.init_params(cfg, 3, D)
+    b = OM.synthetic_batch(6, 1, D, S.one_coin_confusion(0.5), cfg)
+    L = OM.losses(P, b, cfg)
+    G = L['G']
+    la = L['D_logits_all_']
+    # one trunk: h3, then psi + <h3, V_j>
+    n = 'discriminator/'
+    y0 = torch.eye(10, dtype=D)[0].expand(6, 10)
+    l0 = OM.discriminator(P, G, y0, cfg)
+    V = P[n + 'd_h5_y_lin/Matrix'] + P[n + 'd_h5_y_lin/bias']
+    # recover h3 from two label evaluations is awkward; instead check linearity in the label embedding
+    l_mix = OM.discriminator(P, G, 0.5 * torch.eye(10, dtype=D)[1].expand(6, 10) + 0.5 * torch.eye(10, dtype=D)[2].expand(6, 10), cfg)
+    assert torch.allclose(l_mix[:, 0], 0.5 * la[:, 1] + 0.5 * la[:, 2], atol=1e-12)
+    assert torch.allclose(l0[:, 0], la[:, 0], atol=1e-12) and V.shape == (10, 64)
+
+
+def test_variable_partition_and_max_norm_names():
+    cfg = OM.default_config(batch_size=4, algorithm='rcgan', disc_type='projection', estimate_confuse=True)
+    P = OM.init_params(cfg, 0, D)
+    d, g = OM.d_var_names(P), OM.g_var_names(P)
+    assert 'classifier/d_classifier_h1/Matrix' in d and 'confusion_logits' not in d + g
+    assert not set(d) & set(g)
+    assert sorted(OM.max_norm_names(P, cfg)) == ['discriminator/d_h4_lin/Matrix', 'discriminator/d_h4_lin/bias',
+                                                  'discriminator/d_h5_y_lin/Matrix', 'discriminator/d_h5_y_lin/bias']
+
+
+def test_bf16_conditioning_of_bn_backward_is_inherent():
+    """Rounding ONE class of tensors (the conv outputs feeding the discriminator's batch norms) to bf16 in the fp64
+    oracle moves the trunk gradients by several percent at initialisation: the BN backward
+    dx = istd*(g - mean(g) - xhat*mean(g*xhat)) cancels ~50x there.  This is why the bf16 parity tests bound the
+    trunk gradients by direction and a loose relative error instead of the 1e-2 that every other tensor meets."""
+    class RoundFwd(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x.to(torch.bfloat16).to(x.dtype)
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    B = 32
+    cfg = OM.default_config(batch_size=B, alpha=0.5, algorithm='rcgan', disc_type='projection', estimate_confuse=False)
+    C = S.one_coin_confusion(0.5)
+    batch = OM.synthetic_batch(B, 3, D, C, cfg)
+    orig = OM._bn
+    grads = {}
+    try:
+        for rounded in (False, True):
+            def bn(P, name, x, train, upd, track=True, _r=rounded):
+                if _r and name.startswith('discriminator'):
+                    x = RoundFwd.apply(x)
+                return orig(P, name, x, train, upd, track)
+            OM._bn = bn
+            P = OM.init_params(cfg, 1, D)
+            names = ['discriminator/d_h%d_conv/w' % i for i in range(4)]
+            for n in names:
+                P[n] = P[n].requires_grad_(True)
+            L = OM.losses(P, batch, cfg, C)
+            grads[rounded] = torch.autograd.grad(L['d_loss'], [P[n] for n in names])
+    finally:
+        OM._bn = orig
+    errs = [float((a - b).norm() / b.norm()) for a, b in zip(grads[True], grads[False])]
+    assert min(errs) > 2e-2, errs
