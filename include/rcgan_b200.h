@@ -60,6 +60,8 @@ typedef struct {
 /* bytes of the bf16 tensor-core weight pack for this shape, 0 if the shape runs on the
  * CUDA-core path (tiny channel counts: cin or cout not a multiple of 8, K < 64 ...). */
 size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d);
+/* 1 when the given direction (0 fprop, 1 dgrad, 2 wgrad) of this shape runs on the tcgen05 path when a pack is passed */
+int rcgan_conv_uses_tensor_cores(const rcgan_conv_desc* d, int direction);
 /* w_f32 (optionally scaled by *scale_dev, e.g. 1/sigma) -> bf16 pack (both GEMM layouts) */
 int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scale_dev, void* pack, void* stream);
 

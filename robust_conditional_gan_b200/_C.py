@@ -35,6 +35,7 @@ _SIGS = {
     'rcgan_launch_count': (c_long, []),
     'rcgan_device_ok': (c_int, []),
     'rcgan_conv_wpack_bytes': (c_size_t, [DP]),
+    'rcgan_conv_uses_tensor_cores': (c_int, [DP, c_int]),
     'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
     'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_conv2d_dgrad': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, c_int, P]),

@@ -223,6 +223,134 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p, const T* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow-output path: N <= 4 output channels (g_h3's cout = 1, G.Output's cout = 3, the dgrad into a 1- or 3-channel
+// image).  These are bandwidth-bound gather-dots (AI < 30 flop/B), not GEMMs: 8 lanes share one output
+// pixel, each lane streams 16-byte channel chunks of the source pixels selected by the filter taps (coalesced 128 B
+// per pixel) against the weights staged in shared memory as [tap][n][c]; a 3-step shuffle finishes the dot product.
+template <int MODE, int NOUT, typename T, typename TO>
+__global__ void __launch_bounds__(256) conv_narrow_kernel(ConvP p, const T* __restrict__ src, const float* __restrict__ wt,
+                                                          TO* __restrict__ out) {
+  constexpr int V = 16 / sizeof(T);                 // elements per 16-byte chunk
+  extern __shared__ float wsm[];                    // [taps][NOUT][Cp], Cp = C rounded up to V, zero padded
+  const int taps = p.kh * p.kw;
+  const int C = MODE == MODE_FPROP ? p.cin : p.cout;   // contraction channels
+  const int nchunk = (C + V - 1) / V;
+  const int Cp = nchunk * V;
+  const int ldsrc = MODE == MODE_FPROP ? p.ldx : p.ldy;
+  for (int i = threadIdx.x; i < taps * NOUT * Cp; i += 256) {
+    int c = i % Cp, r = i / Cp, n = r % NOUT, tap = r / NOUT;
+    // w is [tap][cin][cout]: fprop contracts cin (n = cout index), dgrad contracts cout (n = cin index)
+    float v = 0.f;
+    if (c < C) v = MODE == MODE_FPROP ? wt[((size_t)tap * p.cin + c) * p.cout + n] : wt[((size_t)tap * p.cin + n) * p.cout + c];
+    wsm[i] = v;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;                  // lane within the 8-lane group
+  const int SH = MODE == MODE_FPROP ? p.h : p.ho, SW = MODE == MODE_FPROP ? p.w : p.wo;
+  const int OHh = MODE == MODE_FPROP ? p.ho : p.h, OWw = MODE == MODE_FPROP ? p.wo : p.w;
+  const int st = p.stride;
+  for (long mb = (long)blockIdx.x * 32; mb < p.M; mb += (long)gridDim.x * 32) {   // block-uniform trip count
+    const long m = mb + (threadIdx.x >> 3);
+    const bool valid = m < p.M;
+    const long mm = valid ? m : 0;
+    const int b = (int)(mm % OWw);
+    const long r = mm / OWw;
+    const int a = (int)(r % OHh), n = (int)(r / OHh);
+    float acc[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; j++) acc[j] = 0.f;
+    // fprop: every tap, source = a*stride - pad + k.   dgrad: only taps with (a + pad - k) % stride == 0, i.e.
+    // k = k0 + stride*i, source = (a + pad - k) / stride (exact), so the loop steps by the stride and never divides
+    const int ky0 = MODE == MODE_FPROP ? 0 : (a + p.pad_t) % st, kx0 = MODE == MODE_FPROP ? 0 : (b + p.pad_l) % st;
+    const int kstep = MODE == MODE_FPROP ? 1 : st;
+    const int sy0 = MODE == MODE_FPROP ? a * st - p.pad_t : (a + p.pad_t - ky0) / st;
+    const int sx0 = MODE == MODE_FPROP ? b * st - p.pad_l : (b + p.pad_l - kx0) / st;
+    if (valid) {
+      for (int ky = ky0, iy = 0; ky < p.kh; ky += kstep, iy++) {
+        const int sy = MODE == MODE_FPROP ? sy0 + ky : sy0 - iy;
+        if (sy < 0 || sy >= SH) continue;
+        for (int kx = kx0, ix = 0; kx < p.kw; kx += kstep, ix++) {
+          const int sx = MODE == MODE_FPROP ? sx0 + kx : sx0 - ix;
+          if (sx < 0 || sx >= SW) continue;
+          const T* sp = src + ((size_t)(n * SH + sy) * SW + sx) * ldsrc;
+          const float* wp = wsm + (size_t)(ky * p.kw + kx) * NOUT * Cp;
+          for (int ck = sub; ck < nchunk; ck += 8) {
+            float xv[V];
+            const uint4 q = *reinterpret_cast<const uint4*>(sp + ck * V);   // pad channels (C..ld) are finite, weights 0
+            if (sizeof(T) == 2) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < V / 2; e++) { float2 f = __bfloat1622float2(h[e]); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
+            } else {
+              const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+              for (int e = 0; e < V; e++) xv[e] = f[e];
+            }
+#pragma unroll
+            for (int j = 0; j < NOUT; j++) {
+              const float4* w4 = reinterpret_cast<const float4*>(wp + j * Cp + ck * V);
+#pragma unroll
+              for (int e = 0; e < V / 4; e++) {
+                float4 wv = w4[e];
+                acc[j] = fmaf(xv[4 * e], wv.x, acc[j]);
+                acc[j] = fmaf(xv[4 * e + 1], wv.y, acc[j]);
+                acc[j] = fmaf(xv[4 * e + 2], wv.z, acc[j]);
+                acc[j] = fmaf(xv[4 * e + 3], wv.w, acc[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NOUT; j++) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    }
+    if (valid && sub < NOUT) {
+      float v = acc[0];
+#pragma unroll
+      for (int j = 1; j < NOUT; j++)
+        if (sub == j) v = acc[j];
+      if (p.bias) v += p.bias[sub];
+      v = act_fwd(v, p.act, p.leak);
+      size_t o = (size_t)m * (MODE == MODE_FPROP ? p.ldy : p.ldx) + sub;
+      if (p.accumulate) v += to_f(out[o]);
+      out[o] = from_f<TO>(v);
+    }
+  }
+}
+
+template <int MODE, int NOUT, typename T, typename TO>
+void launch_narrow_n(const ConvP& p, const void* src, const float* w, void* out, size_t shb, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_narrow_kernel<MODE, NOUT, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  long groups = ((long)p.M + 31) / 32;
+  int grid = (int)(groups < 1 ? 1 : (groups > RCGAN_NUM_SMS * 16 ? RCGAN_NUM_SMS * 16 : groups));
+  conv_narrow_kernel<MODE, NOUT, T, TO><<<grid, 256, shb, st>>>(p, (const T*)src, w, (TO*)out);
+}
+
+template <int MODE, typename T, typename TO>
+bool launch_narrow(const ConvP& p, const void* src, const float* w, void* out, cudaStream_t st) {
+  const int C = MODE == MODE_FPROP ? p.cin : p.cout, ldsrc = MODE == MODE_FPROP ? p.ldx : p.ldy;
+  const int V = 16 / (int)sizeof(T);
+  const int Cp = ((C + V - 1) / V) * V;
+  size_t shb = (size_t)p.kh * p.kw * p.N * Cp * sizeof(float);
+  if (p.N > 4 || C < 32 || ldsrc % V != 0 || Cp > ldsrc || shb > 96 * 1024) return false;
+  switch (p.N) {
+    case 1: launch_narrow_n<MODE, 1, T, TO>(p, src, w, out, shb, st); break;
+    case 2: launch_narrow_n<MODE, 2, T, TO>(p, src, w, out, shb, st); break;
+    case 3: launch_narrow_n<MODE, 3, T, TO>(p, src, w, out, shb, st); break;
+    default: launch_narrow_n<MODE, 4, T, TO>(p, src, w, out, shb, st); break;
+  }
+  return true;
+}
+
 // dw (=|+=) sum over splits
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long mn, int nsplit, int accumulate) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,9 +407,13 @@ void launch(const ConvP& p, const void* a, const float* w, const void* dy, void*
 // operand dtype x output dtype: (f32,f32) (bf16,bf16) (bf16,f32 -- tensors that feed a batch norm stay fp32)
 template <int MODE>
 int launch_io(const ConvP& p, int dtype, int out_dtype, const void* a, const float* w, void* out, cudaStream_t st) {
-  if (dtype == RCGAN_F32 && out_dtype == RCGAN_F32) launch<MODE, float, float>(p, a, w, nullptr, out, 1, st);
-  else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_BF16) launch<MODE, bf16, bf16>(p, a, w, nullptr, out, 1, st);
-  else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_F32) launch<MODE, bf16, float>(p, a, w, nullptr, out, 1, st);
+  if (dtype == RCGAN_F32 && out_dtype == RCGAN_F32) {
+    if (!launch_narrow<MODE, float, float>(p, a, w, out, st)) launch<MODE, float, float>(p, a, w, nullptr, out, 1, st);
+  } else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_BF16) {
+    if (!launch_narrow<MODE, bf16, bf16>(p, a, w, out, st)) launch<MODE, bf16, bf16>(p, a, w, nullptr, out, 1, st);
+  } else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_F32) {
+    if (!launch_narrow<MODE, bf16, float>(p, a, w, out, st)) launch<MODE, bf16, float>(p, a, w, nullptr, out, 1, st);
+  }
   else { rcgan_set_error("conv: unsupported dtype pair (%d -> %d)", dtype, out_dtype); return RCGAN_EUNSUPPORTED; }
   return 0;
 }
@@ -293,6 +425,9 @@ int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, c
                    int act, float leak, cudaStream_t st, int* handled);
 int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
                    int act, float leak, int accumulate, cudaStream_t st, int* handled);
+
+int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st,
+                   int* handled);
 
 extern "C" int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
                                   const float* bias, void* y, int out_dtype, int act, float leak, void* stream) {
@@ -339,6 +474,11 @@ extern "C" size_t rcgan_conv2d_wgrad_workspace(const rcgan_conv_desc* d) {
 extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,
                                   void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_desc(d, "conv2d_wgrad")) return e;
+  {
+    int handled = 0;
+    int e = rcgan_tc_wgrad(d, x, dy, dw, accumulate, as_stream(stream), &handled);
+    if (e || handled) return e;
+  }
   ConvP p = make_p(d);
   p.M = d->kh * d->kw * d->cin; p.N = d->cout; p.K = d->n * d->ho * d->wo;
   int ns = wgrad_splits(p);

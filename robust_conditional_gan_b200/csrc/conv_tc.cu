@@ -1,19 +1,751 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution path (bf16 operands, fp32 accumulate in TMEM).
-// Placeholder translation unit: the tensor-core kernels land here; until then every shape reports
-// "not handled" and the CUDA-core path in conv_simt.cu runs.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 operands, fp32 accumulation in tensor memory).
+//
+// Covers the GEMM-shaped layers of the reference in bf16 mode -- tf.nn.conv2d fprop and its dgrad
+// (mnist/ops.py:62, cifar10/common/ops/conv2d.py:181-187), tf.nn.conv2d_transpose as a forward op
+// (mnist/ops.py:78, = dgrad; stride 2 runs as four output-parity classes, each a dense small-filter conv, so only
+// useful flops are issued) and the tf.matmul linears (1x1, h=w=1).
+//
+//   GEMM view:  D[128 pixels x BN channels] += A[128 x 64] * B[BN x 64]^T   per K block (one filter tap x 64 channels)
+//   A (activations): gathered by 4 producer warps with 16-byte cp.async (zero-fill for the SAME-padding halo and the
+//       channel tail) straight into the UMMA canonical K-major SWIZZLE_128B layout, then fence.proxy.async + mbarrier
+//   B (weights)    : TMA 3-D tiled load (cp.async.bulk.tensor, SWIZZLE_128B) from the packed bf16 weight copy
+//   MMA            : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per K block,
+//                    accumulator in TMEM; tcgen05.commit releases the smem stage / signals the epilogue
+//   epilogue       : the 4 producer warps read TMEM with tcgen05.ld.32x32b, add bias, apply the activation and store
+//                    bf16 or fp32 NHWC rows (optionally accumulating: dgrad into a gradient that already has a writer)
+// 3-4 stage mbarrier ring, <= 96 KB smem per CTA so two CTAs share an SM (one CTA's epilogue overlaps the other's MMAs).
+#include <cuda.h>
+
 #include "common.cuh"
 
-extern "C" size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d) { (void)d; return 0; }
-extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scale_dev, void* pack, void* stream) {
-  (void)d; (void)w; (void)scale_dev; (void)pack; (void)stream;
-  rcgan_set_error("conv_wpack: shape has no tensor-core pack");
-  return RCGAN_EUNSUPPORTED;
+namespace {
+
+constexpr int BM = 128;       // pixels per CTA tile (UMMA M)
+constexpr int BK = 64;        // bf16 channels per K block = one 128-byte swizzle row
+constexpr int LAG = 2;        // cp.async groups in flight per producer thread
+constexpr int MAX_TAPS = 25;
+
+struct TcParams {
+  const bf16* src;            // gathered operand (x for fprop, dy for dgrad), NHWC with channel stride ld_src
+  int SH, SW, ld_src, cvalid; // source image dims; channels readable as 16-byte chunks (multiple of 8, <= ld_src)
+  int MH, MW, M;              // GEMM rows: m -> (n, a, b), a < MH, b < MW
+  int by_mul, by_add, bx_mul, bx_add;   // source base coordinate of a row: (a*by_mul + by_add, b*bx_mul + bx_add)
+  int ntaps, kb_per_tap;
+  short tdy[MAX_TAPS], tdx[MAX_TAPS], twi[MAX_TAPS];   // per tap: source offset, weight-pack tap index
+  void* out;                  // output NHWC
+  int out_f32, ld_out, OH, OW, oy_mul, oy_add, ox_mul, ox_add, N;
+  const float* bias;
+  int act;
+  float leak;
+  int accumulate;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int rcgan_tc_fprop(const rcgan_conv_desc*, const void*, const void*, const float*, void*, int, int, float, cudaStream_t, int* handled) {
-  *handled = 0;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: LBO = 1 (unused), SBO = 1024 B (8 rows x 128 B), version 1
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (>>4), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset (>>4), bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 64 ? 4 : 3;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
+                                                         const __grid_constant__ CUtensorMap wmap) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * C::B_BYTES);
+  uint64_t* full = bars;                  // [STAGES]  128 producer arrivals + 1 expect_tx arrival
+  uint64_t* empty = bars + STAGES;        // [STAGES]  1 arrival (tcgen05.commit)
+  uint64_t* accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nkb = p.ntaps * p.kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(smem_u32(&full[s]), 128 + 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), BN);
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== A producers (then epilogue)
+    const int t = threadIdx.x;
+    const int chunk = t & 7;               // 16-byte chunk within the 128-byte row
+    int rbase[8], ry[8], rx[8];            // per handled row: image base (pixels), source base coordinates
+    bool rok[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int m = m0 + (t >> 3) + 16 * i;
+      rok[i] = m < p.M;
+      int mm = rok[i] ? m : 0;
+      int b = mm % p.MW, r = mm / p.MW, a = r % p.MH, n = r / p.MH;
+      rbase[i] = n * p.SH * p.SW;
+      ry[i] = a * p.by_mul + p.by_add;
+      rx[i] = b * p.bx_mul + p.bx_add;
+    }
+    for (int kb = 0; kb < nkb; kb++) {
+      const int s = kb % STAGES;
+      mbar_wait(smem_u32(&empty[s]), ((kb / STAGES) & 1) ^ 1);
+      const int tap = kb / p.kb_per_tap;
+      const int ch = (kb - tap * p.kb_per_tap) * BK + chunk * 8;
+      const int dy = p.tdy[tap], dx = p.tdx[tap];
+      const bool chok = ch < p.cvalid;
+      const uint32_t abase = smem_u32(smA + s * C::A_BYTES);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int row = (t >> 3) + 16 * i;
+        const int sy = ry[i] + dy, sx = rx[i] + dx;
+        const bool ok = chok && rok[i] && sy >= 0 && sy < p.SH && sx >= 0 && sx < p.SW;
+        const bf16* src = ok ? p.src + ((size_t)(rbase[i] + sy * p.SW + sx) * p.ld_src + ch) : p.src;
+        cp_async16(abase + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (kb >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full[(kb - LAG) % STAGES]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (nkb > LAG ? nkb - LAG : 0); kb < nkb; kb++) mbar_arrive(smem_u32(&full[kb % STAGES]));
+
+    // =========================================================== epilogue: TMEM -> registers -> global
+    mbar_wait(smem_u32(accum_full), 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const bool mok = m < p.M;
+    size_t obase = 0;
+    if (mok) {
+      int b = m % p.MW, r = m / p.MW, a = r % p.MH, n = r / p.MH;
+      obase = ((size_t)(n * p.OH + a * p.oy_mul + p.oy_add) * p.OW + (b * p.ox_mul + p.ox_add)) * p.ld_out;
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);   // warp-collective: all lanes execute
+      if (!mok || n0 + c0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        int nn = n0 + c0 + j;
+        float x = __uint_as_float(r[j]);
+        if (p.bias && nn < p.N) x += p.bias[nn];
+        v[j] = act_fwd(x, p.act, p.leak);
+      }
+      const bool full32 = (n0 + c0 + 32 <= p.N);
+      if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + obase + n0 + c0;
+        if (full32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (n0 + c0 + j < p.N) o[j] = p.accumulate ? o[j] + v[j] : v[j];
+        }
+      } else {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + obase + n0 + c0;
+        if (full32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(o + j) = q;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (n0 + c0 + j < p.N) o[j] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[j]) + v[j] : v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================================================== B producer (TMA)
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(smem_u32(&empty[s]), ((kb / STAGES) & 1) ^ 1);
+        const int tap = kb / p.kb_per_tap;
+        const int k0 = (kb - tap * p.kb_per_tap) * BK;
+        mbar_arrive_expect_tx(smem_u32(&full[s]), C::B_BYTES);
+        tma_load_3d(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0, p.twi[tap]);
+      }
+    }
+  } else {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(smem_u32(&full[s]), (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + s * C::A_BYTES));
+        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + s * C::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)   // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(smem_u32(&empty[s]));   // implies tcgen05.fence::before_thread_sync
+      }
+      umma_commit(smem_u32(accum_full));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[tap][ci][co] = sum over output pixels m of x[pix(m, tap)][ci] * dy[m][co]: the contraction runs over PIXELS, which
+// is the strided dimension of both NHWC operands, so both tiles are MN-major for the UMMA (a_major = b_major = 1):
+//   A: [K = 128 pixels][MN = 64 channels] per unit, unit = (filter tap, 64-channel block of cin); a CTA tile stacks
+//      TWO units into M = 128 (for cin = 64 that is two taps side by side, for cin = 128 the two halves of one tap);
+//      gathered with cp.async exactly like the fprop A tile (the swizzle is address based, so the same physical
+//      layout is the canonical MN-major SWIZZLE_128B atom: 64 channels contiguous, 8 pixel rows per 1024 B group)
+//   B: [K = 128 pixels][MN = 64 channels of dy] per 64-column box, plain 2-D TMA over dy (rows are consecutive pixels)
+// split-K over pixel blocks across gridDim.z, fp32 partial sums are red.global.add'ed into dW.
+struct WgParams {
+  const bf16* x;
+  int H, W, ldx, cvalid;
+  int HO, WO, HW, Mpix;
+  int stride, pad_t, pad_l, kw;
+  int cin, cout, cblks, units;
+  int kb_total, kb_per_split;
+  float* dw;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // distance between 64-element MN atoms
+  d |= (uint64_t)(1024 >> 4) << 32;                   // distance between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int BN> struct WgCfg {
+  static constexpr int STAGES = BN == 64 ? 4 : 3;
+  static constexpr int UNIT_BYTES = 128 * 128;                 // 128 pixel rows x 128 B
+  static constexpr int A_BYTES = 2 * UNIT_BYTES;
+  static constexpr int B_BYTES = (BN / 64) * UNIT_BYTES;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 + 256 + 2048 /*pixel lut*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p,
+                                                          const __grid_constant__ CUtensorMap dymap) {
+  using C = WgCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * C::B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint16_t* lut = reinterpret_cast<uint16_t*>(bars + 2 * STAGES + 2);   // pixel-in-image -> (oy << 8 | ox), HW <= 1024
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * 2;                 // first of the two stacked units
+  const int n0 = blockIdx.y * BN;
+  const int kb_beg = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
+  const int nkb = kb_end - kb_beg;
+
+  for (int i = threadIdx.x; i < p.HW; i += 192) lut[i] = (uint16_t)(((i / p.WO) << 8) | (i % p.WO));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(smem_u32(&full[s]), 128 + 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), BN);
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nkb <= 0) {            // empty split (cannot happen with the host's split choice; keep teardown well-formed)
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, BN);
+    return;
+  }
+
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    const int chunk = t & 7;
+    // the two units of this tile: tap offsets and channel bases
+    int udy[2], udx[2], uch[2];
+    bool uok[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      int u = u0 + j;
+      uok[j] = u < p.units;
+      int uu = uok[j] ? u : 0;
+      int tap = uu / p.cblks, cb = uu - tap * p.cblks;
+      udy[j] = tap / p.kw - p.pad_t;
+      udx[j] = tap % p.kw - p.pad_l;
+      uch[j] = cb * 64 + chunk * 8;
+      uok[j] = uok[j] && uch[j] < p.cvalid;
+    }
+    // per handled row: image index and pixel-in-image index of pixel m = kb*128 + row, advanced by 128 per K block
+    int rn[8], rpi[8];
+    const int adv_n = 128 / p.HW, adv_pi = 128 % p.HW;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      long m = (long)kb_beg * 128 + (t >> 3) + 16 * i;
+      rn[i] = (int)(m / p.HW);
+      rpi[i] = (int)(m - (long)rn[i] * p.HW);
+    }
+    for (int kk = 0; kk < nkb; kk++) {
+      const int s = kk % STAGES;
+      mbar_wait(smem_u32(&empty[s]), ((kk / STAGES) & 1) ^ 1);
+      const uint32_t abase = smem_u32(smA + s * C::A_BYTES);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int row = (t >> 3) + 16 * i;
+        const bool rowok = ((long)rn[i] * p.HW + rpi[i]) < p.Mpix;
+        const int e = lut[rowok ? rpi[i] : 0];
+        const int oy = e >> 8, ox = e & 255;
+        const uint32_t soff = row * 128 + ((chunk ^ (row & 7)) << 4);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int iy = oy * p.stride + udy[j], ix = ox * p.stride + udx[j];
+          const bool ok = uok[j] && rowok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          const bf16* src = ok ? p.x + ((size_t)((rn[i] * p.H + iy) * p.W + ix) * p.ldx + uch[j]) : p.x;
+          cp_async16(abase + j * C::UNIT_BYTES + soff, src, ok ? 16u : 0u);
+        }
+        rn[i] += adv_n; rpi[i] += adv_pi;
+        if (rpi[i] >= p.HW) { rpi[i] -= p.HW; rn[i] += 1; }
+      }
+      cp_async_commit();
+      if (kk >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full[(kk - LAG) % STAGES]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kk = (nkb > LAG ? nkb - LAG : 0); kk < nkb; kk++) mbar_arrive(smem_u32(&full[kk % STAGES]));
+
+    // ---- epilogue: accumulator row r = unit (r / 64), channel (r % 64)
+    mbar_wait(smem_u32(accum_full), 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const int u = u0 + (r >> 6);
+    int tap = 0, ci = p.cin;
+    if (u < p.units) { tap = u / p.cblks; ci = (u - tap * p.cblks) * 64 + (r & 63); }
+    const bool rok = ci < p.cin;
+    float* orow = p.dw + ((size_t)tap * p.cin + (rok ? ci : 0)) * p.cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (!rok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        int co = n0 + c0 + j;
+        if (co < p.cout) atomicAdd(orow + co, __uint_as_float(v[j]));
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int kk = 0; kk < nkb; kk++) {
+        const int s = kk % STAGES;
+        mbar_wait(smem_u32(&empty[s]), ((kk / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(smem_u32(&full[s]), C::B_BYTES);
+#pragma unroll
+        for (int j = 0; j < BN / 64; j++)
+          tma_load_2d(smem_u32(smB + s * C::B_BYTES + j * C::UNIT_BYTES), &dymap, smem_u32(&full[s]), n0 + j * 64,
+                      (kb_beg + kk) * 128);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      for (int kk = 0; kk < nkb; kk++) {
+        const int s = kk % STAGES;
+        mbar_wait(smem_u32(&full[s]), (kk / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_mnmajor_sw128(smem_u32(smA + s * C::A_BYTES), C::UNIT_BYTES);
+        const uint64_t db = umma_desc_mnmajor_sw128(smem_u32(smB + s * C::B_BYTES), C::UNIT_BYTES);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; k++)   // 16 pixel rows per MMA = two 1024-byte K groups: +2048 B = +128 units
+          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kk | k) != 0);
+        umma_commit(smem_u32(&empty[s]));
+      }
+      umma_commit(smem_u32(accum_full));
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// weights fp32 [taps][cin][cout] (* scale) -> bf16  F: [taps][cout][kpadF]   D: [taps][cin][kpadD]
+__global__ void wpack_kernel(const float* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ packF,
+                             bf16* __restrict__ packD, int taps, int cin, int cout, int kpadF, int kpadD) {
+  const float sc = scale ? *scale : 1.f;
+  long nF = (long)taps * cout * kpadF, nD = (long)taps * cin * kpadD;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nF + nD; i += (long)gridDim.x * blockDim.x) {
+    if (i < nF) {
+      int k = (int)(i % kpadF);
+      long r = i / kpadF;
+      int co = (int)(r % cout), tap = (int)(r / cout);
+      packF[i] = __float2bfloat16_rn(k < cin ? w[((size_t)tap * cin + k) * cout + co] * sc : 0.f);
+    } else {
+      long j = i - nF;
+      int k = (int)(j % kpadD);
+      long r = j / kpadD;
+      int ci = (int)(r % cin), tap = (int)(r / cin);
+      packD[j] = __float2bfloat16_rn(k < cout ? w[((size_t)tap * cin + ci) * cout + k] * sc : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+struct PackGeo { int taps, kpadF, kpadD; size_t offD, bytes; };
+PackGeo pack_geo(const rcgan_conv_desc* d) {
+  PackGeo g;
+  g.taps = d->kh * d->kw;
+  g.kpadF = round_up(d->cin, BK);
+  g.kpadD = round_up(d->cout, BK);
+  g.offD = (size_t)g.taps * d->cout * g.kpadF;                       // elements
+  g.bytes = (g.offD + (size_t)g.taps * d->cin * g.kpadD) * sizeof(bf16);
+  return g;
+}
+bool fprop_ok(const rcgan_conv_desc* d) {
+  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && d->cin >= 32 && d->cout >= 16 && d->kh * d->kw <= MAX_TAPS;
+}
+bool wgrad_ok(const rcgan_conv_desc* d) {
+  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && d->ldy % 8 == 0 && d->cin >= 32 && d->cout >= 32 &&
+         d->ho * d->wo <= 1024 && d->wo <= 255 && d->ho <= 255;
+}
+bool dgrad_ok(const rcgan_conv_desc* d) {
+  return d->dtype == RCGAN_BF16 && d->ldy % 8 == 0 && d->cout >= 32 && d->cin >= 16 && d->kh * d->kw <= MAX_TAPS &&
+         (d->stride == 1 || d->stride == 2);
+}
+
+int make_wmap(CUtensorMap* map, const bf16* base, int kpad, int rows, int taps, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { rcgan_set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return RCGAN_ECUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)taps};
+  cuuint64_t gstr[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)kpad * 2 * rows};
+  cuuint32_t box[3] = {BK, (cuuint32_t)bn, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { rcgan_set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return RCGAN_ECUDA; }
   return 0;
 }
-int rcgan_tc_dgrad(const rcgan_conv_desc*, const void*, const void*, const float*, void*, int, int, float, int, cudaStream_t, int* handled) {
+
+template <int BN>
+int launch_tc(const TcParams& p, const CUtensorMap& map, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+    if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+    attr_done = true;
+  }
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
+  conv_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(p, map);
+  RCGAN_LAUNCH_CHECK("conv_tc");
+  return 0;
+}
+
+int run_tc(const TcParams& p, const bf16* wbase, int kpad, int rows, int taps, cudaStream_t st) {
+  const int bn = p.N <= 64 ? 64 : 128;
+  CUtensorMap map;
+  if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
+  return bn == 64 ? launch_tc<64>(p, map, st) : launch_tc<128>(p, map, st);
+}
+
+}  // namespace
+
+extern "C" size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d) {
+  if (!d || !(fprop_ok(d) || dgrad_ok(d))) return 0;
+  return pack_geo(d).bytes;
+}
+
+extern "C" int rcgan_conv_uses_tensor_cores(const rcgan_conv_desc* d, int direction) {
+  if (!d) return 0;
+  if (direction == 0) return fprop_ok(d) ? 1 : 0;
+  if (direction == 1) return dgrad_ok(d) ? 1 : 0;
+  if (direction == 2) return wgrad_ok(d) ? 1 : 0;
+  return 0;
+}
+
+extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scale_dev, void* pack, void* stream) {
+  RCGAN_CHECK_ARG(d && w && pack, "conv_wpack: null argument");
+  if (!(fprop_ok(d) || dgrad_ok(d))) { rcgan_set_error("conv_wpack: shape has no tensor-core pack"); return RCGAN_EUNSUPPORTED; }
+  PackGeo g = pack_geo(d);
+  long n = (long)(g.bytes / sizeof(bf16));
+  int grid = (int)((n + 255) / 256);
+  if (grid > RCGAN_NUM_SMS * 8) grid = RCGAN_NUM_SMS * 8;
+  bf16* pk = reinterpret_cast<bf16*>(pack);
+  wpack_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
+  RCGAN_LAUNCH_CHECK("conv_wpack");
+  return 0;
+}
+
+int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
+                   int act, float leak, cudaStream_t st, int* handled) {
   *handled = 0;
+  if (!fprop_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
+  PackGeo g = pack_geo(d);
+  TcParams p;
+  p.src = reinterpret_cast<const bf16*>(x);
+  p.SH = d->h; p.SW = d->w; p.ld_src = d->ldx; p.cvalid = round_up(d->cin, 8);
+  p.MH = d->ho; p.MW = d->wo; p.M = d->n * d->ho * d->wo;
+  p.by_mul = d->stride; p.by_add = -d->pad_t; p.bx_mul = d->stride; p.bx_add = -d->pad_l;
+  p.ntaps = g.taps; p.kb_per_tap = g.kpadF / BK;
+  for (int t = 0; t < g.taps; t++) { p.tdy[t] = (short)(t / d->kw); p.tdx[t] = (short)(t % d->kw); p.twi[t] = (short)t; }
+  p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->ho; p.OW = d->wo;
+  p.oy_mul = 1; p.oy_add = 0; p.ox_mul = 1; p.ox_add = 0; p.N = d->cout;
+  p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0;
+  if (int e = run_tc(p, reinterpret_cast<const bf16*>(wpack), g.kpadF, d->cout, g.taps, st)) return e;
+  *handled = 1;
+  return 0;
+}
+
+int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
+                   int act, float leak, int accumulate, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (!dgrad_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
+  PackGeo g = pack_geo(d);
+  const bf16* wD = reinterpret_cast<const bf16*>(wpack) + g.offD;
+  const int s = d->stride;
+  for (int py = 0; py < s; py++)
+    for (int px = 0; px < s; px++) {
+      TcParams p;
+      p.src = reinterpret_cast<const bf16*>(dy);
+      p.SH = d->ho; p.SW = d->wo; p.ld_src = d->ldy; p.cvalid = round_up(d->cout, 8);
+      p.MH = (d->h - py + s - 1) / s; p.MW = (d->w - px + s - 1) / s;
+      if (p.MH <= 0 || p.MW <= 0) continue;
+      p.M = d->n * p.MH * p.MW;
+      // input pixel iy = s*a + py receives tap ky iff (iy + pad_t - ky) % s == 0:  ky = kpar + s*j,  oy = a + cy - j
+      const int kpy = (py + d->pad_t) % s, kpx = (px + d->pad_l) % s;
+      const int cy = (py + d->pad_t - kpy) / s, cx = (px + d->pad_l - kpx) / s;
+      p.by_mul = 1; p.by_add = cy; p.bx_mul = 1; p.bx_add = cx;
+      int nt = 0;
+      for (int ky = kpy, jy = 0; ky < d->kh; ky += s, jy++)
+        for (int kx = kpx, jx = 0; kx < d->kw; kx += s, jx++) {
+          p.tdy[nt] = (short)(-jy); p.tdx[nt] = (short)(-jx); p.twi[nt] = (short)(ky * d->kw + kx);
+          nt++;
+        }
+      p.ntaps = nt; p.kb_per_tap = g.kpadD / BK;
+      p.out = dx; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldx; p.OH = d->h; p.OW = d->w;
+      p.oy_mul = s; p.oy_add = py; p.ox_mul = s; p.ox_add = px; p.N = d->cin;
+      p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate;
+      if (nt == 0) { rcgan_set_error("conv_tc dgrad: parity class without taps"); return RCGAN_EUNSUPPORTED; }
+      if (int e = run_tc(p, wD, g.kpadD, d->cin, g.taps, st)) return e;
+    }
+  *handled = 1;
+  return 0;
+}
+
+template <int BN>
+static int launch_wgrad_tc(const WgParams& p, const CUtensorMap& map, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM);
+    if (e != cudaSuccess) { rcgan_set_error("wgrad_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+    attr_done = true;
+  }
+  wgrad_tc_kernel<BN><<<grid, 192, WgCfg<BN>::SMEM, st>>>(p, map);
+  RCGAN_LAUNCH_CHECK("wgrad_tc");
+  return 0;
+}
+
+// dw (=|+=) x^T dy on the tensor cores.  dw must be zero-initialised by the caller path when !accumulate.
+int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st,
+                   int* handled) {
+  *handled = 0;
+  if (!wgrad_ok(d)) return 0;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { rcgan_set_error("wgrad_tc: cuTensorMapEncodeTiled unavailable"); return RCGAN_ECUDA; }
+  WgParams p;
+  p.x = reinterpret_cast<const bf16*>(x);
+  p.H = d->h; p.W = d->w; p.ldx = d->ldx; p.cvalid = round_up(d->cin, 8);
+  p.HO = d->ho; p.WO = d->wo; p.HW = d->ho * d->wo; p.Mpix = d->n * p.HW;
+  p.stride = d->stride; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.kw = d->kw;
+  p.cin = d->cin; p.cout = d->cout; p.cblks = (d->cin + 63) / 64; p.units = d->kh * d->kw * p.cblks;
+  p.kb_total = (p.Mpix + 127) / 128;
+  p.dw = dw;
+  const int bn = d->cout <= 64 ? 64 : 128;
+  const int tiles = ((p.units + 1) / 2) * ((d->cout + bn - 1) / bn);
+  int splits = (2 * RCGAN_NUM_SMS + tiles - 1) / tiles;        // aim for ~2 CTAs per SM worth of work items
+  int max_splits = (p.kb_total + 3) / 4;                        // at least 4 K blocks (512 pixels) per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  CUtensorMap map;
+  cuuint64_t gdim[2] = {(cuuint64_t)d->ldy, (cuuint64_t)p.Mpix};
+  cuuint64_t gstr[1] = {(cuuint64_t)d->ldy * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { rcgan_set_error("wgrad_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return RCGAN_ECUDA; }
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->kh * d->kw * d->cin * d->cout, st);
+    if (e != cudaSuccess) { rcgan_set_error("wgrad_tc: memset failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+  }
+  dim3 grid((p.units + 1) / 2, (d->cout + bn - 1) / bn, splits);
+  if (int e = (bn == 64 ? launch_wgrad_tc<64>(p, map, grid, st) : launch_wgrad_tc<128>(p, map, grid, st))) return e;
+  *handled = 1;
   return 0;
 }

@@ -116,12 +116,14 @@ __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const TX* __restr
   }
 }
 
-__global__ void bn_stats_finalize_kernel(Geo g, const float* __restrict__ ws, float eps, float decay, float* mm, float* mv,
-                                         float* __restrict__ save) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the chunks, Chan-merge their partials, then merge across lanes by shuffle
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(Geo g, const float* __restrict__ ws, float eps, float decay,
+                                                               float* mm, float* mv, float* __restrict__ save) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (ch >= g.c) return;
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int k = 0; k < g.nchunk; k++) {
+  for (int k = lane; k < g.nchunk; k += 32) {
     int r0 = k * g.chunk_rows;
     float nb = (float)(min(g.rows, r0 + g.chunk_rows) - r0);
     float mb = ws[(size_t)k * g.c + ch], m2b = ws[(size_t)(g.nchunk + k) * g.c + ch];
@@ -130,13 +132,27 @@ __global__ void bn_stats_finalize_kernel(Geo g, const float* __restrict__ ws, fl
     m2 += m2b + delta * delta * (n * nb / nt);
     n = nt;
   }
-  float var = m2 / n;
-  save[ch] = mean;
-  save[g.c + ch] = rsqrtf(var + eps);
-  if (mm) {
-    float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
-    mm[ch] = decay * mm[ch] + (1.f - decay) * mean;
-    mv[ch] = decay * mv[ch] + (1.f - decay) * unbiased;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+          m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+    float nt = n + nb;
+    if (nt > 0.f) {
+      float delta = mb - mean;
+      mean += delta * (nb / nt);
+      m2 += m2b + delta * delta * (n * nb / nt);
+    }
+    n = nt;
+  }
+  if (lane == 0) {
+    float var = m2 / n;
+    save[ch] = mean;
+    save[g.c + ch] = rsqrtf(var + eps);
+    if (mm) {
+      float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
+      mm[ch] = decay * mm[ch] + (1.f - decay) * mean;
+      mv[ch] = decay * mv[ch] + (1.f - decay) * unbiased;
+    }
   }
 }
 
@@ -216,27 +232,55 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restric
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(Geo g, float* __restrict__ ws, const float* __restrict__ scale,
-                                       const int* __restrict__ labels, int n_labels, float* __restrict__ dscale,
-                                       float* __restrict__ doffset, int accumulate_param) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel.  Unconditional norm (labels == NULL): lanes stride over the chunks and shuffle-reduce.
+// Conditional norm: the per-label sums need a scatter, so lane l owns label l (n_labels <= 32) and scans the chunks.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(Geo g, float* __restrict__ ws, const float* __restrict__ scale,
+                                                             const int* __restrict__ labels, int n_labels,
+                                                             float* __restrict__ dscale, float* __restrict__ doffset,
+                                                             int accumulate_param) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (ch >= g.c) return;
-  if (!accumulate_param)
-    for (int l = 0; l < n_labels; l++) { dscale[(size_t)l * g.c + ch] = 0.f; doffset[(size_t)l * g.c + ch] = 0.f; }
   float A = 0.f, B = 0.f;
-  for (int k = 0; k < g.nchunk; k++) {
-    int lab = labels ? labels[((long)k * g.chunk_rows) / g.hw] : 0;
-    float p1 = ws[(size_t)k * g.c + ch], p2 = ws[(size_t)(g.nchunk + k) * g.c + ch];
-    float sc = scale[(size_t)lab * g.c + ch];
-    A = fmaf(sc, p1, A);
-    B = fmaf(sc, p2, B);
-    doffset[(size_t)lab * g.c + ch] += p1;
-    dscale[(size_t)lab * g.c + ch] += p2;
+  if (!labels) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < g.nchunk; k += 32) {
+      s1 += ws[(size_t)k * g.c + ch];
+      s2 += ws[(size_t)(g.nchunk + k) * g.c + ch];
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float sc = scale[ch];
+    A = sc * s1; B = sc * s2;
+    if (lane == 0) {
+      doffset[ch] = accumulate_param ? doffset[ch] + s1 : s1;
+      dscale[ch] = accumulate_param ? dscale[ch] + s2 : s2;
+    }
+  } else {
+    for (int l0 = 0; l0 < n_labels; l0 += 32) {
+      const int l = l0 + lane;
+      float s1 = 0.f, s2 = 0.f;
+      if (l < n_labels) {
+        for (int k = 0; k < g.nchunk; k++) {
+          if (labels[((long)k * g.chunk_rows) / g.hw] == l) {
+            s1 += ws[(size_t)k * g.c + ch];
+            s2 += ws[(size_t)(g.nchunk + k) * g.c + ch];
+          }
+        }
+        const float sc = scale[(size_t)l * g.c + ch];
+        A = fmaf(sc, s1, A); B = fmaf(sc, s2, B);
+        size_t o = (size_t)l * g.c + ch;
+        doffset[o] = accumulate_param ? doffset[o] + s1 : s1;
+        dscale[o] = accumulate_param ? dscale[o] + s2 : s2;
+      }
+    }
+    A = warp_sum(A); B = warp_sum(B);
   }
-  float inv = 1.f / (float)g.rows;
-  float* AB = ws + (size_t)2 * g.nchunk * g.c;
-  AB[ch] = A * inv;
-  AB[g.c + ch] = B * inv;
+  if (lane == 0) {
+    float inv = 1.f / (float)g.rows;
+    float* AB = ws + (size_t)2 * g.nchunk * g.c;
+    AB[ch] = A * inv;
+    AB[g.c + ch] = B * inv;
+  }
 }
 
 template <typename TX, typename TY, int V>
@@ -319,7 +363,7 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
     size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
     BN_DISPATCH(xdtype, ydtype, g.V, bn_stats_partial_kernel<TX, VV><<<grid, 256, shb, st>>>((const TX*)x, g, (float*)ws));
     RCGAN_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(g, (const float*)ws, eps, decay, moving_mean, moving_var, save);
+    bn_stats_finalize_kernel<<<ceil_div(c, 8), 256, 0, st>>>(g, (const float*)ws, eps, decay, moving_mean, moving_var, save);
     RCGAN_LAUNCH_CHECK("bn_stats_finalize");
   } else {
     RCGAN_CHECK_ARG(moving_mean && moving_var, "bn_fwd: inference needs moving statistics");
@@ -348,7 +392,7 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
   BN_DISPATCH(xdtype, ydtype, g.V, bn_bwd_partial_kernel<TX, TY, VV><<<grid, 256, shb, st>>>(
                                        (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws));
   RCGAN_LAUNCH_CHECK("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(g, (float*)ws, scale, labels, n_labels, dscale, doffset,
+  bn_bwd_finalize_kernel<<<ceil_div(c, 8), 256, 0, st>>>(g, (float*)ws, scale, labels, n_labels, dscale, doffset,
                                                             accumulate_param);
   RCGAN_LAUNCH_CHECK("bn_bwd_finalize");
   const float* AB = (const float*)ws + (size_t)2 * g.nchunk * c;

@@ -233,6 +233,7 @@ class Program:
         self.loss_names = []
         self.losses = None          # fp32 [n_losses] device
         self.updates = []           # (dst tensor, src tensor) state assignments applied after backward
+        self.packs = {}             # id(weight base) -> bf16 tensor-core weight pack (torch uint8 buffer)
         self.finalized = False
 
     def __enter__(self):
@@ -258,6 +259,19 @@ class Program:
     def add(self, op):
         self.ops.append(op)
         return op
+
+    def weight_pack(self, w, desc):
+        """bf16 tensor-core pack of a conv weight, shared by every op of this program that uses the weight.
+        Returns (buffer or None, owner): the owner (first user in program order) refreshes the pack each run."""
+        nbytes = _C.load().rcgan_conv_wpack_bytes(desc)
+        if nbytes == 0:
+            return None, False
+        key = id(w.base)
+        if key in self.packs:
+            assert self.packs[key].numel() == nbytes
+            return self.packs[key], False
+        self.packs[key] = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return self.packs[key], True
 
     def loss_slot(self, name):
         self.loss_names.append(name)

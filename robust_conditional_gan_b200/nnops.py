@@ -15,6 +15,11 @@ def dp(t):
     return None if t is None else t.data.data_ptr()
 
 
+def pp(buf):
+    """device pointer of a raw torch buffer (None -> NULL)"""
+    return None if buf is None else buf.data_ptr()
+
+
 def gp(t):
     return None if t is None or t.grad is None else t.grad.data_ptr()
 
@@ -52,6 +57,7 @@ class ConvOp(Op):
         self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
+        self.pack, self.pack_owner = prog.weight_pack(w, self.desc)
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -61,7 +67,9 @@ class ConvOp(Op):
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
     def forward(self, prog):
-        call('rcgan_conv2d_fprop', self.desc, dp(self.x), dp(self.w), None, dp(self.b), dp(self.y), self.y.dtype, self.act,
+        if self.pack_owner:
+            call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.pack), stream_ptr())
+        call('rcgan_conv2d_fprop', self.desc, dp(self.x), dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, stream_ptr())
 
     def backward(self, prog):
@@ -73,8 +81,8 @@ class ConvOp(Op):
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if nx:
-            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None, None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0,
-                 self.acc_x, st)
+            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype,
+                 _C.ACT_NONE, 0.0, self.acc_x, st)
         if nw:
             call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
         if nb and self.b is not None:
@@ -102,6 +110,7 @@ class DeconvOp(Op):
         self.desc = ConvDesc(n, oh, ow, cout, h, wd, cin, kh, kw, stride, pt, pl, self.y.ld, x.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
+        self.pack, self.pack_owner = prog.weight_pack(w, self.desc)
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -112,7 +121,9 @@ class DeconvOp(Op):
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
     def forward(self, prog):
-        call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), None, dp(self.b), dp(self.y), self.y.dtype, self.act,
+        if self.pack_owner:
+            call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.pack), stream_ptr())
+        call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, 0, stream_ptr())
 
     def backward(self, prog):
@@ -124,7 +135,8 @@ class DeconvOp(Op):
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if nx:
-            call('rcgan_conv2d_fprop', self.desc, dy, dp(self.w), None, None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, st)
+            call('rcgan_conv2d_fprop', self.desc, dy, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE,
+                 0.0, st)
         if nw:
             call('rcgan_conv2d_wgrad', self.desc, dy, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
         if nb and self.b is not None:

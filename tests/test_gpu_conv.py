@@ -134,3 +134,116 @@ def test_bad_args_fail_loudly(lib):
     d = ConvDesc(1, 4, 4, 8, 4, 4, 8, 3, 3, 1, 1, 1, 4, 8, _C.F32)      # ldx < cin
     with pytest.raises(_C.RcganError, match='ld smaller'):
         call('rcgan_conv2d_fprop', d, None, None, None, None, None, 0, 0, 0.0, st())
+
+
+# ----------------------------------------------------------------------------- tcgen05 path
+TC_SHAPES = [
+    (4, 14, 14, 64, 64, 5, 2, 0, 0),      # d_h1_conv
+    (4, 7, 7, 64, 64, 5, 2, 0, 0),        # d_h2_conv
+    (40, 4, 4, 64, 64, 5, 2, 0, 0),       # d_h3_conv
+    (3, 14, 14, 128, 138, 5, 2, 0, 6),    # g_h2 (deconv = dgrad), y side ld 144
+    (5, 28, 28, 64, 74, 5, 2, 0, 6),      # odd channel counts, ld 80
+    (4, 32, 32, 128, 128, 3, 1, 0, 0),    # CIFAR D 3x3
+    (2, 16, 16, 256, 256, 3, 1, 0, 0),    # CIFAR G 3x3
+    (2, 8, 8, 1024, 256, 1, 1, 0, 0),     # CIFAR G shortcut 1x1
+    (300, 1, 1, 110, 1024, 1, 1, 2, 0),   # g_h0_lin
+    (70, 1, 1, 1034, 896, 1, 1, 6, 0),    # g_h1_lin (N reduced)
+    (130, 1, 1, 64, 32, 1, 1, 0, 0),      # small N
+]
+
+
+def pack_for(lib, d, wt):
+    nb = lib.rcgan_conv_wpack_bytes(d)
+    assert nb > 0
+    pack = torch.zeros(nb, dtype=torch.uint8, device='cuda')
+    wd = dev(wt)
+    call('rcgan_conv_wpack', d, wd.data_ptr(), None, pack.data_ptr(), st())
+    return pack, wd
+
+
+@pytest.mark.parametrize('shape', TC_SHAPES)
+def test_tc_fprop(lib, shape):
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, _C.BF16)
+    n, cout, s = shape[0], shape[4], shape[6]
+    assert lib.rcgan_conv_uses_tensor_cores(d, 0) == 1
+    pack, wd = pack_for(lib, d, wt)
+    bd = dev(b)
+    ref = O.lrelu(O.conv2d(x.double(), wt.to(torch.bfloat16).double(), s) + b.double())
+    for odt in (_C.BF16, _C.F32):
+        y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=TD[odt])
+        call('rcgan_conv2d_fprop', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y.data_ptr(), odt,
+             _C.ACT_LRELU, 0.2, st())
+        torch.cuda.synchronize()
+        assert relerr(y[..., :cout].float(), ref) < (6e-3 if odt == _C.BF16 else 2e-5), odt
+        if ldy > cout:
+            assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('shape', TC_SHAPES)
+def test_tc_dgrad_and_deconv(lib, shape):
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, _C.BF16)
+    n, h, w, cin, cout, k, s = shape[:7]
+    assert lib.rcgan_conv_uses_tensor_cores(d, 1) == 1
+    pack, wd = pack_for(lib, d, wt)
+    wq = wt.to(torch.bfloat16).double()
+    xr = x.double().requires_grad_(True)
+    O.conv2d(xr, wq, s).backward(dy.double())
+    dx = torch.zeros(n, h, w, ldx, device='cuda', dtype=torch.float32)
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, dx.data_ptr(), _C.F32, _C.ACT_NONE, 0.0,
+         0, st())
+    torch.cuda.synchronize()
+    assert relerr(dx[..., :cin], xr.grad) < 2e-5
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, dx.data_ptr(), _C.F32, _C.ACT_NONE, 0.0,
+         1, st())
+    assert relerr(dx[..., :cin], 2 * xr.grad) < 2e-5                 # accumulate
+    bias = torch.randn(cin, generator=torch.Generator().manual_seed(5))
+    out = torch.zeros(n, h, w, ldx, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), keep(dev(bias)), out.data_ptr(), _C.BF16,
+         _C.ACT_SIGMOID, 0.0, 0, st())
+    if s == 2:
+        ref = torch.sigmoid(O.conv2d_transpose(dy.double(), wq, (h, w), s) + bias.double())
+    else:
+        ref = torch.sigmoid(xr.grad + bias.double())
+    assert relerr(out[..., :cin].float(), ref) < 6e-3
+
+
+def test_tc_full_size_linearity(lib):
+    """BASELINE config-2 size (d_h1_conv at batch 1024): conv(a*x1 + x2) == a*conv(x1) + conv(x2) through the
+    tcgen05 path (fp32 output), a size-independent property where the oracle would take minutes."""
+    shape = (1024, 14, 14, 64, 64, 5, 2, 0, 0)
+    n, h, w, cin, cout, k, s = shape[:7]
+    g = torch.Generator().manual_seed(9)
+    d = ConvDesc(n, h, w, cin, 7, 7, cout, k, k, s, 1, 1, cin, cout, _C.BF16)
+    wt = torch.randn(k, k, cin, cout, generator=g) * 0.1
+    pack, wd = pack_for(lib, d, wt)
+    # power-of-two scale and disjoint-exponent inputs keep a*x1 + x2 exactly representable in bf16
+    x1 = torch.randint(-4, 5, (n, h, w, cin), generator=g).float()
+    x2 = torch.randint(-4, 5, (n, h, w, cin), generator=g).float()
+    outs = []
+    for xin in (x1, x2, 2 * x1 + x2):
+        y = torch.zeros(n, 7, 7, cout, device='cuda')
+        xd = dev(xin, torch.bfloat16)
+        call('rcgan_conv2d_fprop', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, y.data_ptr(), _C.F32, _C.ACT_NONE, 0.0,
+             st())
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert relerr(outs[2], 2 * outs[0] + outs[1]) < 1e-5
+    assert float(outs[0].abs().max()) > 0
+
+
+@pytest.mark.parametrize('shape', TC_SHAPES + [(256, 14, 14, 64, 64, 5, 2, 0, 0), (64, 32, 32, 128, 128, 3, 1, 0, 0)])
+def test_tc_wgrad(lib, shape):
+    """tcgen05 wgrad (MN-major operands, split-K with fp32 atomics) vs the fp64 oracle on bf16-exact inputs"""
+    d, x, wt, b, dy, xd, dyd, _ = make(shape, _C.BF16)
+    s = shape[6]
+    assert lib.rcgan_conv_uses_tensor_cores(d, 2) == 1
+    wr = wt.double().requires_grad_(True)
+    O.conv2d(x.double(), wr, s).backward(dy.double())
+    nb = lib.rcgan_conv2d_wgrad_workspace(d)
+    ws = torch.zeros(max(nb, 4), dtype=torch.uint8, device='cuda')
+    dw = torch.full(wt.shape, 3.0, device='cuda')
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
+    torch.cuda.synchronize()
+    assert relerr(dw, wr.grad) < 2e-5
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
+    assert relerr(dw, 2 * wr.grad) < 2e-5
