@@ -1,0 +1,405 @@
+"""Drop-in for the hot path of cifar10/gan_resnet.py: the SN-ResNet generator / projection discriminator
+(:199-421), the permutation classifier (:458-483), the RCGAN loss graph (:498-786) and one training iteration
+(:919-947), recorded as static programs of librcgan_b200.so launches.
+
+Towers (`DEVICES`, gan_resnet.py:183-192) are ranks here: each process holds one tower's shard (n = BATCH_SIZE / T),
+computes its own conditional-BN statistics (the reference does per tower) and the gradient is the NCCL mean over ranks.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _C, scope as S
+from ..graph import I32, Program, VariableStore, tf_adam_lr
+from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
+                     SoftmaxRowsOp, Upsample2Op, adam_step)
+from . import ops as lib_ops
+
+NO_OPS = 'NO_OPS'
+Z_DIM, VOCAB_SIZE, EMBEDDING_DIM, IMG_SIZE, IMG_DIM, OUTPUT_DIM = 128, 10, 300, 32, 3, 3072
+N_CRITIC, GEN_BS_MULTIPLE = 5, 2
+
+
+def default_flags(**kw):
+    """cifar10/gan_resnet.py:40-76 (hot-path subset)."""
+    f = SimpleNamespace(dataset='cifar', algorithm='rcgan', alpha=0.8, batch_size=64, niters=50000, lr=2e-4, ngpus=2,
+                        multi_gpu_multi_batch=True, confuse_init=False, confuse_init_diag=0.2, confuse_multiplier=1.0,
+                        confuse_lr_decay=False, perm_classifier=False, perm_multiplier=1.0, perm_type='linear')
+    for k, v in kw.items():
+        setattr(f, k, v)
+    return f
+
+
+class Net:
+    """The module-level constants + network functions of gan_resnet.py, bound to one configuration."""
+
+    def __init__(self, algorithm, dim_g=128, dim_d=128):
+        self.ALGORITHM, self.DIM_G, self.DIM_D = algorithm, dim_g, dim_d
+
+    # gan_resnet.py:199-205
+    @staticmethod
+    def nonlinearity(x, activation_fn='relu', leakiness=0.2):
+        return ActOp(x, 'relu' if activation_fn == 'relu' else 'lrelu', leakiness).y
+
+    def Normalize(self, name, inputs, labels=None, fuse_act=None):
+        """:207-228 with the shipped constants (CONDITIONAL, NORMALIZATION_G, not NORMALIZATION_D, not ACGAN):
+        conditional batch norm in G, identity in D."""
+        with S.variable_scope(name):
+            if 'G.' in name and labels is not None:
+                return lib_ops.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, fuse_act=fuse_act)
+        return ActOp(inputs, fuse_act).y if fuse_act else inputs
+
+    @staticmethod
+    def ConvMeanPool(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
+                     inputs_norm=False, he_init=True, biases=True):
+        """:231-241"""
+        out = lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
+                             update_collection=update_collection, he_init=he_init, biases=biases)
+        return Pool2Op(out).y
+
+    @staticmethod
+    def MeanPoolConv(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
+                     inputs_norm=False, he_init=True, biases=True):
+        """:244-256"""
+        out = Pool2Op(inputs).y
+        return lib_ops.Conv2D(out, out.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
+                              update_collection=update_collection, he_init=he_init, biases=biases)
+
+    @staticmethod
+    def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
+                     inputs_norm=False, he_init=True, biases=True, pre_norm=False):
+        """:259-272"""
+        out = Upsample2Op(inputs).y
+        return lib_ops.Conv2D(out, out.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
+                              update_collection=update_collection, he_init=he_init, biases=biases, pre_norm=pre_norm)
+
+    def ResidualBlock(self, inputs, input_dim, output_dim, filter_size, name, spectral_normed=False, update_collection=None,
+                      inputs_norm=False, resample=None, labels=None, biases=True):
+        """:275-328 pre-activation block."""
+        kw = dict(spectral_normed=spectral_normed, update_collection=update_collection, biases=biases)
+        if resample == 'down':
+            conv_1 = lambda x, **k: lib_ops.Conv2D(x, input_dim, input_dim, **k)
+            conv_2 = lambda x, **k: self.ConvMeanPool(x, output_dim, **k)
+            conv_shortcut = self.ConvMeanPool
+        elif resample == 'up':
+            conv_1 = lambda x, **k: self.UpsampleConv(x, output_dim, **k)
+            conv_shortcut = self.UpsampleConv
+            conv_2 = lambda x, **k: lib_ops.Conv2D(x, output_dim, output_dim, **k)
+        elif resample is None:
+            conv_shortcut = lambda x, output_dim, **k: lib_ops.Conv2D(x, input_dim, output_dim, **k)
+            conv_1 = lambda x, **k: lib_ops.Conv2D(x, input_dim, output_dim, **k)
+            conv_2 = lambda x, **k: lib_ops.Conv2D(x, output_dim, output_dim, **k)
+        else:
+            raise Exception('invalid resample value')
+        if output_dim == input_dim and resample is None:
+            shortcut = inputs
+        else:
+            shortcut = conv_shortcut(inputs, output_dim=output_dim, filter_size=1, name=name + '.Shortcut', he_init=False, **kw)
+        output = self.Normalize(name + '.N1', inputs, labels=labels, fuse_act='relu')
+        output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, **kw)
+        output = self.Normalize(name + '.N2', output, labels=labels, fuse_act='relu')
+        output = conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, **kw)
+        return AddOp(shortcut, output).y
+
+    def OptimizedResBlockDisc1(self, inputs, spectral_normed=False, update_collection=None, inputs_norm=False, biases=True):
+        """:331-353"""
+        kw = dict(spectral_normed=spectral_normed, update_collection=update_collection, biases=biases)
+        shortcut = self.MeanPoolConv(inputs, output_dim=self.DIM_D, filter_size=1, name='D.Block.1.Shortcut', he_init=False, **kw)
+        output = lib_ops.Conv2D(inputs, IMG_DIM, self.DIM_D, 3, 1, 'D.Block.1.Conv1', he_init=True, fuse_act='relu', **kw)
+        output = self.ConvMeanPool(output, self.DIM_D, filter_size=3, name='D.Block.1.Conv2', he_init=True, **kw)
+        return AddOp(shortcut, output).y
+
+    def Generator(self, n_samples_, labels, noise=None, reuse=False):
+        """:356-371.  noise: graph tensor [n,128] (the in-graph tf.random_normal is replaced by a fed tensor).
+        Returns the NHWC image tensor [n,32,32,3] (the reference flattens it to [n,3072])."""
+        D = self.DIM_G
+        with S.variable_scope("Generator"):
+            output = lib_ops.Linear(noise, 128, 4 * 4 * D * 8, 'G.Input')
+            output = output.view([n_samples_, 4, 4, D * 8])
+            output = self.ResidualBlock(output, D * 8, D * 2, 3, 'G.Block.1', resample='up', labels=labels, biases=True)
+            output = self.ResidualBlock(output, D * 2, D * 2, 3, 'G.Block.2', resample='up', labels=labels, biases=True)
+            output = self.ResidualBlock(output, D * 2, D * 2, 3, 'G.Block.3', resample='up', labels=labels, biases=True)
+            output = self.Normalize('G.OutputNorm', output, labels, fuse_act='relu')
+            return lib_ops.Conv2D(output, D * 2, IMG_DIM, 3, 1, 'G.Output', he_init=False, fuse_act='tanh')
+
+    def Discriminator(self, inputs, labels, update_collection=None, reuse=False):
+        """:374-412.  Returns (output [N, DIM_D], output_wgan [N,1])."""
+        D = self.DIM_D
+        with S.variable_scope("Discriminator"):
+            output = self.OptimizedResBlockDisc1(inputs, spectral_normed=True, update_collection=update_collection, biases=True)
+            output = self.ResidualBlock(output, D, D, 3, 'D.Block.2', spectral_normed=True, update_collection=update_collection,
+                                        resample='down', labels=None, biases=True)
+            for i in (3, 4, 5, 6):
+                output = self.ResidualBlock(output, D, D, 3, 'D.Block.%d' % i, spectral_normed=True,
+                                            update_collection=update_collection, resample=None, labels=None, biases=True)
+            output = MeanHWOp(output, relu=True).y                 # nonlinearity + reduce_mean(axis=[1,2])
+            out32 = CastOp(output, _C.F32).y
+            output_wgan = lib_ops.Linear(out32, D, 1, 'D.Output', spectral_normed=True, update_collection=update_collection)
+            return out32, output_wgan
+
+    def Discriminator_projection(self, labels, update_collection=None, reuse=False):
+        """:414-421.  labels None -> the embeddings of all VOCAB_SIZE classes [10, DIM_D]."""
+        with S.variable_scope("Discriminator"):
+            embedding_y = lib_ops.embed_y(labels, VOCAB_SIZE, EMBEDDING_DIM)
+            return lib_ops.Linear(embedding_y, EMBEDDING_DIM, self.DIM_D, 'D.Embedding_y', spectral_normed=True,
+                                  update_collection=update_collection, biases=True)
+
+    @staticmethod
+    def perm_classifier(x, reuse=False):
+        """:458-466 (perm_type 'linear'); x fp32 [n,32,32,3]."""
+        with S.variable_scope("Discriminator"):
+            flat = x.view([x.shape[0], OUTPUT_DIM])
+            return lib_ops.Linear(flat, OUTPUT_DIM, VOCAB_SIZE, 'D.d_perm_classifier_h1', spectral_normed=True, biases=True)
+
+
+def _group_of(name):
+    """gan_resnet.py:788-800: optimizer ownership by substring."""
+    if name == 'confusion_logits':
+        return 'c'
+    if 'Discriminator' in name:
+        return 'd'
+    if 'Generator' in name:
+        return 'g'
+    return None
+
+
+def lr_decay(it):
+    """:700-703"""
+    return max(0., 1. - it / 100000.) if it < 50000 else 0.5
+
+
+class RCGANCifar(object):
+    """The graph of gan_resnet.main() (:498-817) for ONE tower and its training iteration (:919-947)."""
+
+    def __init__(self, flags=None, tower_batch=32, device='cuda', precision='bf16', seed=0, world_size=1, rank=0, dim=128,
+                 use_cuda_graph=True):
+        self.FLAGS = flags if flags is not None else default_flags()
+        self.n = tower_batch                       # BATCH_SIZE / len(DEVICES)
+        self.device = torch.device(device)
+        self.act_dtype = {'bf16': _C.BF16, 'fp32': _C.F32}[precision]
+        self.world_size, self.rank, self.seed, self.dim = world_size, rank, seed, dim
+        self.use_cuda_graph = use_cuda_graph
+        if self.FLAGS.algorithm not in ('rcgan', 'rcgan-u', 'biased', 'unbiased'):
+            raise ValueError('unknown algorithm ' + str(self.FLAGS.algorithm))
+        if getattr(self.FLAGS, 'perm_type', 'linear') != 'linear':
+            raise NotImplementedError("perm_type '2layer' is not built")
+        if not _C.load().rcgan_device_ok():
+            raise _C.RcganError('rcgan_b200 needs an sm_100 device: ' + _C.last_error())
+        a = self.FLAGS.alpha
+        self.C_ALPHA = ((1 - a) / 9.0) * np.ones((10, 10)) + (a - (1 - a) / 9.0) * np.eye(10)   # :106
+        self.build()
+
+    # ------------------------------------------------------------------ graph
+    def _confusion(self, prog):
+        """:498-524"""
+        F = self.FLAGS
+        if F.algorithm == 'rcgan-u':
+            def init(shape):
+                if F.confuse_init:
+                    aa = 7.0 if F.confuse_init_diag > 0.99 else np.log(VOCAB_SIZE * F.confuse_init_diag / (1. - F.confuse_init_diag))
+                    aa = min(7.0, aa)
+                    ci = (0 - aa / VOCAB_SIZE) * np.ones([VOCAB_SIZE, VOCAB_SIZE], dtype=np.float32)
+                    np.fill_diagonal(ci, aa - aa / VOCAB_SIZE)
+                    return torch.as_tensor(ci)
+                lim = math.sqrt(6.0 / (2 * VOCAB_SIZE))
+                return (torch.rand(tuple(shape), generator=S.init_generator()) * 2 - 1) * lim
+            return SoftmaxRowsOp(S.get_variable('confusion_logits', [VOCAB_SIZE, VOCAB_SIZE], init)).y
+        C = prog.new((VOCAB_SIZE, VOCAB_SIZE), _C.F32)
+        C.data.copy_(torch.as_tensor(self.C_ALPHA, dtype=torch.float32).reshape(-1))
+        return C
+
+    def _eye(self, prog):
+        if not hasattr(prog, '_eye'):
+            prog._eye = prog.new((VOCAB_SIZE, VOCAB_SIZE), _C.F32)
+            prog._eye.data.copy_(torch.eye(VOCAB_SIZE, device=self.device).reshape(-1))
+        return prog._eye
+
+    def build(self):
+        F, n, dev = self.FLAGS, self.n, self.device
+        alg = F.algorithm
+        net = self.net = Net(alg, self.dim, self.dim)
+        self.store = VariableStore(dev, _group_of)
+        S.set_store(self.store, self.seed)
+        onehot = lambda prog, lab: GatherRowsOp(self._eye(prog), lab).out
+        # ---------------- D step (:526-697)
+        self.d_prog = dp_ = Program('d_step', dev, self.act_dtype)
+        with dp_:
+            raw = dp_.input('all_real_data_int', [n, OUTPUT_DIM], I32)
+            labels = dp_.input('all_real_labels', [n, 1], I32)
+            labels_random = dp_.input('all_random_labels', [n, 1], I32)
+            labels_biased = dp_.input('all_labels_biased', [n, 1], I32)
+            inv_w = dp_.input('all_labels_inv_weights', [n, VOCAB_SIZE])
+            noise = dp_.input('noise', [n, Z_DIM])
+            dq = dp_.input('dequant_noise', [n, OUTPUT_DIM])           # tf.random_uniform(0, 1/128), fed (zeros for parity)
+            real32 = PreprocessCifarOp(raw, dq, _C.F32).y
+            real = CastOp(real32, self.act_dtype).y
+            fake = net.Generator(n, labels_random, noise=CastOp(noise, self.act_dtype).y)
+            h_r, psi_r = net.Discriminator(real, labels, update_collection=None)
+            h_f, psi_f = net.Discriminator(fake, labels_random, update_collection=None, reuse=True)
+            V = net.Discriminator_projection(None, update_collection=None)
+            w_real = inv_w if alg == 'unbiased' else onehot(dp_, labels)
+            if alg == 'rcgan-u':
+                w_fake = GatherRowsOp(self._confusion(dp_), labels_random).out
+            elif alg == 'rcgan':
+                w_fake = onehot(dp_, labels_biased)
+            else:
+                w_fake = onehot(dp_, labels_random)
+            self.disc_real = ChannelLossOp(h_r, psi_r, V, w_real, _C.HINGE_D_REAL, 'disc_real_l').logits
+            self.disc_fake = ChannelLossOp(h_f, psi_f, V, w_fake, _C.HINGE_D_FAKE, 'disc_fake_l').logits
+            if F.perm_classifier:
+                SigmoidCEOp(net.perm_classifier(real32), onehot(dp_, labels), 'perm_classifier_real_loss', 1.0)
+        # ---------------- G step (:715-786)
+        self.g_prog = gp_ = Program('g_step', dev, self.act_dtype)
+        with gp_:
+            m = GEN_BS_MULTIPLE * n
+            noise = gp_.input('noise', [m, Z_DIM])
+            lab_rand = gp_.input('all_random_labels_G', [m, 1], I32)
+            lab_bias = gp_.input('all_labels_biased_G', [m, 1], I32)
+            fakeG = net.Generator(m, lab_rand, noise=CastOp(noise, self.act_dtype).y, reuse=True)
+            h, psi = net.Discriminator(fakeG, lab_bias, update_collection=NO_OPS, reuse=True)
+            V = net.Discriminator_projection(None, update_collection=None, reuse=True)
+            if alg == 'rcgan-u':
+                w = GatherRowsOp(self._confusion(gp_), lab_rand).out
+            elif alg == 'rcgan':
+                w = onehot(gp_, lab_bias)
+            else:
+                w = onehot(gp_, lab_rand)
+            ChannelLossOp(h, psi, V, w, _C.HINGE_G, 'gen_wgan')
+            if F.perm_classifier:
+                SigmoidCEOp(net.perm_classifier(CastOp(fakeG, _C.F32).y, reuse=True), onehot(gp_, lab_rand),
+                            'perm_classifier_fake_loss', F.perm_multiplier)
+            self.fake_G = fakeG
+        self.store.finalize()
+        V_ = self.store.vars
+        self.disc_params = [v for k, v in V_.items() if v.trainable and 'Discriminator' in k]
+        self.gen_params = [v for k, v in V_.items() if v.trainable and 'Generator' in k]
+        self.c_params = [V_['confusion_logits']] if 'confusion_logits' in V_ else []
+        self.d_prog.finalize(self.disc_params)
+        self.g_prog.finalize(self.gen_params + self.c_params)
+        self.groups = {k: g for k, g in self.store.groups.items()}
+        self.lr_dev = {k: torch.zeros(1, dtype=torch.float32, device=dev) for k in self.groups}
+        self._lr_ring = torch.zeros(4096, dtype=torch.float32).pin_memory()
+        self._lr_pos = 0
+        self._graphs = {}
+        self._host_losses = {p.name: torch.zeros(max(len(p.loss_names), 1), dtype=torch.float32).pin_memory()
+                             for p in (self.d_prog, self.g_prog)}
+        self.iteration = 0
+
+    # ------------------------------------------------------------------ steps
+    def _push_lr(self, key, value):
+        i = self._lr_pos
+        self._lr_pos = (i + 1) % self._lr_ring.numel()
+        self._lr_ring[i] = value
+        self.lr_dev[key].copy_(self._lr_ring[i:i + 1], non_blocking=True)
+
+    def _allreduce(self, group):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(group.grads)
+
+    def _body_a(self, prog, keys):
+        for k in keys:
+            if k in self.groups:
+                g = self.groups[k]
+                _C.call('rcgan_zero', g.grads.data_ptr(), g.numel * 4, _C.stream_ptr())
+        prog.run_forward()
+        prog.run_backward()
+
+    def _body_b(self, prog, keys):
+        for k in keys:
+            if k in self.groups:
+                adam_step(self.groups[k], self.lr_dev[k], 0.0, 0.9, 1e-8, 1.0 / self.world_size)
+        prog.run_updates()
+
+    def _run(self, name, fn):
+        if not self.use_cuda_graph:
+            fn()
+            return
+        g = self._graphs.get(name)
+        if g is None:
+            snap = self._snapshot()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._restore(snap)
+            self._graphs[name] = g
+        g.replay()
+
+    def _snapshot(self):
+        snap = {n: v.data.clone() for n, v in self.store.vars.items()}
+        for k, g in self.groups.items():
+            snap['__m_' + k], snap['__v_' + k] = g.m.clone(), g.v.clone()
+        return snap
+
+    def _restore(self, snap):
+        for n, v in self.store.vars.items():
+            v.data.copy_(snap[n])
+        for k, g in self.groups.items():
+            g.m.copy_(snap['__m_' + k]); g.v.copy_(snap['__v_' + k])
+
+    def _step(self, prog, keys, tag, lrs):
+        for k in keys:
+            if k in self.groups:
+                self.groups[k].t += 1
+                self._push_lr(k, tf_adam_lr(lrs[k], 0.0, 0.9, self.groups[k].t))
+        if self.world_size > 1:
+            self._run(tag + '_a', lambda: self._body_a(prog, keys))
+            for k in keys:
+                if k in self.groups:
+                    self._allreduce(self.groups[k])
+            self._run(tag + '_b', lambda: self._body_b(prog, keys))
+        else:
+            self._run(tag, lambda: (self._body_a(prog, keys), self._body_b(prog, keys)))
+
+    def d_step(self, it=None):
+        it = self.iteration if it is None else it
+        self._step(self.d_prog, ('d',), 'd', {'d': self.FLAGS.lr * lr_decay(it)})
+
+    def g_step(self, it=None):
+        it = self.iteration if it is None else it
+        F = self.FLAGS
+        clr = F.lr * F.confuse_multiplier * (lr_decay(it) if F.confuse_lr_decay else 1.0)
+        self._step(self.g_prog, ('g', 'c'), 'g', {'g': F.lr * lr_decay(it), 'c': clr})
+
+    def feed(self, prog, **feeds):
+        for name, src in feeds.items():
+            if src is None:
+                continue
+            t = prog.inputs[name]
+            src = torch.as_tensor(src)
+            want = t.data.dtype
+            if src.dtype != want:
+                src = src.to(want)
+            t.data.copy_(src.reshape(-1), non_blocking=True)
+
+    def fetch_losses(self):
+        for p in (self.d_prog, self.g_prog):
+            self._host_losses[p.name].copy_(p.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = self.d_prog.loss_dict(self._host_losses['d_step'])
+        out.update(self.g_prog.loss_dict(self._host_losses['g_step']))
+        return out
+
+    def train_iteration(self, d_feeds, g_feeds=None, fetch=True):
+        """One iteration of gan_resnet.py:919-947: [G(+C) step if iteration > 0] then N_CRITIC D steps.
+        d_feeds: list of N_CRITIC feed dicts (or one dict reused); g_feeds: feed dict of the G step."""
+        if self.iteration > 0:
+            if g_feeds:
+                self.feed(self.g_prog, **g_feeds)
+            self.g_step()
+        for i in range(N_CRITIC):
+            f = d_feeds[i] if isinstance(d_feeds, (list, tuple)) else d_feeds
+            if f:
+                self.feed(self.d_prog, **f)
+            self.d_step()
+        self.iteration += 1
+        return self.fetch_losses() if fetch else None

@@ -18,7 +18,8 @@ import torch
 from . import _C
 from ._C import ConvDesc, call, ptr, stream_ptr
 
-TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16}
+I32 = 100   # host-side dtype tag for integer label tensors (never passed to the library as an activation dtype)
+TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16, I32: torch.int32}
 
 
 def same_pad(size, k, stride):

@@ -335,6 +335,7 @@ class SpectralNormOp(Op):
         prog.ws.request(lib.rcgan_sn_workspace(self.m, self.c))
         self.inputs, self.outputs = (W,), (self.wbar,)
         prog.add(self)
+        self.updates_u = bool(update)
         if update:
             prog.add_update(u, self.u_new)
 
@@ -619,6 +620,25 @@ class ConcatRowsOp(Op):
         if self.need[1]:
             call('rcgan_copy_acc', gp(self.y) + self.a.numel() * self._esz(), gp(self.b), self.b.numel(), self.a.dtype,
                  self.acc_b, st)
+
+
+class PreprocessCifarOp(Op):
+    """int32 CHW [n,3072] -> 2*(v/256 - .5) (+ dequantisation noise) -> NHWC (cifar10/gan_resnet.py:548-552)."""
+
+    def __init__(self, raw, noise, dtype):
+        prog = cur()
+        self.raw, self.noise = raw, noise
+        self.n = raw.shape[0]
+        self.y = prog.new((self.n, 32, 32, 3), dtype)
+        self.inputs, self.outputs = (), (self.y,)
+        prog.add(self)
+
+    def plan(self, prog):
+        self.y.base.needs_grad = False
+
+    def forward(self, prog):
+        call('rcgan_preprocess_cifar', self.raw.data.data_ptr(), None if self.noise is None else self.noise.data.data_ptr(),
+             dp(self.y), self.n, self.y.dtype, stream_ptr())
 
 
 def adam_step(group, lr_t_dev, b1, b2, eps, grad_scale=1.0):

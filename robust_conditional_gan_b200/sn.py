@@ -22,5 +22,15 @@ def spectral_normed_weight(W, u=None, num_iters=1, update_collection=None, with_
     with S.variable_scope('spectral_norm'):
         if u is None:
             u = S.get_variable('u', [1, W.shape[-1]], _trunc_normal, trainable=False)
-    op = SpectralNormOp(W, u, update=(update_collection != NO_OPS))
+    # one power iteration per weight per program run: every call site of a run computes the same (W, u) -> W_bar
+    # (the reference's repeated assigns are idempotent), so the op is shared.
+    from .graph import cur
+    prog = cur()
+    cache = prog.__dict__.setdefault('sn_cache', {})
+    op = cache.get(id(W))
+    if op is None:
+        op = cache[id(W)] = SpectralNormOp(W, u, update=False)
+    if update_collection != NO_OPS and not op.updates_u:
+        op.updates_u = True
+        prog.add_update(u, op.u_new)
     return op.wbar

@@ -247,3 +247,20 @@ def test_tc_wgrad(lib, shape):
     assert relerr(dw, wr.grad) < 2e-5
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
     assert relerr(dw, 2 * wr.grad) < 2e-5
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('shape', [(3, 32, 32, 256, 3, 3, 1, 0, 0), (3, 32, 32, 3, 128, 3, 1, 0, 0), (4, 16, 16, 3, 128, 1, 1, 0, 0),
+                                   (5, 28, 28, 1, 138, 5, 2, 0, 6), (6, 28, 28, 1, 64, 5, 2, 0, 0)])
+def test_narrow_wgrad(lib, shape, dtype):
+    """register-accumulated wgrad for <= 4 channels on one side (G.Output, D.Block.1.*, g_h3, d_h0_conv)"""
+    d, x, wt, b, dy, xd, dyd, _ = make(shape, dtype)
+    wr = wt.double().requires_grad_(True)
+    O.conv2d(x.double(), wr, shape[6]).backward(dy.double())
+    nb = lib.rcgan_conv2d_wgrad_workspace(d)
+    ws = torch.zeros(max(nb, 4), dtype=torch.uint8, device='cuda')
+    dw = torch.full(wt.shape, 3.0, device='cuda')
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
+    assert relerr(dw, wr.grad) < 2e-5
+    call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
+    assert relerr(dw, 2 * wr.grad) < 2e-5
