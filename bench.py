@@ -20,6 +20,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # BASELINE configs[3] / [4]: CIFAR-10 SN-ResNet, batch = per-GPU BATCH_SIZE (one tower per GPU); a step = one
+    # iteration of gan_resnet.py:919-947 = 1 G step (batch 2B) + 5 D steps (B real + B fake each) -> 5B real images
+    'cifar_rcgan_b256': dict(kind='cifar', batch=256, flags=dict(algorithm='rcgan', perm_classifier=False)),
+    'cifar_rcganu_b256': dict(kind='cifar', batch=256, flags=dict(algorithm='rcgan-u', perm_classifier=True, confuse_init=True)),
     'mnist_rcganu_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=True)),
     'mnist_rcgan_b64': dict(batch=64, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False)),
     'mnist_rcgany_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False,
@@ -160,6 +164,68 @@ def op_profile(model, reps=5):
     return rows
 
 
+class CifarBench:
+    """adapter giving RCGANCifar the same (feed / train_iteration / programs) surface bench.py drives for DCGAN"""
+
+    def __init__(self, B, flags, precision, world, rank):
+        import torch
+        from robust_conditional_gan_b200.cifar.gan_resnet import RCGANCifar, default_flags
+        self.m = RCGANCifar(default_flags(alpha=0.5, **flags), tower_batch=B, precision=precision, world_size=world, rank=rank)
+        self.m.iteration = 1                       # steady state: every iteration has its G step
+        self.d_prog, self.g_prog, self.B = self.m.d_prog, self.m.g_prog, B
+        g = torch.Generator().manual_seed(rank)
+        ri = lambda n: torch.randint(0, 10, (n,), generator=g).to(torch.int32)
+        pin = lambda t: t.contiguous().pin_memory()
+        # 5 distinct real batches per iteration (uint8-range ints as int32, like the reference's placeholders)
+        self.d_feeds = [dict(all_real_data_int=pin(torch.randint(0, 256, (B, 3072), generator=g).to(torch.int32)),
+                             all_real_labels=pin(ri(B)), all_random_labels=pin(ri(B)), all_labels_biased=pin(ri(B)),
+                             all_labels_inv_weights=pin(torch.eye(10)[ri(B).long()]), noise=pin(torch.randn(B, 128, generator=g)),
+                             dequant_noise=pin(torch.rand(B, 3072, generator=g) / 128)) for _ in range(5)]
+        self.g_feeds = dict(noise=pin(torch.randn(2 * B, 128, generator=g)), all_random_labels_G=pin(ri(2 * B)),
+                            all_labels_biased_G=pin(ri(2 * B)))
+        self.images_per_step = 5 * B
+        self.h2d = sum(v.numel() * v.element_size() for f in self.d_feeds for v in f.values()) + \
+            sum(v.numel() * v.element_size() for v in self.g_feeds.values())
+        self.d2h = 4 * (len(self.d_prog.loss_names) + len(self.g_prog.loss_names))
+
+    def set_graph(self, on):
+        self.m.use_cuda_graph = on
+
+    def resident(self):
+        self.m.feed(self.d_prog, **self.d_feeds[0]); self.m.feed(self.g_prog, **self.g_feeds)
+
+    def step(self, e2e):
+        if e2e:
+            return self.m.train_iteration(self.d_feeds, self.g_feeds, fetch=True)
+        return self.m.train_iteration(None, None, fetch=False)
+
+
+class MnistBench:
+    def __init__(self, B, flags_kw, precision, world, rank):
+        from robust_conditional_gan_b200.model import DCGAN, default_flags
+        flags = default_flags(batch_size=B, alpha=0.5, **flags_kw)
+        self.m = DCGAN(batch_size=B, algorithm=flags.algorithm, estimate_confuse=flags.estimate_confuse, perm_regularizer=True,
+                       alpha=0.5, disc_type=flags.disc_type, config=flags, precision=precision, world_size=world, rank=rank,
+                       seed=0)
+        self.d_prog, self.g_prog, self.B = self.m.d_prog, self.m.g_prog, B
+        self.feeds = synthetic(B, seed=rank)
+        self.images_per_step = B
+        self.h2d = sum(v.numel() * 4 for v in self.feeds.values()) + \
+            sum(self.feeds[k].numel() * 4 for k in ('batch_z', 'batch_labels_gen', 'batch_labels_fake'))
+        self.d2h = 4 * (len(self.d_prog.loss_names) + len(self.g_prog.loss_names))
+
+    def set_graph(self, on):
+        self.m.use_cuda_graph = on
+
+    def resident(self):
+        self.m.feed(**self.feeds)
+
+    def step(self, e2e):
+        if e2e:
+            return self.m.train_iteration(fetch_losses=True, **self.feeds)
+        return self.m.train_iteration(fetch_losses=False)
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -170,18 +236,15 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     B = wl['batch']
-    flags = default_flags(batch_size=B, alpha=0.5, **wl['flags'])
     lib = _C.load()
-    model = DCGAN(batch_size=B, algorithm=flags.algorithm, estimate_confuse=flags.estimate_confuse, perm_regularizer=True,
-                  alpha=0.5, disc_type=flags.disc_type, config=flags, precision=args.precision, world_size=world, rank=rank,
-                  seed=0)
-    feeds = synthetic(B, seed=rank)
+    bench = (CifarBench if wl.get('kind') == 'cifar' else MnistBench)(B, wl['flags'], args.precision, world, rank)
+    model = bench
     # launches per iteration: count once with eager (uncaptured) launches
-    model.use_cuda_graph = False
+    bench.set_graph(False)
     n0 = lib.rcgan_launch_count()
-    model.train_iteration(**feeds)
+    bench.step(True)
     launches_per_iter = lib.rcgan_launch_count() - n0
-    model.use_cuda_graph = True
+    bench.set_graph(True)
 
     def barrier():
         if world > 1:
@@ -189,16 +252,16 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        model.train_iteration(**feeds)
+        bench.step(True)
     # ---- leg 1: inputs resident in HBM, device-timed
-    model.feed(**feeds)
+    bench.resident()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        model.train_iteration(fetch_losses=False)
+        bench.step(False)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -206,7 +269,7 @@ def run_ours(args, wl):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = model.train_iteration(fetch_losses=True, **feeds)
+        out = bench.step(True)
     barrier()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -214,28 +277,28 @@ def run_ours(args, wl):
         t = torch.tensor([ms, e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-    h2d = sum(v.numel() * 4 for v in feeds.values()) + sum(feeds[k].numel() * 4 for k in ('batch_z', 'batch_labels_gen', 'batch_labels_fake'))
-    d2h = 4 * (len(model.d_prog.loss_names) + len(model.g_prog.loss_names))
+    h2d, d2h = bench.h2d, bench.d2h
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
     ms_step = ms / args.steps
-    value = world * B / (ms_step / 1e3)
+    value = world * bench.images_per_step / (ms_step / 1e3)
     result = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': world * B, 'step': '1 D step + 2 G(+C) steps',
+        'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': world * B,
+                   'step': '1 G step (batch 2B) + 5 D steps (B real + B fake)' if wl.get('kind') == 'cifar' else '1 D step + 2 G(+C) steps',
                    'parallelism': 'dp%d' % world,
                    'l2': 'no explicit flush: one iteration touches ~1.5 GB of activations/gradients, >> 126 MB L2'},
         'clocks': clk,
-        'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'e2e': {'value': world * bench.images_per_step * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': launches_per_iter * args.steps,
         'losses': {k: round(v, 5) for k, v in out.items()},
     }
-    if world == 1:
+    if world == 1 and not args.no_op_profile:
         # roofline of the dominant op (timed live, CUDA events, L2 flushed) ...
         rows = op_profile(model)
         tot = sum(r['ms'] for r in rows)
@@ -254,7 +317,7 @@ def run_ours(args, wl):
         with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
             json.dump(rows, f, indent=1)
         # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and wl.get('kind') != 'cifar':
             cores = os.cpu_count()
             step = oracle_iteration_timer(B, wl['flags'], cores)
             step()
@@ -275,6 +338,7 @@ def main():
     ap.add_argument('--workload', default='mnist_rcganu_b1024', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-op-profile', action='store_true', help='skip the per-op roofline pass (clean ncu launch lists)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

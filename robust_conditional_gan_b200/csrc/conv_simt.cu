@@ -250,13 +250,13 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(ConvP p, const T* __re
   const int SH = MODE == MODE_FPROP ? p.h : p.ho, SW = MODE == MODE_FPROP ? p.w : p.wo;
   const int OHh = MODE == MODE_FPROP ? p.ho : p.h, OWw = MODE == MODE_FPROP ? p.wo : p.w;
   const int st = p.stride;
-  for (long mb = (long)blockIdx.x * 32; mb < p.M; mb += (long)gridDim.x * 32) {   // block-uniform trip count
-    const long m = mb + (threadIdx.x >> 3);
+  for (int mb = blockIdx.x * 32; mb < p.M; mb += gridDim.x * 32) {   // block-uniform trip count
+    const int m = mb + (threadIdx.x >> 3);
     const bool valid = m < p.M;
-    const long mm = valid ? m : 0;
-    const int b = (int)(mm % OWw);
-    const long r = mm / OWw;
-    const int a = (int)(r % OHh), n = (int)(r / OHh);
+    const int mm = valid ? m : 0;
+    const int b = mm % OWw;
+    const int r = mm / OWw;
+    const int a = r % OHh, n = r / OHh;
     float acc[NOUT];
 #pragma unroll
     for (int j = 0; j < NOUT; j++) acc[j] = 0.f;
@@ -275,28 +275,39 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(ConvP p, const T* __re
           if (sx < 0 || sx >= SW) continue;
           const T* sp = src + ((size_t)(n * SH + sy) * SW + sx) * ldsrc;
           const float* wp = wsm + (size_t)(ky * p.kw + kx) * NOUT * Cp;
-          for (int ck = sub; ck < nchunk; ck += 8) {
-            float xv[V];
-            const uint4 q = *reinterpret_cast<const uint4*>(sp + ck * V);   // pad channels (C..ld) are finite, weights 0
-            if (sizeof(T) == 2) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+          for (int ck0 = sub; ck0 < nchunk; ck0 += 32) {
+            // up to 4 chunks of this lane are fetched before any of them is consumed (loads overlap)
+            uint4 q[4];
 #pragma unroll
-              for (int e = 0; e < V / 2; e++) { float2 f = __bfloat1622float2(h[e]); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
-            } else {
-              const float* f = reinterpret_cast<const float*>(&q);
-#pragma unroll
-              for (int e = 0; e < V; e++) xv[e] = f[e];
+            for (int u = 0; u < 4; u++) {
+              const int ck = ck0 + 8 * u;
+              q[u] = ck < nchunk ? *reinterpret_cast<const uint4*>(sp + ck * V) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int j = 0; j < NOUT; j++) {
-              const float4* w4 = reinterpret_cast<const float4*>(wp + j * Cp + ck * V);
+            for (int u = 0; u < 4; u++) {
+              const int ck = ck0 + 8 * u;
+              if (ck >= nchunk) break;
+              float xv[V];
+              if (sizeof(T) == 2) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
 #pragma unroll
-              for (int e = 0; e < V / 4; e++) {
-                float4 wv = w4[e];
-                acc[j] = fmaf(xv[4 * e], wv.x, acc[j]);
-                acc[j] = fmaf(xv[4 * e + 1], wv.y, acc[j]);
-                acc[j] = fmaf(xv[4 * e + 2], wv.z, acc[j]);
-                acc[j] = fmaf(xv[4 * e + 3], wv.w, acc[j]);
+                for (int e = 0; e < V / 2; e++) { float2 f = __bfloat1622float2(h[e]); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
+              } else {
+                const float* f = reinterpret_cast<const float*>(&q[u]);
+#pragma unroll
+                for (int e = 0; e < V; e++) xv[e] = f[e];
+              }
+#pragma unroll
+              for (int j = 0; j < NOUT; j++) {
+                const float4* w4 = reinterpret_cast<const float4*>(wp + j * Cp + ck * V);
+#pragma unroll
+                for (int e = 0; e < V / 4; e++) {
+                  float4 wv = w4[e];
+                  acc[j] = fmaf(xv[4 * e], wv.x, acc[j]);
+                  acc[j] = fmaf(xv[4 * e + 1], wv.y, acc[j]);
+                  acc[j] = fmaf(xv[4 * e + 2], wv.z, acc[j]);
+                  acc[j] = fmaf(xv[4 * e + 3], wv.w, acc[j]);
+                }
               }
             }
           }
@@ -347,106 +358,6 @@ bool launch_narrow(const ConvP& p, const void* src, const float* w, void* out, c
     case 2: launch_narrow_n<MODE, 2, T, TO>(p, src, w, out, shb, st); break;
     case 3: launch_narrow_n<MODE, 3, T, TO>(p, src, w, out, shb, st); break;
     default: launch_narrow_n<MODE, 4, T, TO>(p, src, w, out, shb, st); break;
-  }
-  return true;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Narrow wgrad: one of the two channel counts is <= 4 (G.Output cout = 3, D.Block.1 cin = 3, g_h3 / d_h0 cin = 1).
-// dW[tap][ci][co] = sum_pixels x[pixel shifted by tap][ci] * dy[pixel][co] is then a bandwidth-bound reduction: one
-// thread per channel of the WIDE operand (coalesced), the <= 4 narrow values are warp-broadcast loads, taps*narrow
-// accumulators live in registers over a contiguous slab of pixels, one red.global.add per accumulator per block.
-template <bool XWIDE, int KS, int CN, typename T>
-__global__ void __launch_bounds__(256) conv_wgrad_narrow_kernel(ConvP p, const T* __restrict__ x, const T* __restrict__ dy,
-                                                                float* __restrict__ dw, int pix_per_block) {
-  constexpr int TAPS = KS * KS;
-  const int cw = XWIDE ? p.cin : p.cout;       // wide channel count; CN = narrow channel count (<= 4)
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  const bool cok = c < cw;
-  float acc[TAPS][CN];
-#pragma unroll
-  for (int t = 0; t < TAPS; t++)
-#pragma unroll
-    for (int j = 0; j < CN; j++) acc[t][j] = 0.f;
-  const long Mpix = (long)p.n * p.ho * p.wo;
-  const long m0 = (long)blockIdx.x * pix_per_block, m1 = min(Mpix, m0 + pix_per_block);
-  int ox = (int)(m0 % p.wo);
-  long r = m0 / p.wo;
-  int oy = (int)(r % p.ho), n = (int)(r / p.ho);
-  for (long m = m0; m < m1; m++) {
-    float wv = 0.f, nv[CN];
-    if (XWIDE) {
-#pragma unroll
-      for (int j = 0; j < CN; j++) nv[j] = to_f(dy[(size_t)m * p.ldy + j]);
-    } else {
-      if (cok) wv = to_f(dy[(size_t)m * p.ldy + c]);
-    }
-    const int iy0 = oy * p.stride - p.pad_t, ix0 = ox * p.stride - p.pad_l;
-#pragma unroll
-    for (int ky = 0; ky < KS; ky++) {
-      const int iy = iy0 + ky;
-      if (iy < 0 || iy >= p.h) continue;                                  // block-uniform branches
-#pragma unroll
-      for (int kx = 0; kx < KS; kx++) {
-        const int ix = ix0 + kx;
-        if (ix < 0 || ix >= p.w) continue;
-        const size_t xoff = ((size_t)(n * p.h + iy) * p.w + ix) * p.ldx;
-        if (XWIDE) {
-          const float xv = cok ? to_f(x[xoff + c]) : 0.f;
-#pragma unroll
-          for (int j = 0; j < CN; j++) acc[ky * KS + kx][j] = fmaf(xv, nv[j], acc[ky * KS + kx][j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CN; j++) acc[ky * KS + kx][j] = fmaf(to_f(x[xoff + j]), wv, acc[ky * KS + kx][j]);
-        }
-      }
-    }
-    if (++ox == p.wo) { ox = 0; if (++oy == p.ho) { oy = 0; n++; } }
-  }
-  if (!cok) return;
-#pragma unroll
-  for (int t = 0; t < TAPS; t++)
-#pragma unroll
-    for (int j = 0; j < CN; j++) {
-      const int ci = XWIDE ? c : j, co = XWIDE ? j : c;
-      atomicAdd(&dw[((size_t)t * p.cin + ci) * p.cout + co], acc[t][j]);
-    }
-}
-
-template <bool XW, int KS, typename T>
-void launch_wgrad_narrow_cn(const ConvP& p, int cn, const void* x, const void* dy, float* dw, dim3 grid, int bx, int ppb,
-                            cudaStream_t st) {
-  switch (cn) {
-    case 1: conv_wgrad_narrow_kernel<XW, KS, 1, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    case 2: conv_wgrad_narrow_kernel<XW, KS, 2, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    case 3: conv_wgrad_narrow_kernel<XW, KS, 3, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    default: conv_wgrad_narrow_kernel<XW, KS, 4, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-  }
-}
-
-template <typename T>
-bool launch_wgrad_narrow(const ConvP& p, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st) {
-  const int taps = p.kh * p.kw;
-  const bool xwide = p.cout <= 4 && p.cin >= 32, dywide = p.cin <= 4 && p.cout >= 32;
-  if ((!xwide && !dywide) || p.kh != p.kw || (p.kh != 1 && p.kh != 3 && p.kh != 5)) return false;
-  const int cn = xwide ? p.cout : p.cin, cw = xwide ? p.cin : p.cout;
-  if (p.kh == 5 && cn > 2) return false;        // 25 taps x 4 accumulators would spill
-  if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * p.cin * p.cout, st);
-  const int bx = cw >= 256 ? 256 : ((cw + 31) / 32) * 32;
-  const int gy = (cw + bx - 1) / bx;
-  const long Mpix = (long)p.n * p.ho * p.wo;
-  long want = (4L * RCGAN_NUM_SMS + gy - 1) / gy;
-  long ppb = (Mpix + want - 1) / want;
-  if (ppb < 64) ppb = 64;
-  dim3 grid((unsigned)((Mpix + ppb - 1) / ppb), gy);
-  if (xwide) {
-    if (p.kh == 1) launch_wgrad_narrow_cn<true, 1, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
-    else if (p.kh == 3) launch_wgrad_narrow_cn<true, 3, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
-    else launch_wgrad_narrow_cn<true, 5, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
-  } else {
-    if (p.kh == 1) launch_wgrad_narrow_cn<false, 1, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
-    else if (p.kh == 3) launch_wgrad_narrow_cn<false, 3, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
-    else launch_wgrad_narrow_cn<false, 5, T>(p, cn, x, dy, dw, grid, bx, (int)ppb, st);
   }
   return true;
 }
@@ -581,11 +492,6 @@ extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const
   }
   ConvP p = make_p(d);
   p.M = d->kh * d->kw * d->cin; p.N = d->cout; p.K = d->n * d->ho * d->wo;
-  if (d->dtype == RCGAN_F32 ? launch_wgrad_narrow<float>(p, x, dy, dw, accumulate, as_stream(stream))
-                            : launch_wgrad_narrow<bf16>(p, x, dy, dw, accumulate, as_stream(stream))) {
-    RCGAN_LAUNCH_CHECK("conv2d_wgrad_narrow");
-    return 0;
-  }
   int ns = wgrad_splits(p);
   RCGAN_CHECK_ARG(ws && ws_bytes >= (size_t)ns * p.M * p.N * sizeof(float), "conv2d_wgrad: workspace too small");
   int klen = (p.K + ns - 1) / ns;

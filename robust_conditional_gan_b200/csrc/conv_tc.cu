@@ -180,33 +180,40 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     // =========================================================== A producers (then epilogue)
     const int t = threadIdx.x;
     const int chunk = t & 7;               // 16-byte chunk within the 128-byte row
-    int rbase[8], ry[8], rx[8];            // per handled row: image base (pixels), source base coordinates
-    bool rok[8];
+    // per handled row: element offset of its base source pixel and a bit mask of the taps that land inside the image
+    // (SAME-padding halo, rows past M) -- the K loop then costs one shift/and + one add per 16-byte cp.async
+    int roff[8];
+    uint32_t rmask[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       int m = m0 + (t >> 3) + 16 * i;
-      rok[i] = m < p.M;
-      int mm = rok[i] ? m : 0;
+      const bool rok = m < p.M;
+      int mm = rok ? m : 0;
       int b = mm % p.MW, r = mm / p.MW, a = r % p.MH, n = r / p.MH;
-      rbase[i] = n * p.SH * p.SW;
-      ry[i] = a * p.by_mul + p.by_add;
-      rx[i] = b * p.bx_mul + p.bx_add;
+      const int ry = a * p.by_mul + p.by_add, rx = b * p.bx_mul + p.bx_add;
+      roff[i] = ((n * p.SH + ry) * p.SW + rx) * p.ld_src + chunk * 8;
+      uint32_t msk = 0;
+      if (rok)
+        for (int tp = 0; tp < p.ntaps; tp++) {
+          const int sy = ry + p.tdy[tp], sx = rx + p.tdx[tp];
+          if (sy >= 0 && sy < p.SH && sx >= 0 && sx < p.SW) msk |= 1u << tp;
+        }
+      rmask[i] = msk;
     }
     for (int kb = 0; kb < nkb; kb++) {
       const int s = kb % STAGES;
       mbar_wait(smem_u32(&empty[s]), ((kb / STAGES) & 1) ^ 1);
       const int tap = kb / p.kb_per_tap;
-      const int ch = (kb - tap * p.kb_per_tap) * BK + chunk * 8;
-      const int dy = p.tdy[tap], dx = p.tdx[tap];
-      const bool chok = ch < p.cvalid;
-      const uint32_t abase = smem_u32(smA + s * C::A_BYTES);
+      const int c0 = (kb - tap * p.kb_per_tap) * BK;
+      const int toff = (p.tdy[tap] * p.SW + p.tdx[tap]) * p.ld_src + c0;
+      const bool chok = c0 + chunk * 8 < p.cvalid;
+      const uint32_t abase = smem_u32(smA + s * C::A_BYTES) + ((t >> 3) * 128);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int row = (t >> 3) + 16 * i;
-        const int sy = ry[i] + dy, sx = rx[i] + dx;
-        const bool ok = chok && rok[i] && sy >= 0 && sy < p.SH && sx >= 0 && sx < p.SW;
-        const bf16* src = ok ? p.src + ((size_t)(rbase[i] + sy * p.SW + sx) * p.ld_src + ch) : p.src;
-        cp_async16(abase + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+        const bool ok = chok && ((rmask[i] >> tap) & 1u);
+        const bf16* src = p.src + (ok ? (ptrdiff_t)roff[i] + toff : 0);
+        cp_async16(abase + i * 2048 + ((chunk ^ (row & 7)) << 4), src, ok ? 16u : 0u);
       }
       cp_async_commit();
       if (kb >= LAG) {

@@ -323,9 +323,8 @@ class DCGAN(object):
         self.lr_dev[key].copy_(self._lr_ring[i:i + 1], non_blocking=True)
 
     def _allreduce(self, group):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(group.grads)
+        from .parallel import allreduce_sum_
+        allreduce_sum_(group.grads, self.world_size)
 
     def _d_body_a(self):
         g = self.groups['d']
