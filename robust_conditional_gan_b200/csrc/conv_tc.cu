@@ -38,6 +38,10 @@ struct TcParams {
   int act;
   float leak;
   int accumulate;
+  // TMA im2col A loader (one cp.async.bulk.tensor.im2col per K block instead of 1024 cp.async):
+  // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
+  int im_w_lo, im_h_lo, im_sw, im_sh;
+  unsigned short toffw[MAX_TAPS], toffh[MAX_TAPS];
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -83,6 +87,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                   unsigned short off_w, unsigned short off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 
@@ -140,9 +153,10 @@ template <int BN> struct Cfg {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN>
+template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
-                                                         const __grid_constant__ CUtensorMap wmap) {
+                                                         const __grid_constant__ CUtensorMap wmap,
+                                                         const __grid_constant__ CUtensorMap amap) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(smem_u32(&full[s]), 128 + 1);
+      mbar_init(smem_u32(&full[s]), IM2COL ? 1 : 128 + 1);
       mbar_init(smem_u32(&empty[s]), 1);
     }
     mbar_init(smem_u32(accum_full), 1);
@@ -169,7 +183,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   }
   if (warp == 4) {
     tmem_alloc(smem_u32(tmem_slot), BN);
-    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+      if (IM2COL) asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -179,6 +196,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   if (warp < 4) {
     // =========================================================== A producers (then epilogue)
     const int t = threadIdx.x;
+    if (!IM2COL) {
     const int chunk = t & 7;               // 16-byte chunk within the 128-byte row
     // per handled row: element offset of its base source pixel and a bit mask of the taps that land inside the image
     // (SAME-padding halo, rows past M) -- the K loop then costs one shift/and + one add per 16-byte cp.async
@@ -225,6 +243,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     cp_async_wait<0>();
     fence_proxy_async();
     for (int kb = (nkb > LAG ? nkb - LAG : 0); kb < nkb; kb++) mbar_arrive(smem_u32(&full[kb % STAGES]));
+    }
 
     // =========================================================== epilogue: TMEM -> registers -> global
     mbar_wait(smem_u32(accum_full), 0);
@@ -280,14 +299,19 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
     tc_fence_before();
   } else if (warp == 4) {
-    // =========================================================== B producer (TMA)
+    // =========================================================== B (and, with IM2COL, A) producer (TMA)
     if (lane == 0) {
+      const int mb = m0 % p.MW, mr = m0 / p.MW;
+      const int im_w = p.im_w_lo + mb * p.im_sw, im_h = p.im_h_lo + (mr % p.MH) * p.im_sh, im_n = mr / p.MH;
       for (int kb = 0; kb < nkb; kb++) {
         const int s = kb % STAGES;
         mbar_wait(smem_u32(&empty[s]), ((kb / STAGES) & 1) ^ 1);
         const int tap = kb / p.kb_per_tap;
         const int k0 = (kb - tap * p.kb_per_tap) * BK;
-        mbar_arrive_expect_tx(smem_u32(&full[s]), C::B_BYTES);
+        mbar_arrive_expect_tx(smem_u32(&full[s]), C::B_BYTES + (IM2COL ? C::A_BYTES : 0));
+        if (IM2COL)
+          tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES), &amap, smem_u32(&full[s]), k0, im_w, im_h, im_n, p.toffw[tap],
+                             p.toffh[tap]);
         tma_load_3d(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0, p.twi[tap]);
       }
     }
@@ -543,6 +567,9 @@ __global__ void wpack_kernel(const float* __restrict__ w, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -559,6 +586,30 @@ EncodeTiledFn get_encode() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+
+// RCGAN_TC_IM2COL=0 forces the cp.async gather (A/B comparison and a fallback switch for debugging)
+bool im2col_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RCGAN_TC_IM2COL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -597,25 +648,50 @@ int make_wmap(CUtensorMap* map, const bf16* base, int kpad, int rows, int taps, 
   return 0;
 }
 
-template <int BN>
-int launch_tc(const TcParams& p, const CUtensorMap& map, cudaStream_t st) {
+template <int BN, bool IM2COL>
+int launch_tc(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
     if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-  conv_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(p, map);
+  conv_tc_kernel<BN, IM2COL><<<grid, 192, Cfg<BN>::SMEM, st>>>(p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc");
   return 0;
 }
 
-int run_tc(const TcParams& p, const bf16* wbase, int kpad, int rows, int taps, cudaStream_t st) {
+// im2col tensor map over the gathered operand [n, SH, SW, C] (channel stride ld): 128 pixels x 64 channels per load,
+// SWIZZLE_128B; the pixel bounding box is [lo, lo + (MW-1)*stride] x [lo, lo + (MH-1)*stride] base positions so that
+// the TMA's own w -> h -> n traversal enumerates exactly the GEMM rows m = (n, a, b) of the tile.
+bool make_amap(CUtensorMap* map, const TcParams& p, int channels, int nimg) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc || !im2col_enabled()) return false;
+  if ((p.ld_src * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(p.src) & 15)) return false;
+  const int up_w = p.im_w_lo + (p.MW - 1) * p.im_sw + 1 - p.SW, up_h = p.im_h_lo + (p.MH - 1) * p.im_sh + 1 - p.SH;
+  const int lim = 120;
+  if (p.im_w_lo < -lim || p.im_w_lo > lim || p.im_h_lo < -lim || p.im_h_lo > lim || up_w < -lim || up_w > lim || up_h < -lim ||
+      up_h > lim)
+    return false;
+  if (p.im_sw < 1 || p.im_sw > 8 || p.im_sh < 1 || p.im_sh > 8) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)channels, (cuuint64_t)p.SW, (cuuint64_t)p.SH, (cuuint64_t)nimg};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.ld_src * 2, (cuuint64_t)p.SW * p.ld_src * 2, (cuuint64_t)p.SH * p.SW * p.ld_src * 2};
+  int lo[2] = {p.im_w_lo, p.im_h_lo}, up[2] = {up_w, up_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)p.im_sw, (cuuint32_t)p.im_sh, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p.src, gdim, gstr, lo, up, BK, BM, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int channels, int nimg, cudaStream_t st) {
   const int bn = p.N <= 64 ? 64 : 128;
-  CUtensorMap map;
+  CUtensorMap map, amap;
   if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
-  return bn == 64 ? launch_tc<64>(p, map, st) : launch_tc<128>(p, map, st);
+  if (make_amap(&amap, p, channels, nimg))
+    return bn == 64 ? launch_tc<64, true>(p, map, amap, st) : launch_tc<128, true>(p, map, amap, st);
+  return bn == 64 ? launch_tc<64, false>(p, map, map, st) : launch_tc<128, false>(p, map, map, st);
 }
 
 }  // namespace
@@ -661,7 +737,9 @@ int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, c
   p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->ho; p.OW = d->wo;
   p.oy_mul = 1; p.oy_add = 0; p.ox_mul = 1; p.ox_add = 0; p.N = d->cout;
   p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0;
-  if (int e = run_tc(p, reinterpret_cast<const bf16*>(wpack), g.kpadF, d->cout, g.taps, st)) return e;
+  p.im_w_lo = -d->pad_l; p.im_h_lo = -d->pad_t; p.im_sw = d->stride; p.im_sh = d->stride;
+  for (int t = 0; t < g.taps; t++) { p.toffh[t] = (unsigned short)(t / d->kw); p.toffw[t] = (unsigned short)(t % d->kw); }
+  if (int e = run_tc(p, reinterpret_cast<const bf16*>(wpack), g.kpadF, d->cout, g.taps, d->cin, d->n, st)) return e;
   *handled = 1;
   return 0;
 }
@@ -686,17 +764,20 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
       const int cy = (py + d->pad_t - kpy) / s, cx = (px + d->pad_l - kpx) / s;
       p.by_mul = 1; p.by_add = cy; p.bx_mul = 1; p.bx_add = cx;
       int nt = 0;
+      const int njy = (d->kh - kpy + s - 1) / s, njx = (d->kw - kpx + s - 1) / s;   // taps of this parity class per dim
       for (int ky = kpy, jy = 0; ky < d->kh; ky += s, jy++)
         for (int kx = kpx, jx = 0; kx < d->kw; kx += s, jx++) {
           p.tdy[nt] = (short)(-jy); p.tdx[nt] = (short)(-jx); p.twi[nt] = (short)(ky * d->kw + kx);
+          p.toffh[nt] = (unsigned short)(njy - 1 - jy); p.toffw[nt] = (unsigned short)(njx - 1 - jx);
           nt++;
         }
+      p.im_h_lo = cy - (njy - 1); p.im_w_lo = cx - (njx - 1); p.im_sh = 1; p.im_sw = 1;
       p.ntaps = nt; p.kb_per_tap = g.kpadD / BK;
       p.out = dx; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldx; p.OH = d->h; p.OW = d->w;
       p.oy_mul = s; p.oy_add = py; p.ox_mul = s; p.ox_add = px; p.N = d->cin;
       p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate;
       if (nt == 0) { rcgan_set_error("conv_tc dgrad: parity class without taps"); return RCGAN_EUNSUPPORTED; }
-      if (int e = run_tc(p, wD, g.kpadD, d->cin, g.taps, st)) return e;
+      if (int e = run_tc(p, wD, g.kpadD, d->cin, g.taps, d->cout, d->n, st)) return e;
     }
   *handled = 1;
   return 0;
