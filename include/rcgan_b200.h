@@ -79,6 +79,12 @@ size_t rcgan_conv2d_wgrad_workspace(const rcgan_conv_desc* d);
 int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* Patch matrix of a conv whose input has very few channels (cin <= 4: d_h0_conv, D.Block.1.*, g_h3's transposed conv):
+ * P[m, (ky*kw + kx)*cin + ci] = x[n, oy*s - pad_t + ky, ox*s - pad_l + kx, ci] (0 in the halo and for columns >= kh*kw*cin),
+ * m = (n, oy, ox), row stride ldp.  The conv then runs as a dense GEMM on the tensor cores (1x1 desc over P) instead of a
+ * K = 25..27 implicit GEMM on CUDA cores.  Same dtype as d->dtype. */
+int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp, void* stream);
+
 /* ---------------------------------------------------------------- rows x channels helpers */
 /* db[c] (=|+=) sum_r dy[r,c]   (bias gradients of conv / deconv / linear) */
 int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream);

@@ -651,10 +651,13 @@ PackGeo pack_geo(const rcgan_conv_desc* d) {
 bool fprop_ok(const rcgan_conv_desc* d) {
   // any cout: a 3-channel output (G.Output) still moves 9 x 256 input channels per pixel -- the A-operand stream, not the MMA,
   // is the cost, and the TMA im2col path streams it ~3x faster than the CUDA-core gather-dot
-  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && d->cin >= 32 && d->cout >= 1 && d->kh * d->kw <= MAX_TAPS;
+  // cin < 32 only for pure GEMMs (1x1 over a [rows,1,1,K] patch matrix, see rcgan_im2col)
+  const bool gemm = d->kh == 1 && d->kw == 1 && d->h == 1 && d->w == 1;
+  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && (d->cin >= 32 || gemm) && d->cout >= 1 && d->kh * d->kw <= MAX_TAPS;
 }
 bool wgrad_ok(const rcgan_conv_desc* d) {
-  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && d->ldy % 8 == 0 && d->cin >= 32 && d->cout >= 32 &&
+  const bool gemm = d->kh == 1 && d->kw == 1 && d->h == 1 && d->w == 1;
+  return d->dtype == RCGAN_BF16 && d->ldx % 8 == 0 && d->ldy % 8 == 0 && (d->cin >= 32 || gemm) && d->cout >= 32 &&
          d->ho * d->wo <= 1024 && d->wo <= 255 && d->ho <= 255;
 }
 bool dgrad_ok(const rcgan_conv_desc* d) {

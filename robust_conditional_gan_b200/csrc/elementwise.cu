@@ -212,6 +212,28 @@ __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld,
   }
 }
 
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n, int h, int w, int cin, int ho, int wo, int kh,
+                              int kw, int stride, int pad_t, int pad_l, int ldx, int ldp) {
+  const int K = kh * kw * cin;
+  long total = (long)n * ho * wo * ldp;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int k = (int)(i % ldp);
+    long m = i / ldp;
+    T v = from_f<T>(0.f);
+    if (k < K) {
+      int ci = k % cin, tap = k / cin;
+      int ox = (int)(m % wo);
+      long r = m / wo;
+      int oy = (int)(r % ho);
+      long nb = r / ho;
+      int iy = oy * stride - pad_t + tap / kw, ix = ox * stride - pad_l + tap % kw;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = x[((nb * h + iy) * w + ix) * ldx + ci];
+    }
+    P[i] = v;
+  }
+}
+
 __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
   long total = (long)n * 3072;
@@ -366,6 +388,16 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
   dim3 grid(gx, gy), block(32, 8);
   DISPATCH_T(dtype, colsum_kernel<T><<<grid, block, 0, st>>>((const T*)dy, rows, c, ld, db, accumulate, gy > 1));
   RCGAN_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+extern "C" int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp, void* stream) {
+  RCGAN_CHECK_ARG(d && x && patches && ldp >= d->kh * d->kw * d->cin, "im2col: bad args");
+  long total = (long)d->n * d->ho * d->wo * ldp;
+  DISPATCH_T(d->dtype, im2col_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+                           (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
+                           d->pad_l, d->ldx, ldp));
+  RCGAN_LAUNCH_CHECK("im2col");
   return 0;
 }
 

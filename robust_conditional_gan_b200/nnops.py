@@ -24,6 +24,18 @@ def gp(t):
     return None if t is None or t.grad is None else t.grad.data_ptr()
 
 
+def make_patch(prog, desc, rows, ld_out):
+    """(patch tensor, GEMM desc) for a bf16 conv with cin <= 4 and kh*kw*cin <= 64, else (None, None).
+    The GEMM desc is the 1x1 conv over the [rows, 1, 1, K'] patch matrix with the same weights viewed as [K', cout]."""
+    kp = desc.kh * desc.kw * desc.cin
+    if desc.dtype != _C.BF16 or desc.cin > 4 or kp > 64 or desc.cout < 32 or desc.ldy % 8 != 0:
+        return None, None
+    ldp = round_up(kp, 8)
+    patch = prog.new((rows, kp), _C.BF16, ld=ldp)
+    g = ConvDesc(rows, 1, 1, kp, 1, 1, desc.cout, 1, 1, 1, 0, 0, ldp, ld_out, desc.dtype)
+    return patch, g
+
+
 def spatial(t):
     """(n, h, w) of a 2-D [n,c] or 4-D [n,h,w,c] tensor"""
     if len(t.shape) == 2:
@@ -57,7 +69,9 @@ class ConvOp(Op):
         self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
-        self.pack, self.pack_owner = prog.weight_pack(w, self.desc)
+        # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
+        self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
+        self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -67,9 +81,13 @@ class ConvOp(Op):
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
     def forward(self, prog):
+        d, xin = self.desc, dp(self.x)
+        if self.patch is not None:
+            call('rcgan_im2col', self.desc, dp(self.x), dp(self.patch), self.patch.ld, stream_ptr())
+            d, xin = self.gdesc, dp(self.patch)
         if self.pack_owner:
-            call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.pack), stream_ptr())
-        call('rcgan_conv2d_fprop', self.desc, dp(self.x), dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
+            call('rcgan_conv_wpack', d, dp(self.w), None, pp(self.pack), stream_ptr())
+        call('rcgan_conv2d_fprop', d, xin, dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, stream_ptr())
 
     def backward(self, prog):
@@ -81,10 +99,13 @@ class ConvOp(Op):
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if nx:
-            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype,
-                 _C.ACT_NONE, 0.0, self.acc_x, st)
+            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
+                 gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
         if nw:
-            call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+            if self.patch is not None:
+                call('rcgan_conv2d_wgrad', self.gdesc, dp(self.patch), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+            else:
+                call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
         if nb and self.b is not None:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 
@@ -110,7 +131,10 @@ class DeconvOp(Op):
         self.desc = ConvDesc(n, oh, ow, cout, h, wd, cin, kh, kw, stride, pt, pl, self.y.ld, x.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
-        self.pack, self.pack_owner = prog.weight_pack(w, self.desc)
+        # the conv being transposed has cin = deconv cout: for a 1-channel image (g_h3) its fprop / wgrad (= this op's backward)
+        # run as GEMMs on the patch matrix of dL/dy
+        self.patch, self.gdesc = make_patch(prog, self.desc, n * h * wd, x.ld)
+        self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -122,8 +146,10 @@ class DeconvOp(Op):
 
     def forward(self, prog):
         if self.pack_owner:
-            call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.pack), stream_ptr())
-        call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
+            call('rcgan_conv_wpack', self.gdesc if self.patch is not None else self.desc, dp(self.w), None, pp(self.pack),
+                 stream_ptr())
+        call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), None if self.patch is not None else pp(self.pack),
+             dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, 0, stream_ptr())
 
     def backward(self, prog):
@@ -134,11 +160,15 @@ class DeconvOp(Op):
         y, dy = self.y, gp(self.y)
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        d, dyin = self.desc, dy
+        if self.patch is not None and (nx or nw):
+            call('rcgan_im2col', self.desc, dy, dp(self.patch), self.patch.ld, st)
+            d, dyin = self.gdesc, dp(self.patch)
         if nx:
-            call('rcgan_conv2d_fprop', self.desc, dy, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE,
+            call('rcgan_conv2d_fprop', d, dyin, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE,
                  0.0, st)
         if nw:
-            call('rcgan_conv2d_wgrad', self.desc, dy, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+            call('rcgan_conv2d_wgrad', d, dyin, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
         if nb and self.b is not None:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 
