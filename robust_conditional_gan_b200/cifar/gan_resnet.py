@@ -96,7 +96,16 @@ class Net:
         if output_dim == input_dim and resample is None:
             shortcut = inputs
         else:
-            shortcut = conv_shortcut(inputs, output_dim=output_dim, filter_size=1, name=name + '.Shortcut', he_init=False, **kw)
+            # 1x1 shortcuts commute with the resampling (a 1x1 conv touches one pixel; nearest-neighbour upsampling copies
+            # pixels, mean-pooling averages them and the conv is linear): UpsampleConv_1x1(x) == Upsample(Conv_1x1(x)) bit for
+            # bit, ConvMeanPool_1x1(x) == Conv_1x1(MeanPool(x)) up to fp32 summation order.  Running the conv on the SMALL
+            # grid is a 4x flop / traffic cut (legal for parity; rooflines still use the reference flops).
+            if resample == 'up':
+                shortcut = Upsample2Op(lib_ops.Conv2D(inputs, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)).y
+            elif resample == 'down':
+                shortcut = lib_ops.Conv2D(Pool2Op(inputs).y, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)
+            else:
+                shortcut = conv_shortcut(inputs, output_dim=output_dim, filter_size=1, name=name + '.Shortcut', he_init=False, **kw)
         output = self.Normalize(name + '.N1', inputs, labels=labels, fuse_act='relu')
         output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, **kw)
         output = self.Normalize(name + '.N2', output, labels=labels, fuse_act='relu')

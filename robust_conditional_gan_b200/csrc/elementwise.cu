@@ -1,7 +1,10 @@
-// Bandwidth-bound rows x channels helpers: bias/activation, label concat, spatial mean,
-// 2x2 mean-pool, nearest-neighbour upsample, residual add, casts, column sums.
-// (mnist/ops.py:46-51,94-95; mnist/model.py:678,714-728; cifar10/gan_resnet.py:231-272,328,405-407)
-// All are grid-stride, coalesced along the channel dimension.
+// Bandwidth-bound rows x channels helpers: bias/activation, label concat, spatial mean, 2x2 mean-pool, nearest-neighbour
+// upsample, residual add, casts, column sums, patch matrix, CIFAR preprocessing.
+// (mnist/ops.py:46-51,94-95; mnist/model.py:678,714-728; cifar10/gan_resnet.py:231-272,328,405-407,548-552)
+//
+// Every kernel moves 16 bytes per thread per access (8 bf16 / 4 fp32 channels, `VecIO`) whenever the channel count and
+// strides allow it -- the first version used scalar 2-byte accesses and reached ~0.5 TB/s (ncu/op profile r1b) -- with a
+// scalar instantiation (V = 1) for odd channel counts.  Grid-stride loops, coalesced along channels.
 #include "common.cuh"
 
 namespace {
@@ -12,180 +15,292 @@ inline int grid_for(long work, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-template <typename T>
-__global__ void bias_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y, long rows,
-                                    int c, int ldx, int ldy, int act, float leak) {
-  long total = rows * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r = i / c;
-    int ch = (int)(i - r * c);
-    float v = to_f(x[r * ldx + ch]);
-    if (bias) v += bias[ch];
-    y[r * ldy + ch] = from_f<T>(act_fwd(v, act, leak));
+template <typename T> struct VecW { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float* out) {
+  if (V == 1) { out[0] = to_f(*p); return; }
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  if (sizeof(T) == 4) {
+    const float* f = reinterpret_cast<const float*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; i++) out[i] = f[i];
+  } else {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < V / 2; i++) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+  }
+}
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float* in) {
+  if (V == 1) { *p = from_f<T>(in[0]); return; }
+  uint4 q;
+  if (sizeof(T) == 4) {
+    float* f = reinterpret_cast<float*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; i++) f[i] = in[i];
+  } else {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < V / 2; i++) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+#define GRID_STRIDE(i, total) \
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (total); i += (long)gridDim.x * blockDim.x)
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
+                                                           long rows, int c, int ldx, int ldy, int act, float leak) {
+  const int cv = c / V;
+  GRID_STRIDE(i, rows * cv) {
+    long r = i / cv;
+    int ch = (int)(i - r * cv) * V;
+    float v[V];
+    ldv<T, V>(x + r * ldx + ch, v);
+#pragma unroll
+    for (int k = 0; k < V; k++) v[k] = act_fwd(bias ? v[k] + bias[ch + k] : v[k], act, leak);
+    stv<T, V>(y + r * ldy + ch, v);
   }
 }
 
-template <typename T>
-__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long rows, int c,
-                               int ld_dy, int ld_y, int ld_dx, int act, float leak, int accumulate) {
-  long total = rows * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r = i / c;
-    int ch = (int)(i - r * c);
-    float g = to_f(dy[r * ld_dy + ch]) * act_bwd_from_y(to_f(y[r * ld_y + ch]), act, leak);
-    long o = r * ld_dx + ch;
-    if (accumulate) g += to_f(dx[o]);
-    dx[o] = from_f<T>(g);
-  }
-}
-
-template <typename T>
-__global__ void concat_label_kernel(const T* __restrict__ a, int lda, const float* __restrict__ yb, T* __restrict__ out,
-                                    int ldo, long rows, int rows_per_sample, int c1, int c2) {
-  long total = rows * ldo;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r = i / ldo;
-    int ch = (int)(i - r * ldo);
-    T v;
-    if (ch < c1) v = a[r * lda + ch];
-    else if (ch < c1 + c2) v = from_f<T>(yb[(r / rows_per_sample) * c2 + (ch - c1)]);
-    else v = from_f<T>(0.f);
-    out[i] = v;
-  }
-}
-
-template <typename T>
-__global__ void slice_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ da, int lda, long rows, int c1,
-                                 int accumulate) {
-  long total = rows * c1;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r = i / c1;
-    int ch = (int)(i - r * c1);
-    float g = to_f(dout[r * ldo + ch]);
-    long o = r * lda + ch;
-    if (accumulate) g += to_f(da[o]);
-    da[o] = from_f<T>(g);
-  }
-}
-
-// one thread per (sample, channel); loops hw (coalesced over channels)
-template <typename T>
-__global__ void meanhw_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int samples, int hw, int c, int relu) {
-  long total = (long)samples * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long s = i / c;
-    int ch = (int)(i - s * c);
-    const T* p = x + s * hw * c + ch;
-    float acc = 0.f;
-    for (int k = 0; k < hw; k++) {
-      float v = to_f(p[(long)k * c]);
-      acc += relu ? fmaxf(v, 0.f) : v;
+template <typename T, int V>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long rows,
+                                                      int c, int ld_dy, int ld_y, int ld_dx, int act, float leak, int accumulate) {
+  const int cv = c / V;
+  GRID_STRIDE(i, rows * cv) {
+    long r = i / cv;
+    int ch = (int)(i - r * cv) * V;
+    float g[V], yv[V], o[V];
+    ldv<T, V>(dy + r * ld_dy + ch, g);
+    ldv<T, V>(y + r * ld_y + ch, yv);
+    if (accumulate) ldv<T, V>(dx + r * ld_dx + ch, o);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float v = g[k] * act_bwd_from_y(yv[k], act, leak);
+      o[k] = accumulate ? o[k] + v : v;
     }
-    y[i] = from_f<T>(acc / hw);
+    stv<T, V>(dx + r * ld_dx + ch, o);
   }
 }
 
-template <typename T>
-__global__ void meanhw_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, int samples,
-                                  int hw, int c, int relu, int accumulate) {
-  long total = (long)samples * hw * c;
-  float inv = 1.f / hw;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long s = i / ((long)hw * c);
-    float g = to_f(dy[s * c + ch]) * inv;
-    if (relu && !(to_f(x[i]) > 0.f)) g = 0.f;
-    if (accumulate) g += to_f(dx[i]);
-    dx[i] = from_f<T>(g);
+// one thread per 16-byte chunk of the OUTPUT row: chunks inside [0, c1) are vector copies, the label / padding tail is scalar
+template <typename T, int V>
+__global__ void __launch_bounds__(256) concat_label_kernel(const T* __restrict__ a, int lda, const float* __restrict__ yb,
+                                                           T* __restrict__ out, int ldo, long rows, int rows_per_sample, int c1,
+                                                           int c2) {
+  const int cv = ldo / V;
+  GRID_STRIDE(i, rows * cv) {
+    long r = i / cv;
+    int ch = (int)(i - r * cv) * V;
+    float v[V];
+    if (V > 1 && ch + V <= c1) {
+      ldv<T, V>(a + r * lda + ch, v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        int cc = ch + k;
+        v[k] = cc < c1 ? to_f(a[r * lda + cc]) : (cc < c1 + c2 ? yb[(r / rows_per_sample) * c2 + (cc - c1)] : 0.f);
+      }
+    }
+    stv<T, V>(out + r * ldo + ch, v);
   }
 }
 
-template <typename T>
-__global__ void avgpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
-  int ho = h / 2, wo = w / 2;
-  long total = (long)n * ho * wo * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long r = i / c;
+template <typename T, int V>
+__global__ void __launch_bounds__(256) slice_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ da, int lda, long rows,
+                                                        int c1, int accumulate) {
+  const int cv = c1 / V;
+  GRID_STRIDE(i, rows * cv) {
+    long r = i / cv;
+    int ch = (int)(i - r * cv) * V;
+    float g[V], o[V];
+    ldv<T, V>(dout + r * ldo + ch, g);
+    if (accumulate) {
+      ldv<T, V>(da + r * lda + ch, o);
+#pragma unroll
+      for (int k = 0; k < V; k++) g[k] += o[k];
+    }
+    stv<T, V>(da + r * lda + ch, g);
+  }
+}
+
+// one thread per (sample, channel vector); loops hw (coalesced over channels)
+template <typename T, int V>
+__global__ void __launch_bounds__(128) meanhw_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int samples, int hw, int c, int relu) {
+  const int cv = c / V;
+  GRID_STRIDE(i, (long)samples * cv) {
+    long s = i / cv;
+    int ch = (int)(i - s * cv) * V;
+    const T* p = x + s * hw * c + ch;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) acc[k] = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < hw; q++) {
+      float v[V];
+      ldv<T, V>(p + (long)q * c, v);
+#pragma unroll
+      for (int k = 0; k < V; k++) acc[k] += relu ? fmaxf(v[k], 0.f) : v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < V; k++) acc[k] /= hw;
+    stv<T, V>(y + s * c + ch, acc);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) meanhw_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+                                                         int samples, int hw, int c, int relu, int accumulate) {
+  const int cv = c / V;
+  const float inv = 1.f / hw;
+  GRID_STRIDE(i, (long)samples * hw * cv) {
+    int ch = (int)(i % cv) * V;
+    long row = i / cv, s = row / hw;
+    float g[V], xv[V], o[V];
+    ldv<T, V>(dy + s * c + ch, g);
+    if (relu) ldv<T, V>(x + row * c + ch, xv);
+    if (accumulate) ldv<T, V>(dx + row * c + ch, o);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float v = g[k] * inv;
+      if (relu && !(xv[k] > 0.f)) v = 0.f;
+      o[k] = accumulate ? o[k] + v : v;
+    }
+    stv<T, V>(dx + row * c + ch, o);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+  const int ho = h / 2, wo = w / 2, cv = c / V;
+  GRID_STRIDE(i, (long)n * ho * wo * cv) {
+    int ch = (int)(i % cv) * V;
+    long r = i / cv;
     int ox = (int)(r % wo);
     r /= wo;
     int oy = (int)(r % ho);
     long nb = r / ho;
     const T* p = x + ((nb * h + 2 * oy) * w + 2 * ox) * c + ch;
+    float a[V], b[V], d[V], e[V];
+    ldv<T, V>(p, a); ldv<T, V>(p + (long)w * c, b); ldv<T, V>(p + c, d); ldv<T, V>(p + (long)w * c + c, e);
     // add_n([x[::2,::2], x[1::2,::2], x[::2,1::2], x[1::2,1::2]]) / 4  (gan_resnet.py:239-240)
-    float v = ((to_f(p[0]) + to_f(p[(long)w * c])) + to_f(p[c])) + to_f(p[(long)w * c + c]);
-    y[i] = from_f<T>(v * 0.25f);
+#pragma unroll
+    for (int k = 0; k < V; k++) a[k] = (((a[k] + b[k]) + d[k]) + e[k]) * 0.25f;
+    stv<T, V>(y + i * V, a);
   }
 }
 
-template <typename T>
-__global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
-                                    int accumulate) {
-  int ho = h / 2, wo = w / 2;
-  long total = (long)n * h * w * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long r = i / c;
+template <typename T, int V>
+__global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
+                                                           int accumulate) {
+  const int ho = h / 2, wo = w / 2, cv = c / V;
+  GRID_STRIDE(i, (long)n * h * w * cv) {
+    int ch = (int)(i % cv) * V;
+    long r = i / cv;
     int x_ = (int)(r % w);
     r /= w;
     int y_ = (int)(r % h);
     long nb = r / h;
-    float g = 0.25f * to_f(dy[((nb * ho + y_ / 2) * wo + x_ / 2) * c + ch]);
-    if (accumulate) g += to_f(dx[i]);
-    dx[i] = from_f<T>(g);
+    float g[V], o[V];
+    ldv<T, V>(dy + ((nb * ho + y_ / 2) * wo + x_ / 2) * c + ch, g);
+    if (accumulate) ldv<T, V>(dx + i * V, o);
+#pragma unroll
+    for (int k = 0; k < V; k++) o[k] = accumulate ? o[k] + 0.25f * g[k] : 0.25f * g[k];
+    stv<T, V>(dx + i * V, o);
   }
 }
 
-template <typename T>
-__global__ void upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
-  long total = (long)n * (2 * h) * (2 * w) * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long r = i / c;
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+  const int cv = c / V;
+  GRID_STRIDE(i, (long)n * (2 * h) * (2 * w) * cv) {
+    int ch = (int)(i % cv) * V;
+    long r = i / cv;
     int ox = (int)(r % (2 * w));
     r /= 2 * w;
     int oy = (int)(r % (2 * h));
     long nb = r / (2 * h);
-    y[i] = x[((nb * h + oy / 2) * w + ox / 2) * c + ch];
+    float v[V];
+    ldv<T, V>(x + ((nb * h + oy / 2) * w + ox / 2) * c + ch, v);
+    stv<T, V>(y + i * V, v);
   }
 }
 
-template <typename T>
-__global__ void upsample2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
-                                     int accumulate) {
-  long total = (long)n * h * w * c;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int ch = (int)(i % c);
-    long r = i / c;
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
+                                                            int accumulate) {
+  const int cv = c / V;
+  GRID_STRIDE(i, (long)n * h * w * cv) {
+    int ch = (int)(i % cv) * V;
+    long r = i / cv;
     int x_ = (int)(r % w);
     r /= w;
     int y_ = (int)(r % h);
     long nb = r / h;
     const T* p = dy + ((nb * 2 * h + 2 * y_) * (2 * w) + 2 * x_) * c + ch;
-    float g = to_f(p[0]) + to_f(p[c]) + to_f(p[(long)2 * w * c]) + to_f(p[(long)2 * w * c + c]);
-    if (accumulate) g += to_f(dx[i]);
-    dx[i] = from_f<T>(g);
+    float a[V], b[V], d[V], e[V], o[V];
+    ldv<T, V>(p, a); ldv<T, V>(p + c, b); ldv<T, V>(p + (long)2 * w * c, d); ldv<T, V>(p + (long)2 * w * c + c, e);
+    if (accumulate) ldv<T, V>(dx + i * V, o);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float g = a[k] + b[k] + d[k] + e[k];
+      o[k] = accumulate ? o[k] + g : g;
+    }
+    stv<T, V>(dx + i * V, o);
   }
 }
 
-template <typename T>
-__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long numel) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x)
-    out[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
-}
-
-template <typename T>
-__global__ void copy_acc_kernel(const T* __restrict__ src, T* __restrict__ dst, long numel, int accumulate) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x) {
-    float v = to_f(src[i]);
-    if (accumulate) v += to_f(dst[i]);
-    dst[i] = from_f<T>(v);
+template <typename T, int V>
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long nvec) {
+  GRID_STRIDE(i, nvec) {
+    float x[V], y[V];
+    ldv<T, V>(a + i * V, x); ldv<T, V>(b + i * V, y);
+#pragma unroll
+    for (int k = 0; k < V; k++) x[k] += y[k];
+    stv<T, V>(out + i * V, x);
   }
 }
 
+template <typename T, int V>
+__global__ void __launch_bounds__(256) copy_acc_kernel(const T* __restrict__ src, T* __restrict__ dst, long nvec, int accumulate) {
+  GRID_STRIDE(i, nvec) {
+    float x[V], y[V];
+    ldv<T, V>(src + i * V, x);
+    if (accumulate) {
+      ldv<T, V>(dst + i * V, y);
+#pragma unroll
+      for (int k = 0; k < V; k++) x[k] += y[k];
+    }
+    stv<T, V>(dst + i * V, x);
+  }
+}
+
+// 4 elements per thread (16-byte fp32 side, 8-byte bf16 side)
 template <typename S, typename D>
-__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long numel) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x)
+__global__ void __launch_bounds__(256) cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long numel, int vec) {
+  const long nv = vec ? numel / 4 : 0;
+  GRID_STRIDE(i, nv) {
+    float v[4];
+    if (sizeof(S) == 4) {
+      float4 q = reinterpret_cast<const float4*>(src)[i];
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      uint2 q = reinterpret_cast<const uint2*>(src)[i];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    if (sizeof(D) == 4) {
+      reinterpret_cast<float4*>(dst)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      uint2 q;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+      h[0] = __floats2bfloat162_rn(v[0], v[1]);
+      h[1] = __floats2bfloat162_rn(v[2], v[3]);
+      reinterpret_cast<uint2*>(dst)[i] = q;
+    }
+  }
+  for (long i = nv * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x)
     dst[i] = from_f<D>(to_f(src[i]));
 }
 
@@ -199,8 +314,10 @@ __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld,
   int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
   float acc = 0.f;
-  if (ch < c)
+  if (ch < c) {
+#pragma unroll 4
     for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f(dy[(size_t)r * ld + ch]);
+  }
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && ch < c) {
@@ -217,7 +334,7 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n,
                               int kw, int stride, int pad_t, int pad_l, int ldx, int ldp) {
   const int K = kh * kw * cin;
   long total = (long)n * ho * wo * ldp;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  GRID_STRIDE(i, total) {
     int k = (int)(i % ldp);
     long m = i / ldp;
     T v = from_f<T>(0.f);
@@ -237,7 +354,7 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n,
 __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
   long total = (long)n * 3072;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  GRID_STRIDE(i, total) {
     // i indexes the NHWC output: ((nb*32 + y)*32 + x)*3 + ch ; source is CHW
     int ch = (int)(i % 3);
     long r = i / 3;
@@ -252,19 +369,34 @@ __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const f
   }
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
 
+// KERNEL<T, V> launch with V = 16 bytes worth of T when `vec_ok`, else V = 1
+#define DISPATCH_TV(dtype, vec_ok, ...)                                                                  \
+  if ((dtype) == RCGAN_F32) {                                                                            \
+    typedef float T;                                                                                     \
+    if (vec_ok) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; }         \
+  } else if ((dtype) == RCGAN_BF16) {                                                                    \
+    typedef bf16 T;                                                                                      \
+    if (vec_ok) { constexpr int V = 8; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; }         \
+  } else { rcgan_set_error("bad dtype %d", (int)(dtype)); return RCGAN_EBADSHAPE; }
 #define DISPATCH_T(dtype, ...)                                   \
   if ((dtype) == RCGAN_F32) { typedef float T; __VA_ARGS__; }     \
   else if ((dtype) == RCGAN_BF16) { typedef bf16 T; __VA_ARGS__; } \
   else { rcgan_set_error("bad dtype %d", (int)(dtype)); return RCGAN_EBADSHAPE; }
 
+static inline int vw(int dtype) { return dtype == RCGAN_F32 ? 4 : 8; }
+
 extern "C" int rcgan_bias_act_fwd(const void* x, const float* bias, void* y, long rows, int c, int ldx, int ldy,
                                   int dtype, int act, float leak, void* stream) {
   RCGAN_CHECK_ARG(rows >= 0 && c > 0 && ldx >= c && ldy >= c, "bias_act_fwd: bad shape");
   if (rows == 0) return 0;
-  DISPATCH_T(dtype, bias_act_fwd_kernel<T><<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)x, bias, (T*)y, rows, c, ldx, ldy, act, leak));
+  const int w = vw(dtype);
+  const bool ok = c % w == 0 && ldx % w == 0 && ldy % w == 0 && aligned16(x) && aligned16(y);
+  DISPATCH_TV(dtype, ok, bias_act_fwd_kernel<T, V><<<grid_for(rows * c / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)x, bias, (T*)y, rows, c, ldx, ldy, act, leak));
   RCGAN_LAUNCH_CHECK("bias_act_fwd");
   return 0;
 }
@@ -273,8 +405,10 @@ extern "C" int rcgan_act_bwd(const void* dy, const void* y, void* dx, long rows,
                              int dtype, int act, float leak, int accumulate, void* stream) {
   RCGAN_CHECK_ARG(rows >= 0 && c > 0, "act_bwd: bad shape");
   if (rows == 0) return 0;
-  DISPATCH_T(dtype, act_bwd_kernel<T><<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)dy, (const T*)y, (T*)dx, rows, c, ld_dy, ld_y, ld_dx, act, leak, accumulate));
+  const int w = vw(dtype);
+  const bool ok = c % w == 0 && ld_dy % w == 0 && ld_y % w == 0 && ld_dx % w == 0 && aligned16(dy) && aligned16(y) && aligned16(dx);
+  DISPATCH_TV(dtype, ok, act_bwd_kernel<T, V><<<grid_for(rows * c / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)dy, (const T*)y, (T*)dx, rows, c, ld_dy, ld_y, ld_dx, act, leak, accumulate));
   RCGAN_LAUNCH_CHECK("act_bwd");
   return 0;
 }
@@ -283,8 +417,10 @@ extern "C" int rcgan_concat_label_fwd(const void* a, int lda, const float* yb, v
                                       int rows_per_sample, int c1, int c2, int dtype, void* stream) {
   RCGAN_CHECK_ARG(rows > 0 && rows_per_sample > 0 && c1 >= 0 && c2 >= 0 && ldo >= c1 + c2 && lda >= c1,
                   "concat_label_fwd: bad shape");
-  DISPATCH_T(dtype, concat_label_kernel<T><<<grid_for(rows * ldo, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)a, lda, yb, (T*)out, ldo, rows, rows_per_sample, c1, c2));
+  const int w = vw(dtype);
+  const bool ok = ldo % w == 0 && lda % w == 0 && aligned16(a) && aligned16(out);
+  DISPATCH_TV(dtype, ok, concat_label_kernel<T, V><<<grid_for(rows * ldo / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)a, lda, yb, (T*)out, ldo, rows, rows_per_sample, c1, c2));
   RCGAN_LAUNCH_CHECK("concat_label_fwd");
   return 0;
 }
@@ -292,16 +428,19 @@ extern "C" int rcgan_concat_label_fwd(const void* a, int lda, const float* yb, v
 extern "C" int rcgan_slice_bwd(const void* dout, int ldo, void* da, int lda, long rows, int c1, int dtype,
                                int accumulate, void* stream) {
   RCGAN_CHECK_ARG(rows > 0 && c1 > 0 && ldo >= c1 && lda >= c1, "slice_bwd: bad shape");
-  DISPATCH_T(dtype, slice_bwd_kernel<T><<<grid_for(rows * c1, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)dout, ldo, (T*)da, lda, rows, c1, accumulate));
+  const int w = vw(dtype);
+  const bool ok = c1 % w == 0 && ldo % w == 0 && lda % w == 0 && aligned16(dout) && aligned16(da);
+  DISPATCH_TV(dtype, ok, slice_bwd_kernel<T, V><<<grid_for(rows * c1 / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)dout, ldo, (T*)da, lda, rows, c1, accumulate));
   RCGAN_LAUNCH_CHECK("slice_bwd");
   return 0;
 }
 
 extern "C" int rcgan_meanhw_fwd(const void* x, void* y, int samples, int hw, int c, int dtype, int relu, void* stream) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "meanhw_fwd: bad shape");
-  DISPATCH_T(dtype, meanhw_fwd_kernel<T><<<grid_for((long)samples * c, 128), 128, 0, as_stream(stream)>>>(
-                        (const T*)x, (T*)y, samples, hw, c, relu));
+  const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
+  DISPATCH_TV(dtype, ok, meanhw_fwd_kernel<T, V><<<grid_for((long)samples * c / V, 128), 128, 0, as_stream(stream)>>>(
+                             (const T*)x, (T*)y, samples, hw, c, relu));
   RCGAN_LAUNCH_CHECK("meanhw_fwd");
   return 0;
 }
@@ -309,62 +448,72 @@ extern "C" int rcgan_meanhw_fwd(const void* x, void* y, int samples, int hw, int
 extern "C" int rcgan_meanhw_bwd(const void* dy, const void* x, void* dx, int samples, int hw, int c, int dtype, int relu,
                                 int accumulate, void* stream) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "meanhw_bwd: bad shape");
-  DISPATCH_T(dtype, meanhw_bwd_kernel<T><<<grid_for((long)samples * hw * c, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)dy, (const T*)x, (T*)dx, samples, hw, c, relu, accumulate));
+  const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(x) && aligned16(dx);
+  DISPATCH_TV(dtype, ok, meanhw_bwd_kernel<T, V><<<grid_for((long)samples * hw * c / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)dy, (const T*)x, (T*)dx, samples, hw, c, relu, accumulate));
   RCGAN_LAUNCH_CHECK("meanhw_bwd");
   return 0;
 }
 
 extern "C" int rcgan_avgpool2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "avgpool2_fwd: bad shape");
-  DISPATCH_T(dtype, avgpool2_fwd_kernel<T><<<grid_for((long)n * h * w * c / 4, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)x, (T*)y, n, h, w, c));
+  const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
+  DISPATCH_TV(dtype, ok, avgpool2_fwd_kernel<T, V><<<grid_for((long)n * h * w * c / 4 / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)x, (T*)y, n, h, w, c));
   RCGAN_LAUNCH_CHECK("avgpool2_fwd");
   return 0;
 }
 extern "C" int rcgan_avgpool2_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dtype, int accumulate,
                                   void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "avgpool2_bwd: bad shape");
-  DISPATCH_T(dtype, avgpool2_bwd_kernel<T><<<grid_for((long)n * h * w * c, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)dy, (T*)dx, n, h, w, c, accumulate));
+  const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(dx);
+  DISPATCH_TV(dtype, ok, avgpool2_bwd_kernel<T, V><<<grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)dy, (T*)dx, n, h, w, c, accumulate));
   RCGAN_LAUNCH_CHECK("avgpool2_bwd");
   return 0;
 }
 extern "C" int rcgan_upsample2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2_fwd: bad shape");
-  DISPATCH_T(dtype, upsample2_fwd_kernel<T><<<grid_for((long)n * h * w * c * 4, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)x, (T*)y, n, h, w, c));
+  const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
+  DISPATCH_TV(dtype, ok, upsample2_fwd_kernel<T, V><<<grid_for((long)n * h * w * c * 4 / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)x, (T*)y, n, h, w, c));
   RCGAN_LAUNCH_CHECK("upsample2_fwd");
   return 0;
 }
 extern "C" int rcgan_upsample2_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dtype, int accumulate,
                                    void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2_bwd: bad shape");
-  DISPATCH_T(dtype, upsample2_bwd_kernel<T><<<grid_for((long)n * h * w * c, 256), 256, 0, as_stream(stream)>>>(
-                        (const T*)dy, (T*)dx, n, h, w, c, accumulate));
+  const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(dx);
+  DISPATCH_TV(dtype, ok, upsample2_bwd_kernel<T, V><<<grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream)>>>(
+                             (const T*)dy, (T*)dx, n, h, w, c, accumulate));
   RCGAN_LAUNCH_CHECK("upsample2_bwd");
   return 0;
 }
 extern "C" int rcgan_add(const void* a, const void* b, void* out, long numel, int dtype, void* stream) {
   RCGAN_CHECK_ARG(numel > 0, "add: bad shape");
-  DISPATCH_T(dtype, add_kernel<T><<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, numel));
+  const bool ok = numel % vw(dtype) == 0 && aligned16(a) && aligned16(b) && aligned16(out);
+  DISPATCH_TV(dtype, ok, add_kernel<T, V><<<grid_for(numel / V, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out,
+                                                                                                  numel / V));
   RCGAN_LAUNCH_CHECK("add");
   return 0;
 }
 extern "C" int rcgan_copy_acc(const void* src, void* dst, long numel, int dtype, int accumulate, void* stream) {
   RCGAN_CHECK_ARG(numel > 0, "copy_acc: bad shape");
-  DISPATCH_T(dtype, copy_acc_kernel<T><<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>((const T*)src, (T*)dst, numel, accumulate));
+  const bool ok = numel % vw(dtype) == 0 && aligned16(src) && aligned16(dst);
+  DISPATCH_TV(dtype, ok, copy_acc_kernel<T, V><<<grid_for(numel / V, 256), 256, 0, as_stream(stream)>>>((const T*)src, (T*)dst,
+                                                                                                       numel / V, accumulate));
   RCGAN_LAUNCH_CHECK("copy_acc");
   return 0;
 }
 extern "C" int rcgan_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long numel, void* stream) {
   RCGAN_CHECK_ARG(numel > 0, "cast: bad shape");
-  int g = grid_for(numel, 256);
+  const int vec = aligned16(src) && aligned16(dst);
+  int g = grid_for(numel / 4 + 1, 256);
   cudaStream_t st = as_stream(stream);
-  if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, numel);
-  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, numel);
-  else if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, numel);
-  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, numel);
+  if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, numel, vec);
+  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, numel, vec);
+  else if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, numel, vec);
+  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, numel, vec);
   else { rcgan_set_error("cast: bad dtypes"); return RCGAN_EBADSHAPE; }
   RCGAN_LAUNCH_CHECK("cast");
   return 0;
@@ -375,8 +524,8 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
   int gx = ceil_div(c, 32);
   int gy = 1;
   if (rows >= 1024) {
-    gy = (2 * RCGAN_NUM_SMS + gx - 1) / gx;
-    int maxy = rows / 256;
+    gy = (4 * RCGAN_NUM_SMS + gx - 1) / gx;
+    int maxy = rows / 128;
     if (gy > maxy) gy = maxy;
     if (gy < 1) gy = 1;
   }

@@ -23,6 +23,11 @@ template <typename T, int V> __device__ __forceinline__ void load_vec(const T* p
   if (sizeof(T) == 4) {
     float4 v = *reinterpret_cast<const float4*>(p);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else if (V == 8) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
   } else {
     uint2 v = *reinterpret_cast<const uint2*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -34,6 +39,12 @@ template <typename T, int V> __device__ __forceinline__ void store_vec(T* p, con
   if (V == 1) { *p = from_f<T>(in[0]); return; }
   if (sizeof(T) == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+  } else if (V == 8) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
   } else {
     uint2 v;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -52,10 +63,10 @@ struct Geo {
   int chunk_rows, nchunk;
 };
 
-Geo make_geo(int samples, int hw, int c, bool per_sample) {
+Geo make_geo(int samples, int hw, int c, bool per_sample, int vmax = 4) {
   Geo g;
   g.rows = samples * hw; g.c = c; g.hw = hw;
-  g.V = (c % 4 == 0) ? 4 : 1;
+  g.V = (vmax == 8 && c % 8 == 0) ? 8 : ((c % 4 == 0) ? 4 : 1);   // 16-byte vectors when both x and y are bf16
   g.cg = c / g.V;
   int lc = 1;
   while (lc < 32 && lc * 2 <= g.cg) lc *= 2;
@@ -91,6 +102,7 @@ __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const TX* __restr
   if (cv < g.cg) {
     const TX* base = x + (size_t)cv * V;
     load_vec<TX, V>(base + (size_t)r0 * g.c, piv);
+#pragma unroll 4
     for (int r = r0 + lr; r < r1; r += g.LR) {
       float v[V];
       load_vec<TX, V>(base + (size_t)r * g.c, v);
@@ -170,6 +182,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
                                                        const int* __restrict__ labels, const float* __restrict__ save,
                                                        int act, float leak) {
   long total = (long)g.rows * g.cg;
+#pragma unroll 4
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i / g.cg;
     int ch = (int)(i - r * g.cg) * V;
@@ -200,6 +213,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restric
   if (cv < g.cg) {
 #pragma unroll
     for (int i = 0; i < V; i++) { mean[i] = save[cv * V + i]; istd[i] = save[g.c + cv * V + i]; }
+#pragma unroll 4
     for (int r = r0 + lr; r < r1; r += g.LR) {
       float vd[V], vx[V], vy[V];
       size_t o = (size_t)r * g.c + (size_t)cv * V;
@@ -290,6 +304,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
                                                         const float* __restrict__ save, const float* __restrict__ AB,
                                                         int act, float leak, int accumulate) {
   long total = (long)g.rows * g.cg;
+#pragma unroll 4
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i / g.cg;
     int ch = (int)(i - r * g.cg) * V;
@@ -329,8 +344,12 @@ inline int check_types(int xd, int yd, const char* who) {
 }  // namespace
 
 extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
-  Geo a = make_geo(samples, hw, c, false), b = make_geo(samples, hw, c, true);
-  int nc = a.nchunk > b.nchunk ? a.nchunk : b.nchunk;
+  int nc = 0;
+  for (int vmax = 4; vmax <= 8; vmax += 4)
+    for (int ps = 0; ps < 2; ps++) {
+      Geo g = make_geo(samples, hw, c, ps != 0, vmax);
+      if (g.nchunk > nc) nc = g.nchunk;
+    }
   return ((size_t)2 * nc * c + 2 * c) * sizeof(float);
 }
 
@@ -341,7 +360,8 @@ extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
     if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
   } else if ((xd) == RCGAN_BF16) {                                                                       \
     typedef bf16 TX; typedef bf16 TY;                                                                    \
-    if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
+    if ((V) == 8) { constexpr int VV = 8; __VA_ARGS__; }                                                 \
+    else if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; } \
   } else {                                                                                               \
     typedef float TX; typedef bf16 TY;                                                                   \
     if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
@@ -356,7 +376,7 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
   RCGAN_CHECK_ARG(x && y && scale && offset && save, "bn_fwd: null pointer");
   RCGAN_CHECK_ARG((long)samples * hw * c < 2147483647L, "bn_fwd: too large");
   cudaStream_t st = as_stream(stream);
-  Geo g = make_geo(samples, hw, c, labels != nullptr);
+  Geo g = make_geo(samples, hw, c, labels != nullptr, 4 /* 16-byte bf16 vectors measured slower: fewer blocks in flight */);
   if (train) {
     RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_fwd: workspace too small");
     dim3 grid(g.gx, g.nchunk);
@@ -385,7 +405,7 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
   RCGAN_CHECK_ARG(dy && x && dx && scale && save && dscale && doffset, "bn_bwd: null pointer");
   RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y, "bn_bwd: activation needs y");
   cudaStream_t st = as_stream(stream);
-  Geo g = make_geo(samples, hw, c, labels != nullptr);
+  Geo g = make_geo(samples, hw, c, labels != nullptr, 4 /* 16-byte bf16 vectors measured slower: fewer blocks in flight */);
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);

@@ -217,7 +217,7 @@ def test_cuda_graph_iterations_match_eager_and_oracle(lib):
     # amplifies only on noise-level gradients
     for n, v in m1.store.vars.items():
         diff = (v.data - m2.store.vars[n].data).abs()
-        assert float(diff.max()) < 2e-3 and float((diff > 1e-4).sum()) <= max(2, 2e-2 * diff.numel()), (n, float(diff.max()))
+        assert float(diff.max()) < 5e-3 and float((diff > 2e-4).sum()) <= max(2, 2e-2 * diff.numel()), (n, float(diff.max()))
 
 
 def test_gen_sampler_uses_moving_stats(lib):
