@@ -42,6 +42,7 @@ struct TcParams {
   // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
   int im_w_lo, im_h_lo, im_sw, im_sh;
   unsigned short toffw[MAX_TAPS], toffh[MAX_TAPS];
+  int dbg;   // experiments only: 1 = skip MMA issue, 2 = skip TMA loads, 4 = skip A load, 8 = skip B load
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -145,19 +146,147 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 64 ? 4 : 3;
+template <int BN, int ST> struct Cfg {
+  static constexpr int STAGES = ST;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one 128 x BN accumulator tile.  A thread owns one TMEM lane = one GEMM row, so writing straight from
+// registers scatters 16-byte pieces over 32 different output rows per store instruction (measured: 400 of 508 us of a
+// 1x1 256->256 conv at 512x32x32 were those stores).  Instead each warp stages its 32 rows in shared memory (row pitch
+// padded by 16 B: conflict-free 16-byte accesses) and then writes whole rows, consecutive lanes on consecutive 16-byte
+// pieces.  Only the owning warp touches its slab, so __syncwarp() orders the two phases.
+template <int BN, int AVAIL, typename TO>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
+                                            int n0) {
+  constexpr int VEC = 16 / (int)sizeof(TO);
+  constexpr int PITCH = BN * (int)sizeof(TO) + 16;
+  constexpr int LPR = BN / VEC;                       // 16-byte pieces per row
+  static_assert(4 * 32 * PITCH + 1024 <= AVAIL, "staging must fit the drained pipeline buffers");
+  uint8_t* slab = smem + warp * (32 * PITCH);
+  unsigned long long* rowoff = reinterpret_cast<unsigned long long*>(smem + 4 * 32 * PITCH) + warp * 32;
+  const int m = m0 + warp * 32 + lane;
+  unsigned long long ob = ~0ull;
+  if (m < p.M) {
+    int b = m % p.MW, r = m / p.MW, a = r % p.MH, n = r / p.MH;
+    ob = ((unsigned long long)(n * p.OH + a * p.oy_mul + p.oy_add) * p.OW + (b * p.ox_mul + p.ox_add)) * p.ld_out;
+  }
+  rowoff[lane] = ob;
+  const int ncols = min(BN, p.N - n0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);   // warp-collective: all lanes execute
+    if (c0 >= ncols || (p.dbg & 16)) continue;
+    // bias and activation with the branches hoisted out of the element loops: the 4 epilogue warps run one per
+    // scheduler, so every per-element branch/constant load is exposed latency (ncu: 25 instr/element before, ~3 now)
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+      const float* bp = p.bias + n0 + c0;
+      if (c0 + 32 <= ncols && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (c0 + j < ncols) v[j] += bp[j];
+      }
+    }
+    switch (p.act) {
+      case RCGAN_ACT_RELU:
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+        break;
+      case RCGAN_ACT_LRELU: {
+        const float leak = p.leak;
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], leak * v[j]);
+        break;
+      }
+      case RCGAN_ACT_SIGMOID:
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 1.f / (1.f + expf(-v[j]));
+        break;
+      case RCGAN_ACT_TANH:
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = tanhf(v[j]);
+        break;
+      default: break;
+    }
+    uint8_t* dst = slab + lane * PITCH + c0 * (int)sizeof(TO);
+#pragma unroll
+    for (int j = 0; j < 32; j += VEC) {
+      uint4 q;
+      if (sizeof(TO) == 4) {
+        q = make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+      } else {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[(j + 2 * e) % 32], v[(j + 2 * e + 1) % 32]);
+      }
+      *reinterpret_cast<uint4*>(dst + (j / VEC) * 16) = q;
+    }
+  }
+  __syncwarp();
+  if (p.dbg & 16) return;
+  TO* out = reinterpret_cast<TO*>(p.out);
+  const bool fast = ncols == BN && p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0;
+  if (fast) {
+#pragma unroll 4
+    for (int idx = lane; idx < 32 * LPR; idx += 32) {
+      const int row = idx / LPR, piece = idx % LPR;
+      const unsigned long long o = rowoff[row];
+      if (o == ~0ull) continue;
+      uint4 q = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
+      TO* g = out + o + n0 + piece * VEC;
+      if (p.accumulate) {
+        const uint4 old = *reinterpret_cast<const uint4*>(g);
+        if (sizeof(TO) == 4) {
+          const float* a = reinterpret_cast<const float*>(&old);
+          float* c = reinterpret_cast<float*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; e++) c[e] += a[e];
+        } else {
+          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&old);
+          __nv_bfloat162* c = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float2 fa = __bfloat1622float2(a[e]), fc = __bfloat1622float2(c[e]);
+            c[e] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(g) = q;
+    }
+  } else {
+    // ragged tile (N not a multiple of the tile, odd strides): element-wise, lanes along the row
+    for (int row = 0; row < 32; row++) {
+      const unsigned long long o = rowoff[row];
+      if (o == ~0ull) continue;
+      const TO* srow = reinterpret_cast<const TO*>(slab + row * PITCH);
+      for (int c = lane; c < ncols; c += 32) {
+        TO* g = out + o + n0 + c;
+        float x = to_f(srow[c]);
+        if (p.accumulate) x += to_f(*g);
+        *g = from_f<TO>(x);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, bool IM2COL>
+template <int BN, int ST, bool IM2COL>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
                                                          const __grid_constant__ CUtensorMap wmap,
                                                          const __grid_constant__ CUtensorMap amap) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, ST>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -170,7 +299,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // 1-D grid, N tiles of one M tile adjacent: the A rows they share are fetched from DRAM once and hit in L2
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m0 = (blockIdx.x / n_tiles) * BM, n0 = (blockIdx.x % n_tiles) * BN;
   const int nkb = p.ntaps * p.kb_per_tap;
 
   if (threadIdx.x == 0) {
@@ -245,58 +376,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     for (int kb = (nkb > LAG ? nkb - LAG : 0); kb < nkb; kb++) mbar_arrive(smem_u32(&full[kb % STAGES]));
     }
 
-    // =========================================================== epilogue: TMEM -> registers -> global
+    // =========================================================== epilogue: TMEM -> registers -> smem -> coalesced global rows
     mbar_wait(smem_u32(accum_full), 0);
     tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const bool mok = m < p.M;
-    size_t obase = 0;
-    if (mok) {
-      int b = m % p.MW, r = m / p.MW, a = r % p.MH, n = r / p.MH;
-      obase = ((size_t)(n * p.OH + a * p.oy_mul + p.oy_add) * p.OW + (b * p.ox_mul + p.ox_add)) * p.ld_out;
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);   // warp-collective: all lanes execute
-      if (!mok || n0 + c0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        int nn = n0 + c0 + j;
-        float x = __uint_as_float(r[j]);
-        if (p.bias && nn < p.N) x += p.bias[nn];
-        v[j] = act_fwd(x, p.act, p.leak);
-      }
-      const bool full32 = (n0 + c0 + 32 <= p.N);
-      if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(p.out) + obase + n0 + c0;
-        if (full32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (n0 + c0 + j < p.N) o[j] = p.accumulate ? o[j] + v[j] : v[j];
-        }
-      } else {
-        bf16* o = reinterpret_cast<bf16*>(p.out) + obase + n0 + c0;
-        if (full32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-            for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(o + j) = q;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (n0 + c0 + j < p.N) o[j] = __float2bfloat16_rn(p.accumulate ? __bfloat162float(o[j]) + v[j] : v[j]);
-        }
-      }
-    }
+    // every TMA/cp.async load has landed and every MMA has retired: the pipeline buffers are free for staging
+    if (p.out_f32) tc_epilogue<BN, C::STAGES * (C::A_BYTES + C::B_BYTES), float>(p, smem, tmem_base, warp, lane, m0, n0);
+    else tc_epilogue<BN, C::STAGES * (C::A_BYTES + C::B_BYTES), bf16>(p, smem, tmem_base, warp, lane, m0, n0);
     tc_fence_before();
   } else if (warp == 4) {
     // =========================================================== B (and, with IM2COL, A) producer (TMA)
@@ -308,6 +393,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         mbar_wait(smem_u32(&empty[s]), ((kb / STAGES) & 1) ^ 1);
         const int tap = kb / p.kb_per_tap;
         const int k0 = (kb - tap * p.kb_per_tap) * BK;
+        if (p.dbg & 14) {
+          const bool la = IM2COL && !(p.dbg & 6), lb = !(p.dbg & 10);
+          mbar_arrive_expect_tx(smem_u32(&full[s]), (lb ? C::B_BYTES : 0) + (la ? C::A_BYTES : 0));
+          if (la) tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES), &amap, smem_u32(&full[s]), k0, im_w, im_h, im_n, p.toffw[tap],
+                                     p.toffh[tap]);
+          if (lb) tma_load_3d(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0, p.twi[tap]);
+          continue;
+        }
         mbar_arrive_expect_tx(smem_u32(&full[s]), C::B_BYTES + (IM2COL ? C::A_BYTES : 0));
         if (IM2COL)
           tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES), &amap, smem_u32(&full[s]), k0, im_w, im_h, im_n, p.toffw[tap],
@@ -325,9 +418,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         tc_fence_after();
         const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + s * C::A_BYTES));
         const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + s * C::B_BYTES));
+        if (!(p.dbg & 1)) {
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)   // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
           umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
         umma_commit(smem_u32(&empty[s]));   // implies tcgen05.fence::before_thread_sync
       }
       umma_commit(smem_u32(accum_full));
@@ -680,16 +775,16 @@ int make_wmap(CUtensorMap* map, const bf16* base, int kpad, int rows, int taps, 
   return 0;
 }
 
-template <int BN, bool IM2COL>
+template <int BN, int ST, bool IM2COL>
 int launch_tc(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, ST>::SMEM);
     if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
-  conv_tc_kernel<BN, IM2COL><<<grid, 192, Cfg<BN>::SMEM, st>>>(p, map, amap);
+  dim3 grid(((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN));
+  conv_tc_kernel<BN, ST, IM2COL><<<grid, 192, Cfg<BN, ST>::SMEM, st>>>(p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc");
   return 0;
 }
@@ -717,13 +812,26 @@ bool make_amap(CUtensorMap* map, const TcParams& p, int channels, int nimg) {
   return r == CUDA_SUCCESS;
 }
 
+// experiment switch (read per call): RCGAN_TC_VARIANT=1 -> BN=128 with 6 stages (1 CTA/SM), 2 -> BN=256 for N >= 256
+int tc_variant() {
+  const char* e = getenv("RCGAN_TC_VARIANT");
+  return e ? atoi(e) : 0;
+}
+
 int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int channels, int nimg, cudaStream_t st) {
-  const int bn = p.N <= 64 ? 64 : 128;
+  const int var = tc_variant();
+  { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap map, amap;
+  const bool im2col = make_amap(&amap, p, channels, nimg);
+  const int bn = p.N <= 64 ? 64 : ((var == 2 && p.N >= 256 && im2col) ? 256 : 128);
   if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
-  if (make_amap(&amap, p, channels, nimg))
-    return bn == 64 ? launch_tc<64, true>(p, map, amap, st) : launch_tc<128, true>(p, map, amap, st);
-  return bn == 64 ? launch_tc<64, false>(p, map, map, st) : launch_tc<128, false>(p, map, map, st);
+  if (im2col) {
+    if (bn == 64) return launch_tc<64, 4, true>(p, map, amap, st);
+    if (bn == 256) return launch_tc<256, 4, true>(p, map, amap, st);
+    if (var == 1) return launch_tc<128, 6, true>(p, map, amap, st);
+    return launch_tc<128, 3, true>(p, map, amap, st);
+  }
+  return bn == 64 ? launch_tc<64, 4, false>(p, map, map, st) : launch_tc<128, 3, false>(p, map, map, st);
 }
 
 }  // namespace

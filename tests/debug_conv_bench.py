@@ -1,0 +1,76 @@
+"""Micro-benchmark of single conv launches through the C ABI (debug helper, not a test).
+usage: python tests/debug_conv_bench.py  [variant ...]"""
+import os, sys, ctypes
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from robust_conditional_gan_b200 import _C
+
+SHAPES = [  # n, h, w, cin, cout, k
+    (256, 8, 8, 128, 128, 3),
+    (256, 32, 32, 128, 128, 3),
+    (512, 32, 32, 256, 256, 1),
+    (512, 32, 32, 256, 256, 3),
+]
+
+
+def desc(n, h, w, cin, cout, k):
+    d = _C.ConvDesc()
+    d.n, d.h, d.w, d.cin, d.ho, d.wo, d.cout = n, h, w, cin, h, w, cout
+    d.kh = d.kw = k
+    d.stride = 1
+    d.pad_t = d.pad_l = (k - 1) // 2
+    d.ldx, d.ldy, d.dtype = cin, cout, _C.BF16
+    return d
+
+
+def main():
+    variants = [v for v in sys.argv[1:]] or ['0', '1', '2']
+    dev = torch.device('cuda:0')
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    only = os.environ.get('CONV_BENCH_ONLY')
+    for si, shp in enumerate(SHAPES):
+        if only is not None and int(only) != si:
+            continue
+        n, h, w, cin, cout, k = shp
+        d = desc(*shp)
+        x = torch.randn(n, h, w, cin, device=dev).bfloat16()
+        wt = torch.randn(k, k, cin, cout, device=dev) * 0.05
+        y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+        nb = _C.load().rcgan_conv_wpack_bytes(ctypes.byref(d))
+        pack = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _C.call('rcgan_conv_wpack', ctypes.byref(d), wt.data_ptr(), None, pack.data_ptr(), st)
+        ref = None
+        for var in variants:
+            os.environ['RCGAN_TC_VARIANT'] = var.split(':')[0]
+            os.environ['RCGAN_TC_DBG'] = var.split(':')[1] if ':' in var else '0'
+            ts = []
+            for it in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _C.call('rcgan_conv2d_fprop', ctypes.byref(d), x.data_ptr(), wt.data_ptr(), pack.data_ptr(), None, y.data_ptr(),
+                        _C.BF16, 0, 0.0, st)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            # back-to-back (warm L2) timing
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(20):
+                _C.call('rcgan_conv2d_fprop', ctypes.byref(d), x.data_ptr(), wt.data_ptr(), pack.data_ptr(), None, y.data_ptr(),
+                        _C.BF16, 0, 0.0, st)
+            e1.record()
+            torch.cuda.synchronize()
+            warm = e0.elapsed_time(e1) / 20
+            if ref is None:
+                ref = y.float().clone()
+                err = 0.0
+            else:
+                err = float((y.float() - ref).abs().max())
+            fl = 2.0 * n * h * w * cin * cout * k * k
+            print(f'{shp} var={var} cold {min(ts[1:])*1e3:8.1f} us  warm {warm*1e3:8.1f} us  {fl/warm/1e9:7.1f} TF/s  maxdiff_vs_var0 {err:.3g}', flush=True)
+
+
+if __name__ == '__main__':
+    main()
