@@ -586,24 +586,48 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     for (int kk = (nkb > LAG ? nkb - LAG : 0); kk < nkb; kk++) mbar_arrive(smem_u32(&full[kk % STAGES]));
     }
 
-    // ---- epilogue: accumulator row r = unit (r / 64), channel (r % 64)
+    // ---- epilogue: accumulator row r = unit (r / 64), channel (r % 64).  A thread owns a row, so reducing straight from
+    // registers would issue one L2 atomic per element with 32 different lines per instruction; instead each warp stages
+    // its 32 rows in the drained pipeline buffers and reduces whole rows: 32 lanes x 16 bytes = one 512-byte
+    // red.global.add.v4.f32 per row (scalar, still lane-contiguous, when cout or the base is not 16-byte friendly).
     mbar_wait(smem_u32(accum_full), 0);
     tc_fence_after();
-    const int r = warp * 32 + lane;
-    const int u = u0 + (r >> 6);
-    int tap = 0, ci = p.cin;
-    if (u < p.units) { tap = u / p.cblks; ci = (u - tap * p.cblks) * 64 + (r & 63); }
-    const bool rok = ci < p.cin;
-    float* orow = p.dw + ((size_t)tap * p.cin + (rok ? ci : 0)) * p.cout;
+    constexpr int PITCH = BN * 4 + 16;
+    static_assert(4 * 32 * PITCH <= STAGES * (C::A_BYTES + C::B_BYTES), "staging must fit the drained pipeline buffers");
+    uint8_t* slab = smem + warp * (32 * PITCH);
+    const int ncols = min(BN, p.cout - n0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (!rok) continue;
+      if (c0 >= ncols) continue;
+      uint4* dst = reinterpret_cast<uint4*>(slab + lane * PITCH + c0 * 4);
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        int co = n0 + c0 + j;
-        if (co < p.cout) atomicAdd(orow + co, __uint_as_float(v[j]));
+      for (int j = 0; j < 8; j++) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    // the warp's 32 rows belong to one unit: rows (tap, cb*64 + (warp&1)*32 + i), i = 0..31
+    const int u = u0 + (warp >> 1);
+    if (u < p.units) {
+      const int tap = u / p.cblks;
+      const int ci0 = (u - tap * p.cblks) * 64 + (warp & 1) * 32;
+      float* obase = p.dw + ((size_t)tap * p.cin + ci0) * p.cout + n0;
+      const int nrows = min(32, p.cin - ci0);
+      const bool vec = (ncols % 4 == 0) && (p.cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+      if (vec) {
+        const int lpr = ncols / 4;                    // 16-byte pieces per row
+        for (int idx = lane; idx < nrows * lpr; idx += 32) {
+          const int row = idx / lpr, piece = idx - row * lpr;
+          const float4 q = *reinterpret_cast<const float4*>(slab + row * PITCH + piece * 16);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(obase + (size_t)row * p.cout + piece * 4), "f"(q.x),
+                       "f"(q.y), "f"(q.z), "f"(q.w)
+                       : "memory");
+        }
+      } else {
+        for (int row = 0; row < nrows; row++) {
+          const float* srow = reinterpret_cast<const float*>(slab + row * PITCH);
+          for (int c = lane; c < ncols; c += 32) atomicAdd(obase + (size_t)row * p.cout + c, srow[c]);
+        }
       }
     }
     tc_fence_before();
@@ -953,7 +977,9 @@ int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, floa
   p.dw = dw;
   const int bn = d->cout <= 64 ? 64 : 128;
   const int tiles = ((p.units + 1) / 2) * ((d->cout + bn - 1) / bn);
-  int splits = (2 * RCGAN_NUM_SMS + tiles - 1) / tiles;        // aim for ~2 CTAs per SM worth of work items
+  int waves_x2 = 2;                                            // experiment: RCGAN_WG_WAVES_X2 = CTAs per SM x 2
+  { const char* e = getenv("RCGAN_WG_WAVES_X2"); if (e) waves_x2 = atoi(e); }
+  int splits = (waves_x2 * RCGAN_NUM_SMS / 2 + (waves_x2 > 2 ? tiles - 1 : 0)) / tiles;
   int max_splits = (p.kb_total + 3) / 4;                        // at least 4 K blocks (512 pixels) per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

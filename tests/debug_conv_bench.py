@@ -69,6 +69,34 @@ def main():
             else:
                 err = float((y.float() - ref).abs().max())
             fl = 2.0 * n * h * w * cin * cout * k * k
+            if os.environ.get('CONV_BENCH_BWD') and var == variants[0]:
+                dy = torch.randn(n, h, w, cout, device=dev).bfloat16()
+                dx = torch.empty(n, h, w, cin, device=dev, dtype=torch.bfloat16)
+                dw = torch.empty(k, k, cin, cout, device=dev)
+                db = torch.empty(cout, device=dev)
+                wsb = _C.load().rcgan_conv2d_wgrad_workspace(ctypes.byref(d))
+                ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+                for nm, fn in (('dgrad', lambda: _C.call('rcgan_conv2d_dgrad', ctypes.byref(d), dy.data_ptr(), wt.data_ptr(), pack.data_ptr(),
+                                                          None, dx.data_ptr(), _C.BF16, 0, 0.0, 0, st)),
+                               ('wgrad', lambda: _C.call('rcgan_conv2d_wgrad', ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 0,
+                                                          ws.data_ptr(), wsb, st)),
+                               ('colsum', lambda: _C.call('rcgan_colsum', dy.data_ptr(), n * h * w, cout, cout, _C.BF16, db.data_ptr(), 0, st))):
+                  for wv in os.environ.get('WG_WAVES', '2').split(','):
+                    os.environ['RCGAN_WG_WAVES_X2'] = wv
+                    if nm != 'wgrad' and wv != os.environ.get('WG_WAVES', '2').split(',')[0]:
+                        continue
+                    fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for it in range(20):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tt = e0.elapsed_time(e1) / 20
+                    print(f'{shp} {nm} wv={wv} warm {tt*1e3:8.1f} us  {fl/tt/1e9:7.1f} TF/s', flush=True)
+                refw = torch.einsum('nhwc,nhwd->cd', x.float(), dy.float()) if k == 1 else None
+                if refw is not None:
+                    print('   wgrad relerr', float((dw[0, 0] - refw).abs().max() / refw.abs().max()))
             print(f'{shp} var={var} cold {min(ts[1:])*1e3:8.1f} us  warm {warm*1e3:8.1f} us  {fl/warm/1e9:7.1f} TF/s  maxdiff_vs_var0 {err:.3g}', flush=True)
 
 
