@@ -84,6 +84,11 @@ int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, 
  * m = (n, oy, ox), row stride ldp.  The conv then runs as a dense GEMM on the tensor cores (1x1 desc over P) instead of a
  * K = 25..27 implicit GEMM on CUDA cores.  Same dtype as d->dtype. */
 int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp, void* stream);
+/* Filter of the transposed conv: out[kh-1-ky][kw-1-kx][co][ci] (=|+=) w[ky][kx][ci][co], fp32.  The input gradient of a
+ * stride-1 conv with very few OUTPUT channels (G.Output, cifar10/gan_resnet.py:405-407: 256 -> 3) is the conv of dL/dy with
+ * this filter, so its backward runs as patch-matrix GEMMs like the few-input-channel convs above; applied to the GEMM's
+ * filter gradient (cin/cout swapped) the same call maps it back. */
+int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- rows x channels helpers */
 /* db[c] (=|+=) sum_r dy[r,c]   (bias gradients of conv / deconv / linear) */

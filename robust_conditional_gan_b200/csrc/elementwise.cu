@@ -351,6 +351,19 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n,
   }
 }
 
+__global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ out, int kh, int kw, int cin, int cout,
+                             int accumulate) {
+  long total = (long)kh * kw * cin * cout;
+  GRID_STRIDE(i, total) {      // i indexes out: [tap'][co][ci]
+    int ci = (int)(i % cin);
+    long r = i / cin;
+    int co = (int)(r % cout), tp = (int)(r / cout);
+    int ky = kh - 1 - tp / kw, kx = kw - 1 - tp % kw;
+    float v = w[((size_t)(ky * kw + kx) * cin + ci) * cout + co];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+
 __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
   long total = (long)n * 3072;
@@ -547,6 +560,13 @@ extern "C" int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patch
                            (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
                            d->pad_l, d->ldx, ldp));
   RCGAN_LAUNCH_CHECK("im2col");
+  return 0;
+}
+
+extern "C" int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream) {
+  RCGAN_CHECK_ARG(w && out && kh > 0 && kw > 0 && cin > 0 && cout > 0, "wflip: bad args");
+  wflip_kernel<<<grid_for((long)kh * kw * cin * cout, 256), 256, 0, as_stream(stream)>>>(w, out, kh, kw, cin, cout, accumulate);
+  RCGAN_LAUNCH_CHECK("wflip");
   return 0;
 }
 

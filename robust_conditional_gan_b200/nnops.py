@@ -72,6 +72,18 @@ class ConvOp(Op):
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
+        # few-channel OUTPUTS (G.Output: 256 -> 3): the backward is the transposed conv of dL/dy (cin' = cout <= 4) with the
+        # flipped filter, so it runs as GEMMs on the patch matrix of dL/dy (rcgan_wflip in the header)
+        self.tpatch = None
+        if stride == 1 and cout <= 4 and cin >= 32 and self.patch is None:
+            self.tdesc = ConvDesc(n, ho, wo, cout, h, wd, cin, kh, kw, 1, kh - 1 - pt, kw - 1 - pl, self.y.ld, x.ld, x.dtype)
+            self.tpatch, self.tgdesc = make_patch(prog, self.tdesc, n * h * wd, x.ld)
+        if self.tpatch is not None:
+            nflip = kh * kw * cout * cin
+            self.wflip = torch.zeros(nflip, dtype=torch.float32, device=prog.device)
+            self.dwflip = torch.zeros(nflip, dtype=torch.float32, device=prog.device)
+            self.tpack = torch.zeros(_C.load().rcgan_conv_wpack_bytes(self.tgdesc), dtype=torch.uint8, device=prog.device)
+            prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.tgdesc))
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -79,6 +91,19 @@ class ConvOp(Op):
         self.acc_x = self.claim(self.x) if nx else 0
         self.acc_w = self.claim(self.w) if nw else 0
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
+
+    def _backward_transposed(self, prog, nx, nw, dy, st):
+        d = self.desc
+        call('rcgan_im2col', self.tdesc, dy, dp(self.tpatch), self.tpatch.ld, st)
+        if nx:
+            call('rcgan_wflip', dp(self.w), pp(self.wflip), d.kh, d.kw, d.cin, d.cout, 0, st)
+            call('rcgan_conv_wpack', self.tgdesc, pp(self.wflip), None, pp(self.tpack), st)
+            call('rcgan_conv2d_fprop', self.tgdesc, dp(self.tpatch), pp(self.wflip), pp(self.tpack), None, gp(self.x),
+                 self.x.grad_dtype, _C.ACT_NONE, 0.0, st)
+        if nw:
+            # d(flipped filter)[k', ci] = sum_m patch[m, k'] * x[m, ci]: the GEMM desc's wgrad with x in the dy role
+            call('rcgan_conv2d_wgrad', self.tgdesc, dp(self.tpatch), dp(self.x), pp(self.dwflip), 0, prog.ws.ptr(), prog.ws.bytes, st)
+            call('rcgan_wflip', pp(self.dwflip), gp(self.w), d.kh, d.kw, d.cout, d.cin, self.acc_w, st)
 
     def forward(self, prog):
         d, xin = self.desc, dp(self.x)
@@ -98,6 +123,9 @@ class ConvOp(Op):
         y, dy = self.y, gp(self.y)
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):
+            self._backward_transposed(prog, nx, nw, dy, st)
+            nx = nw = False
         if nx:
             call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
                  gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)

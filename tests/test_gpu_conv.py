@@ -265,3 +265,39 @@ def test_narrow_wgrad(lib, shape, dtype):
     assert relerr(dw, wr.grad) < 2e-5
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
     assert relerr(dw, 2 * wr.grad) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32, 256, 3, 3, 1, 0, 5), (3, 8, 8, 64, 2, 3, 1, 0, 6), (2, 16, 16, 128, 4, 5, 1, 0, 4)])
+def test_few_output_channel_backward_as_transposed_patch_gemm(lib, shape):
+    """G.Output (256 -> 3, gan_resnet.py:405-407): dL/dx and dL/dw through rcgan_wflip + patch matrix of dL/dy + the
+    tensor-core GEMMs, the call sequence ConvOp._backward_transposed issues."""
+    dtype = _C.BF16
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, h, w, cin, cout, k, s = shape[:7]
+    xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    O.conv2d(xr, wr, s).backward(dy.double())
+    td = ConvDesc(n, ho, wo, cout, h, w, cin, k, k, 1, k - 1 - d.pad_t, k - 1 - d.pad_l, ldy, ldx, dtype)
+    kp = k * k * cout
+    ldp = (kp + 7) // 8 * 8
+    patch = torch.full((n * h * w, ldp), 9.0, device='cuda', dtype=torch.bfloat16)
+    g = ConvDesc(n * h * w, 1, 1, kp, 1, 1, cin, 1, 1, 1, 0, 0, ldp, ldx, dtype)
+    assert lib.rcgan_conv_uses_tensor_cores(g, 0) and lib.rcgan_conv_uses_tensor_cores(g, 2)
+    wdev = dev(wt)
+    call('rcgan_im2col', td, dyd.data_ptr(), patch.data_ptr(), ldp, st())
+    wflip = torch.zeros(kp * cin, device='cuda')
+    call('rcgan_wflip', wdev.data_ptr(), wflip.data_ptr(), k, k, cin, cout, 0, st())
+    ref_flip = wt.flip(0, 1).permute(0, 1, 3, 2).reshape(-1)
+    assert float((wflip.cpu() - ref_flip).abs().max()) == 0.0
+    pack = torch.zeros(lib.rcgan_conv_wpack_bytes(g), dtype=torch.uint8, device='cuda')
+    call('rcgan_conv_wpack', g, wflip.data_ptr(), None, pack.data_ptr(), st())
+    dx = torch.zeros(n, h, w, ldx, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_conv2d_fprop', g, patch.data_ptr(), wflip.data_ptr(), pack.data_ptr(), None, dx.data_ptr(), dtype,
+         _C.ACT_NONE, 0.0, st())
+    assert relerr(dx[..., :cin].float(), xr.grad) < TOL[dtype]
+    nb = lib.rcgan_conv2d_wgrad_workspace(g)
+    ws = torch.zeros(max(nb, 4), dtype=torch.uint8, device='cuda')
+    dwflip = torch.full((kp * cin,), 3.0, device='cuda')
+    call('rcgan_conv2d_wgrad', g, patch.data_ptr(), xd.data_ptr(), dwflip.data_ptr(), 0, ws.data_ptr(), nb, st())
+    dw = torch.full(wt.shape, 1.0, device='cuda')
+    call('rcgan_wflip', dwflip.data_ptr(), dw.data_ptr(), k, k, cout, cin, 1, st())
+    assert relerr(dw - 1.0, wr.grad) < TOL[dtype]
