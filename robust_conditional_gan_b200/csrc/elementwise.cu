@@ -329,6 +329,45 @@ __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld,
   }
 }
 
+// vector variant: LC lanes along 16-byte channel vectors x LR row lanes; one slab of rows per blockIdx.y
+template <typename T, int V>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, int rows, int cg, int ld, int LC,
+                                                         float* __restrict__ db, int accumulate, int use_atomic) {
+  __shared__ float sh[256 * V];
+  const int LR = 256 / LC;
+  const int lc = threadIdx.x % LC, lr = threadIdx.x / LC;
+  const int cv = blockIdx.x * LC + lc;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) acc[k] = 0.f;
+  if (cv < cg) {
+    const T* p = dy + (size_t)cv * V;
+#pragma unroll 4
+    for (int r = r0 + lr; r < r1; r += LR) {
+      float v[V];
+      ldv<T, V>(p + (size_t)r * ld, v);
+#pragma unroll
+      for (int k = 0; k < V; k++) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; k++) sh[(lr * LC + lc) * V + k] = acc[k];
+  __syncthreads();
+  // LC*V channel sums, one per thread of the first LC*V threads
+  const int t = threadIdx.x;
+  if (t < LC * V) {
+    const int ch = blockIdx.x * LC * V + t;
+    if (ch < cg * V) {
+      float s = 0.f;
+      for (int k = 0; k < LR; k++) s += sh[k * LC * V + t];
+      if (use_atomic) atomicAdd(&db[ch], s);
+      else db[ch] = accumulate ? db[ch] + s : s;
+    }
+  }
+}
+
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n, int h, int w, int cin, int ho, int wo, int kh,
                               int kw, int stride, int pad_t, int pad_l, int ldx, int ldp) {
@@ -348,6 +387,39 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n,
       if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = x[((nb * h + iy) * w + ix) * ldx + ci];
     }
     P[i] = v;
+  }
+}
+
+// bf16 patch rows, one 16-byte store (8 consecutive k) per thread; ldp % 8 == 0 and a 16-byte aligned patch base
+__global__ void __launch_bounds__(256) im2col_bf16x8_kernel(const bf16* __restrict__ x, bf16* __restrict__ P, int n, int h, int w,
+                                                            int cin, int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l,
+                                                            int ldx, int ldp) {
+  const int K = kh * kw * cin, pieces = ldp / 8;
+  const long total = (long)n * ho * wo * pieces;
+  GRID_STRIDE(i, total) {
+    const int piece = (int)(i % pieces);
+    const long m = i / pieces;
+    const int ox = (int)(m % wo);
+    const long r = m / wo;
+    const int oy = (int)(r % ho);
+    const long nb = r / ho;
+    const int by = oy * stride - pad_t, bx = ox * stride - pad_l;
+    const bf16* xb = x + (size_t)nb * h * w * ldx;
+    uint4 q;
+    bf16* e = reinterpret_cast<bf16*>(&q);
+    int k = piece * 8;
+    int tap = k / cin, ci = k - tap * cin;
+#pragma unroll
+    for (int j = 0; j < 8; j++, k++) {
+      bf16 v = __float2bfloat16_rn(0.f);
+      if (k < K) {
+        const int iy = by + tap / kw, ix = bx + tap % kw;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = xb[((size_t)iy * w + ix) * ldx + ci];
+      }
+      e[j] = v;
+      if (++ci == cin) { ci = 0; tap++; }
+    }
+    *reinterpret_cast<uint4*>(P + m * ldp + piece * 8) = q;
   }
 }
 
@@ -534,7 +606,18 @@ extern "C" int rcgan_cast(const void* src, int src_dtype, void* dst, int dst_dty
 
 extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream) {
   RCGAN_CHECK_ARG(rows > 0 && c > 0 && ld >= c, "colsum: bad shape");
-  int gx = ceil_div(c, 32);
+  cudaStream_t st = as_stream(stream);
+  const int w = vw(dtype);
+  const bool vec = c % w == 0 && ld % w == 0 && aligned16(dy) && rows >= 64;
+  int gx, LC = 32;
+  if (vec) {
+    const int cg = c / w;
+    LC = 1;
+    while (LC < 32 && LC * 2 <= cg) LC *= 2;
+    gx = ceil_div(cg, LC);
+  } else {
+    gx = ceil_div(c, 32);
+  }
   int gy = 1;
   if (rows >= 1024) {
     gy = (4 * RCGAN_NUM_SMS + gx - 1) / gx;
@@ -542,13 +625,19 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
     if (gy > maxy) gy = maxy;
     if (gy < 1) gy = 1;
   }
-  cudaStream_t st = as_stream(stream);
   if (gy > 1 && !accumulate) {
     cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * c, st);
     if (e != cudaSuccess) { rcgan_set_error("colsum: memset failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
   }
-  dim3 grid(gx, gy), block(32, 8);
-  DISPATCH_T(dtype, colsum_kernel<T><<<grid, block, 0, st>>>((const T*)dy, rows, c, ld, db, accumulate, gy > 1));
+  if (vec) {
+    dim3 grid(gx, gy);
+    if (dtype == RCGAN_F32) colsum_vec_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)dy, rows, c / 4, ld, LC, db, accumulate, gy > 1);
+    else if (dtype == RCGAN_BF16) colsum_vec_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)dy, rows, c / 8, ld, LC, db, accumulate, gy > 1);
+    else { rcgan_set_error("bad dtype %d", dtype); return RCGAN_EBADSHAPE; }
+  } else {
+    dim3 grid(gx, gy), block(32, 8);
+    DISPATCH_T(dtype, colsum_kernel<T><<<grid, block, 0, st>>>((const T*)dy, rows, c, ld, db, accumulate, gy > 1));
+  }
   RCGAN_LAUNCH_CHECK("colsum");
   return 0;
 }
@@ -556,6 +645,13 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
 extern "C" int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp, void* stream) {
   RCGAN_CHECK_ARG(d && x && patches && ldp >= d->kh * d->kw * d->cin, "im2col: bad args");
   long total = (long)d->n * d->ho * d->wo * ldp;
+  if (d->dtype == RCGAN_BF16 && ldp % 8 == 0 && aligned16(patches)) {
+    im2col_bf16x8_kernel<<<grid_for(total / 8, 256), 256, 0, as_stream(stream)>>>(
+        (const bf16*)x, (bf16*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx,
+        ldp);
+    RCGAN_LAUNCH_CHECK("im2col");
+    return 0;
+  }
   DISPATCH_T(d->dtype, im2col_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
                            (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
                            d->pad_l, d->ldx, ldp));

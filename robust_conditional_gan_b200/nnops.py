@@ -72,6 +72,11 @@ class ConvOp(Op):
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
+        # ... their input gradient (a 3-channel result from a wide dL/dy: D.Block.1 in the G step) still streams best through
+        # the implicit-GEMM dgrad, which needs the pack of the TRUE conv geometry
+        self.dpack = None
+        if self.patch is not None and _C.load().rcgan_conv_uses_tensor_cores(self.desc, 1):
+            self.dpack = torch.zeros(_C.load().rcgan_conv_wpack_bytes(self.desc), dtype=torch.uint8, device=prog.device)
         # few-channel OUTPUTS (G.Output: 256 -> 3): the backward is the transposed conv of dL/dy (cin' = cout <= 4) with the
         # flipped filter, so it runs as GEMMs on the patch matrix of dL/dy (rcgan_wflip in the header)
         self.tpatch = None
@@ -127,7 +132,11 @@ class ConvOp(Op):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
         if nx:
-            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
+            dpack = None if self.patch is not None else self.pack
+            if self.dpack is not None:
+                call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.dpack), st)
+                dpack = self.dpack
+            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), pp(dpack), None,
                  gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
         if nw:
             if self.patch is not None:
