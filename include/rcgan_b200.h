@@ -89,6 +89,13 @@ int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp
  * this filter, so its backward runs as patch-matrix GEMMs like the few-input-channel convs above; applied to the GEMM's
  * filter gradient (cin/cout swapped) the same call maps it back. */
 int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream);
+/* Adjoint of rcgan_im2col: x[n, iy, ix, ci] (=|+=) act(bias[ci] + sum over taps (ky,kx) with (iy + pad_t - ky) % s == 0 ... of
+ * T[(n, oy, ox), (ky*kw + kx)*cin + ci]), T fp32 with row stride ldt.  With T = dy[M, cout] * W^T[cout, kh*kw*cin] (one dense
+ * GEMM that reads dy once) this is the input gradient of a conv with cin <= 4 -- i.e. the FORWARD of g_h3's
+ * conv2d_transpose to the 1-channel image (mnist/model.py:726-728, ops.py:69-92) and the gradient d_h0_conv sends back into the
+ * generated image (mnist/model.py:678) -- instead of a per-pixel gather that re-reads dy once per filter tap. */
+int rcgan_col2im(const rcgan_conv_desc* d, const float* T, int ldt, const float* bias, void* x, int out_dtype, int act,
+                 float leak, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- rows x channels helpers */
 /* db[c] (=|+=) sum_r dy[r,c]   (bias gradients of conv / deconv / linear) */

@@ -43,6 +43,7 @@ _SIGS = {
     'rcgan_conv2d_wgrad': (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),
     'rcgan_im2col': (c_int, [DP, P, P, c_int, P]),
     'rcgan_wflip': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_col2im': (c_int, [DP, P, c_int, P, P, c_int, c_int, c_float, c_int, P]),
     'rcgan_colsum': (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, P]),
     'rcgan_bias_act_fwd': (c_int, [P, P, P, c_long, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     'rcgan_act_bwd': (c_int, [P, P, P, c_long, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P]),

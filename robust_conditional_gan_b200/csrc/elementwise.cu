@@ -423,6 +423,35 @@ __global__ void __launch_bounds__(256) im2col_bf16x8_kernel(const bf16* __restri
   }
 }
 
+template <typename TO>
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ T, int ldt, const float* __restrict__ bias,
+                                                     TO* __restrict__ x, int n, int h, int w, int cin, int ho, int wo, int kh, int kw,
+                                                     int stride, int pad_t, int pad_l, int ldx, int act, float leak, int accumulate) {
+  const long total = (long)n * h * w * cin;
+  GRID_STRIDE(i, total) {
+    const int ci = (int)(i % cin);
+    long r = i / cin;
+    const int ix = (int)(r % w);
+    r /= w;
+    const int iy = (int)(r % h);
+    const long nb = r / h;
+    float acc = bias ? bias[ci] : 0.f;
+    // taps of this pixel's parity class: ky = (iy + pad_t) % s + s*j  <->  oy = (iy + pad_t - ky) / s
+    for (int ky = (iy + pad_t) % stride; ky < kh; ky += stride) {
+      const int oy = (iy + pad_t - ky) / stride;
+      if (iy + pad_t - ky < 0 || oy >= ho) continue;
+      for (int kx = (ix + pad_l) % stride; kx < kw; kx += stride) {
+        const int ox = (ix + pad_l - kx) / stride;
+        if (ix + pad_l - kx < 0 || ox >= wo) continue;
+        acc += T[((nb * ho + oy) * wo + ox) * ldt + (ky * kw + kx) * cin + ci];
+      }
+    }
+    acc = act_fwd(acc, act, leak);
+    TO* o = x + ((nb * h + iy) * w + ix) * ldx + ci;
+    *o = from_f<TO>(accumulate ? to_f(*o) + acc : acc);
+  }
+}
+
 __global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ out, int kh, int kw, int cin, int cout,
                              int accumulate) {
   long total = (long)kh * kw * cin * cout;
@@ -656,6 +685,24 @@ extern "C" int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patch
                            (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
                            d->pad_l, d->ldx, ldp));
   RCGAN_LAUNCH_CHECK("im2col");
+  return 0;
+}
+
+extern "C" int rcgan_col2im(const rcgan_conv_desc* d, const float* T, int ldt, const float* bias, void* x, int out_dtype, int act,
+                            float leak, int accumulate, void* stream) {
+  RCGAN_CHECK_ARG(d && T && x && ldt >= d->kh * d->kw * d->cin && d->stride >= 1, "col2im: bad args");
+  const long total = (long)d->n * d->h * d->w * d->cin;
+  RCGAN_CHECK_ARG(total > 0, "col2im: empty");
+  if (out_dtype == RCGAN_F32)
+    col2im_kernel<float><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(T, ldt, bias, (float*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
+                                                                            d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
+                                                                            accumulate);
+  else if (out_dtype == RCGAN_BF16)
+    col2im_kernel<bf16><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(T, ldt, bias, (bf16*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
+                                                                           d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
+                                                                           accumulate);
+  else { rcgan_set_error("col2im: bad dtype %d", out_dtype); return RCGAN_EBADSHAPE; }
+  RCGAN_LAUNCH_CHECK("col2im");
   return 0;
 }
 

@@ -36,6 +36,37 @@ def make_patch(prog, desc, rows, ld_out):
     return patch, g
 
 
+class ScatterDgrad:
+    """Input gradient of a conv with cin <= 4 (equivalently the forward of the conv2d_transpose it defines) as ONE dense
+    GEMM T = dy[M, cout] * W^T[cout, kh*kw*cin] on the tensor cores followed by rcgan_col2im: dy is read once instead of
+    once per filter tap.  None-like (ok == False) when the shape does not qualify."""
+
+    def __init__(self, prog, desc, ld_dy):
+        kp = desc.kh * desc.kw * desc.cin
+        rows = desc.n * desc.ho * desc.wo
+        self.ok = desc.dtype == _C.BF16 and desc.cin <= 4 and kp <= 128 and desc.cout >= 32 and ld_dy % 8 == 0
+        if not self.ok:
+            return
+        self.desc, self.kp = desc, kp
+        self.ldt = round_up(kp, 8)
+        self.g = ConvDesc(rows, 1, 1, desc.cout, 1, 1, kp, 1, 1, 1, 0, 0, ld_dy, self.ldt, desc.dtype)
+        nbytes = _C.load().rcgan_conv_wpack_bytes(self.g)
+        self.ok = nbytes > 0
+        if not self.ok:
+            return
+        self.wt = torch.zeros(kp * desc.cout, dtype=torch.float32, device=prog.device)
+        self.pack = torch.zeros(nbytes, dtype=torch.uint8, device=prog.device)
+        self.T = torch.zeros(rows * self.ldt, dtype=torch.float32, device=prog.device)
+
+    def run(self, w_ptr, dy_ptr, out_ptr, out_dtype, bias_ptr, act, leak, accumulate, st):
+        d = self.desc
+        # W viewed as [kh*kw*cin, cout] -> W^T [cout, kh*kw*cin] = the 1x1 filter of the GEMM
+        call('rcgan_wflip', w_ptr, pp(self.wt), 1, 1, self.kp, d.cout, 0, st)
+        call('rcgan_conv_wpack', self.g, pp(self.wt), None, pp(self.pack), st)
+        call('rcgan_conv2d_fprop', self.g, dy_ptr, pp(self.wt), pp(self.pack), None, pp(self.T), _C.F32, _C.ACT_NONE, 0.0, st)
+        call('rcgan_col2im', d, pp(self.T), self.ldt, bias_ptr, out_ptr, out_dtype, act, leak, accumulate, st)
+
+
 def spatial(t):
     """(n, h, w) of a 2-D [n,c] or 4-D [n,h,w,c] tensor"""
     if len(t.shape) == 2:
@@ -72,11 +103,9 @@ class ConvOp(Op):
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
-        # ... their input gradient (a 3-channel result from a wide dL/dy: D.Block.1 in the G step) still streams best through
-        # the implicit-GEMM dgrad, which needs the pack of the TRUE conv geometry
-        self.dpack = None
-        if self.patch is not None and _C.load().rcgan_conv_uses_tensor_cores(self.desc, 1):
-            self.dpack = torch.zeros(_C.load().rcgan_conv_wpack_bytes(self.desc), dtype=torch.uint8, device=prog.device)
+        # ... and their input gradient (a 1..3-channel result from a wide dL/dy: d_h0_conv / D.Block.1 in the G step) as one
+        # dense GEMM + col2im
+        self.scatter = ScatterDgrad(prog, self.desc, self.y.ld) if self.patch is not None else None
         # few-channel OUTPUTS (G.Output: 256 -> 3): the backward is the transposed conv of dL/dy (cin' = cout <= 4) with the
         # flipped filter, so it runs as GEMMs on the patch matrix of dL/dy (rcgan_wflip in the header)
         self.tpatch = None
@@ -132,12 +161,11 @@ class ConvOp(Op):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
         if nx:
-            dpack = None if self.patch is not None else self.pack
-            if self.dpack is not None:
-                call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.dpack), st)
-                dpack = self.dpack
-            call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), pp(dpack), None,
-                 gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
+            if self.scatter is not None and self.scatter.ok:
+                self.scatter.run(dp(self.w), dy, gp(self.x), self.x.grad_dtype, None, _C.ACT_NONE, 0.0, self.acc_x, st)
+            else:
+                call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
+                     gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
         if nw:
             if self.patch is not None:
                 call('rcgan_conv2d_wgrad', self.gdesc, dp(self.patch), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
@@ -172,6 +200,7 @@ class DeconvOp(Op):
         # run as GEMMs on the patch matrix of dL/dy
         self.patch, self.gdesc = make_patch(prog, self.desc, n * h * wd, x.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
+        self.scatter = ScatterDgrad(prog, self.desc, x.ld) if self.patch is not None else None
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -185,6 +214,9 @@ class DeconvOp(Op):
         if self.pack_owner:
             call('rcgan_conv_wpack', self.gdesc if self.patch is not None else self.desc, dp(self.w), None, pp(self.pack),
                  stream_ptr())
+        if self.scatter is not None and self.scatter.ok:
+            self.scatter.run(dp(self.w), dp(self.x), dp(self.y), self.y.dtype, dp(self.b), self.act, self.leak, 0, stream_ptr())
+            return
         call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), None if self.patch is not None else pp(self.pack),
              dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, 0, stream_ptr())

@@ -301,3 +301,40 @@ def test_few_output_channel_backward_as_transposed_patch_gemm(lib, shape):
     dw = torch.full(wt.shape, 1.0, device='cuda')
     call('rcgan_wflip', dwflip.data_ptr(), dw.data_ptr(), k, k, cout, cin, 1, st())
     assert relerr(dw - 1.0, wr.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize('shape', [SHAPES[6], SHAPES[0], (2, 32, 32, 3, 128, 3, 1, 5, 0), SHAPES[8], (2, 9, 9, 2, 64, 5, 2, 2, 0)])
+def test_few_input_channel_dgrad_as_gemm_plus_col2im(lib, shape):
+    """g_h3's conv2d_transpose forward / d_h0_conv's input gradient: T = dy * W^T on the tensor cores, then rcgan_col2im
+    (the call sequence of nnops.ScatterDgrad), against the oracle's conv2d_transpose and autograd."""
+    dtype = _C.BF16
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, h, w, cin, cout, k, s = shape[:7]
+    xr = x.double().requires_grad_(True)
+    O.conv2d(xr, wt.double(), s).backward(dy.double())
+    kp = k * k * cin
+    ldt = (kp + 7) // 8 * 8
+    rows = n * ho * wo
+    g = ConvDesc(rows, 1, 1, cout, 1, 1, kp, 1, 1, 1, 0, 0, ldy, ldt, dtype)
+    assert lib.rcgan_conv_uses_tensor_cores(g, 0)
+    wdev = dev(wt)
+    wT = torch.zeros(kp * cout, device='cuda')
+    call('rcgan_wflip', wdev.data_ptr(), wT.data_ptr(), 1, 1, kp, cout, 0, st())
+    assert float((wT.cpu().reshape(cout, kp) - wt.reshape(kp, cout).t()).abs().max()) == 0.0
+    pack = torch.zeros(lib.rcgan_conv_wpack_bytes(g), dtype=torch.uint8, device='cuda')
+    call('rcgan_conv_wpack', g, wT.data_ptr(), None, pack.data_ptr(), st())
+    T = torch.zeros(rows * ldt, device='cuda')
+    call('rcgan_conv2d_fprop', g, dyd.data_ptr(), wT.data_ptr(), pack.data_ptr(), None, T.data_ptr(), _C.F32, _C.ACT_NONE, 0.0, st())
+    dx = torch.full((n, h, w, ldx), 7.0, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_col2im', d, T.data_ptr(), ldt, None, dx.data_ptr(), dtype, _C.ACT_NONE, 0.0, 0, st())
+    assert relerr(dx[..., :cin].float(), xr.grad) < TOL[dtype]
+    if ldx > cin:
+        assert float((dx[..., cin:].float() - 7.0).abs().max()) == 0.0
+    call('rcgan_col2im', d, T.data_ptr(), ldt, None, dx.data_ptr(), dtype, _C.ACT_NONE, 0.0, 1, st())
+    assert relerr(dx[..., :cin].float(), 2 * xr.grad) < 2 * TOL[dtype]
+    # as a deconv forward with bias + sigmoid into an fp32 image
+    bias = torch.randn(cin, generator=torch.Generator().manual_seed(5))
+    out = torch.zeros(n, h, w, ldx, device='cuda')
+    call('rcgan_col2im', d, T.data_ptr(), ldt, keep(dev(bias)), out.data_ptr(), _C.F32, _C.ACT_SIGMOID, 0.0, 0, st())
+    ref = torch.sigmoid(O.conv2d_transpose(dy.double(), wt.double(), (h, w), s) + bias.double())
+    assert relerr(out[..., :cin], ref) < TOL[dtype]
