@@ -506,6 +506,58 @@ int wgrad_splits(const ConvP& p) {
   return (int)s;
 }
 
+// Skinny linear layers (4 < N <= 16 outputs, e.g. the MNIST classifier 784 -> 10 at batch 1024, mnist/model.py:759-768):
+// a 256x16 tile grid would be 4 blocks.  One warp per row instead: lanes stride over K against the smem-resident
+// weights (row pitch 17 floats: conflict-free), 16 register accumulators, shuffle reduction, lane j writes output j.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) linear_skinny_kernel(ConvP p, const T* __restrict__ x, const float* __restrict__ wt,
+                                                            TO* __restrict__ out) {
+  extern __shared__ float wsk[];   // [K][17]
+  for (int i = threadIdx.x; i < p.K * 16; i += 256) {
+    const int k = i >> 4, j = i & 15;
+    wsk[k * 17 + j] = j < p.N ? wt[(size_t)k * p.N + j] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * 8 + warp; m < p.M; m += gridDim.x * 8) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = 0.f;
+    const T* xr = x + (size_t)m * p.ldx;
+    for (int k = lane; k < p.K; k += 32) {
+      const float xv = to_f(xr[k]);
+      const float* wr = wsk + k * 17;
+#pragma unroll
+      for (int j = 0; j < 16; j++) acc[j] = fmaf(xv, wr[j], acc[j]);
+    }
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const float sj = warp_sum(acc[j]);
+      if (lane == j) v = sj;
+    }
+    if (lane < p.N) {
+      if (p.bias) v += p.bias[lane];
+      out[(size_t)m * p.ldy + lane] = from_f<TO>(act_fwd(v, p.act, p.leak));
+    }
+  }
+}
+
+template <typename T, typename TO>
+bool launch_skinny(const ConvP& p, const void* x, const float* w, void* out, cudaStream_t st) {
+  const size_t shb = (size_t)p.K * 17 * sizeof(float);
+  if (p.kh != 1 || p.kw != 1 || p.stride != 1 || p.N <= 4 || p.N > 16 || p.M < 256 || shb > 96 * 1024) return false;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(linear_skinny_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  int grid = ceil_div(p.M, 8);
+  if (grid > RCGAN_NUM_SMS * 2) grid = RCGAN_NUM_SMS * 2;
+  linear_skinny_kernel<T, TO><<<grid, 256, shb, st>>>(p, (const T*)x, w, (TO*)out);
+  return true;
+}
+
 template <int MODE, typename T, typename TO>
 void launch(const ConvP& p, const void* a, const float* w, const void* dy, void* out, int nz, cudaStream_t st) {
   if (p.N <= 16 && MODE != MODE_WGRAD) {
@@ -521,11 +573,14 @@ void launch(const ConvP& p, const void* a, const float* w, const void* dy, void*
 template <int MODE>
 int launch_io(const ConvP& p, int dtype, int out_dtype, const void* a, const float* w, void* out, cudaStream_t st) {
   if (dtype == RCGAN_F32 && out_dtype == RCGAN_F32) {
-    if (!launch_narrow<MODE, float, float>(p, a, w, out, st)) launch<MODE, float, float>(p, a, w, nullptr, out, 1, st);
+    if (!launch_narrow<MODE, float, float>(p, a, w, out, st) && !(MODE == MODE_FPROP && launch_skinny<float, float>(p, a, w, out, st)))
+      launch<MODE, float, float>(p, a, w, nullptr, out, 1, st);
   } else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_BF16) {
-    if (!launch_narrow<MODE, bf16, bf16>(p, a, w, out, st)) launch<MODE, bf16, bf16>(p, a, w, nullptr, out, 1, st);
+    if (!launch_narrow<MODE, bf16, bf16>(p, a, w, out, st) && !(MODE == MODE_FPROP && launch_skinny<bf16, bf16>(p, a, w, out, st)))
+      launch<MODE, bf16, bf16>(p, a, w, nullptr, out, 1, st);
   } else if (dtype == RCGAN_BF16 && out_dtype == RCGAN_F32) {
-    if (!launch_narrow<MODE, bf16, float>(p, a, w, out, st)) launch<MODE, bf16, float>(p, a, w, nullptr, out, 1, st);
+    if (!launch_narrow<MODE, bf16, float>(p, a, w, out, st) && !(MODE == MODE_FPROP && launch_skinny<bf16, float>(p, a, w, out, st)))
+      launch<MODE, bf16, float>(p, a, w, nullptr, out, 1, st);
   }
   else { rcgan_set_error("conv: unsupported dtype pair (%d -> %d)", dtype, out_dtype); return RCGAN_EUNSUPPORTED; }
   return 0;

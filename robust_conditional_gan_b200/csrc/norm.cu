@@ -386,6 +386,12 @@ inline int check_types(int xd, int yd, const char* who) {
   return 0;
 }
 
+// experiment switch: RCGAN_BN_STATS_V=8 -> 16-byte bf16 vectors in the reduction kernels too
+int stats_vmax() {
+  const char* e = getenv("RCGAN_BN_STATS_V");
+  return (e && atoi(e) == 8) ? 8 : 4;
+}
+
 }  // namespace
 
 extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
@@ -421,7 +427,7 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
   RCGAN_CHECK_ARG(x && y && scale && offset && save, "bn_fwd: null pointer");
   RCGAN_CHECK_ARG((long)samples * hw * c < 2147483647L, "bn_fwd: too large");
   cudaStream_t st = as_stream(stream);
-  Geo g = make_geo(samples, hw, c, labels != nullptr, 4 /* 16-byte bf16 vectors measured slower: fewer blocks in flight */);
+  Geo g = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? stats_vmax() : 4);
   if (train) {
     RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_fwd: workspace too small");
     dim3 grid(g.gx, g.nchunk);
@@ -452,7 +458,7 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
   RCGAN_CHECK_ARG(dy && x && dx && scale && save && dscale && doffset, "bn_bwd: null pointer");
   RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y, "bn_bwd: activation needs y");
   cudaStream_t st = as_stream(stream);
-  Geo g = make_geo(samples, hw, c, labels != nullptr, 4 /* 16-byte bf16 vectors measured slower: fewer blocks in flight */);
+  Geo g = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? stats_vmax() : 4);
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);

@@ -25,6 +25,8 @@ SHAPES = [
     (7, 1, 1, 110, 1024, 1, 1, 2, 0),    # g_h0_lin (ld 112)
     (9, 1, 1, 784, 10, 1, 1, 0, 0),      # classifier
     (33, 1, 1, 64, 1, 1, 1, 0, 0),       # d_h4_lin
+    (300, 1, 1, 784, 10, 1, 1, 0, 0),    # classifier at a batch that takes the warp-per-row skinny kernel
+    (257, 1, 1, 100, 16, 1, 1, 4, 0),    # skinny kernel, N = 16, padded rows
 ]
 
 
