@@ -157,6 +157,16 @@ int rcgan_sn_fwd(const float* W, const float* u, int m, int c, float* w_bar, flo
 /* dW (=|+=) from G = dL/dW_bar */
 int rcgan_sn_bwd(const float* W, const float* u, const float* G, int m, int c, const float* save, float* dW,
                  int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* Every spectrally-normalised weight of a step in one launch per pass (host arrays of `count` device pointers / sizes;
+ * same per-item semantics as rcgan_sn_fwd / rcgan_sn_bwd).  The reference normalises each weight where its layer is built
+ * (cifar10/common/ops/conv2d.py:181-216, linear.py:161-180); the results only depend on the parameters, so a step computes
+ * them all up front: 16 weights x 6 small kernels become 6 launches. */
+size_t rcgan_sn_workspace_batched(int count, const int* m, const int* c);
+int rcgan_sn_fwd_batched(int count, const float* const* W, const float* const* u, const int* m, const int* c,
+                         float* const* w_bar, float* const* u_new, float* const* save, void* ws, size_t ws_bytes, void* stream);
+int rcgan_sn_bwd_batched(int count, const float* const* W, const float* const* u, const float* const* G, const int* m,
+                         const int* c, float* const* save, float* const* dW, const int* accumulate, void* ws, size_t ws_bytes,
+                         void* stream);
 
 /* ---------------------------------------------------------------- losses
  * Unified noisy-channel projection loss (mnist/model.py:150-207,679-686;

@@ -67,6 +67,9 @@ _SIGS = {
     'rcgan_sn_workspace': (c_size_t, [c_int, c_int]),
     'rcgan_sn_fwd': (c_int, [P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
     'rcgan_sn_bwd': (c_int, [P, P, P, c_int, c_int, P, P, c_int, P, c_size_t, P]),
+    'rcgan_sn_workspace_batched': (c_size_t, [c_int, P, P]),
+    'rcgan_sn_fwd_batched': (c_int, [c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'rcgan_sn_bwd_batched': (c_int, [c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'rcgan_channel_loss': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, P, P, P, P]),
     'rcgan_sigmoid_ce': (c_int, [P, P, c_long, c_float, P, P, P]),
     'rcgan_logit_loss': (c_int, [P, c_long, c_int, c_float, P, P, P]),

@@ -437,19 +437,66 @@ class SpectralNormOp(Op):
         self.updates_u = bool(update)
         if update:
             prog.add_update(u, self.u_new)
+        # parameters only: a W computed by another op of the program is not available at program start
+        self.batched = bool(W.is_variable and u.is_variable)
 
     def plan_bwd(self, prog):
         self.acc_w = self.claim(self.W) if self.need[0] else 0
 
+    # The ops of one program form a group: the FIRST one (program order) launches the batched forward for all of them
+    # -- W and u are parameters, available at program start -- and, running last in the reverse sweep, the batched
+    # backward once every dL/dW_bar is complete.  The others are bookkeeping only (rcgan_sn_*_batched in the header).
+    def _group(self, prog):
+        grp = prog.__dict__.get('sn_group')
+        if grp is None:
+            import ctypes
+            ops = [o for o in prog.ops if isinstance(o, SpectralNormOp) and o.batched]
+            n = len(ops)
+            PA, IA = ctypes.c_void_p * n, ctypes.c_int * n
+            grp = prog.sn_group = {
+                'ops': ops, 'leader': ops[0], 'n': n,
+                'W': PA(*[dp(o.W) for o in ops]), 'u': PA(*[dp(o.u) for o in ops]),
+                'wbar': PA(*[dp(o.wbar) for o in ops]), 'unew': PA(*[dp(o.u_new) for o in ops]),
+                'save': PA(*[o.save.data_ptr() for o in ops]),
+                'm': IA(*[o.m for o in ops]), 'c': IA(*[o.c for o in ops]),
+            }
+            grp['ws'] = torch.zeros(_C.load().rcgan_sn_workspace_batched(n, grp['m'], grp['c']), dtype=torch.uint8,
+                                    device=prog.device)
+            bw = [o for o in ops if needs(o.wbar) and o.need[0]]
+            if bw:
+                nb = len(bw)
+                PB, IB = ctypes.c_void_p * nb, ctypes.c_int * nb
+                grp['bwd'] = {
+                    'n': nb, 'W': PB(*[dp(o.W) for o in bw]), 'u': PB(*[dp(o.u) for o in bw]),
+                    'G': PB(*[gp(o.wbar) for o in bw]), 'save': PB(*[o.save.data_ptr() for o in bw]),
+                    'dW': PB(*[gp(o.W) for o in bw]), 'm': IB(*[o.m for o in bw]), 'c': IB(*[o.c for o in bw]),
+                    'acc': IB(*[int(o.acc_w) for o in bw]),
+                }
+        return grp
+
     def forward(self, prog):
-        call('rcgan_sn_fwd', dp(self.W), dp(self.u), self.m, self.c, dp(self.wbar), dp(self.u_new), self.save.data_ptr(),
-             prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+        if not self.batched:
+            call('rcgan_sn_fwd', dp(self.W), dp(self.u), self.m, self.c, dp(self.wbar), dp(self.u_new), self.save.data_ptr(),
+                 prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+            return
+        g = self._group(prog)
+        if g['leader'] is not self:
+            return
+        call('rcgan_sn_fwd_batched', g['n'], g['W'], g['u'], g['m'], g['c'], g['wbar'], g['unew'], g['save'],
+             g['ws'].data_ptr(), g['ws'].numel(), stream_ptr())
 
     def backward(self, prog):
-        if not needs(self.wbar) or not self.need[0]:
+        if not self.batched:
+            if needs(self.wbar) and self.need[0]:
+                call('rcgan_sn_bwd', dp(self.W), dp(self.u), gp(self.wbar), self.m, self.c, self.save.data_ptr(), gp(self.W),
+                     self.acc_w, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
             return
-        call('rcgan_sn_bwd', dp(self.W), dp(self.u), gp(self.wbar), self.m, self.c, self.save.data_ptr(), gp(self.W),
-             self.acc_w, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+        g = self._group(prog)
+        if g['leader'] is not self or 'bwd' not in g:
+            return
+        b = g['bwd']
+        call('rcgan_sn_bwd_batched', b['n'], b['W'], b['u'], b['G'], b['m'], b['c'], b['save'], b['dW'], b['acc'],
+             g['ws'].data_ptr(), g['ws'].numel(), stream_ptr())
 
 
 class ChannelLossOp(Op):

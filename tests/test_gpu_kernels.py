@@ -125,6 +125,38 @@ def test_spectral_norm(lib, m, c):
     assert relerr(dW, const_uv) > 1e-4 or m * c < 200
 
 
+def test_spectral_norm_batched_matches_oracle(lib):
+    """rcgan_sn_fwd_batched / rcgan_sn_bwd_batched over weights of different shapes (more than one 32-item launch group)
+    against the oracle, item by item; one item accumulates into dW."""
+    import ctypes
+    shapes = [(1152, 128), (27, 128), (128, 1), (10, 128), (2304, 256), (25, 64)] * 6        # 36 items
+    g = torch.Generator().manual_seed(11)
+    n = len(shapes)
+    Ws = [torch.randn(m, c, generator=g) * 0.05 for m, c in shapes]
+    us = [torch.randn(1, c, generator=g) for m, c in shapes]
+    Gs = [torch.randn(m, c, generator=g) for m, c in shapes]
+    Wd, ud, Gd = [dev(t) for t in Ws], [dev(t) for t in us], [dev(t) for t in Gs]
+    wbar = [torch.zeros(m, c, device='cuda') for m, c in shapes]
+    un = [torch.zeros(c, device='cuda') for m, c in shapes]
+    save = [torch.zeros(lib.rcgan_sn_save_floats(m, c), device='cuda') for m, c in shapes]
+    dW = [torch.full((m, c), 1.0, device='cuda') for m, c in shapes]
+    PA, IA = ctypes.c_void_p * n, ctypes.c_int * n
+    ptrs = lambda ts: PA(*[t.data_ptr() for t in ts])
+    ms, cs = IA(*[m for m, c in shapes]), IA(*[c for m, c in shapes])
+    acc = IA(*[1 if i == 2 else 0 for i in range(n)])
+    nb = lib.rcgan_sn_workspace_batched(n, ms, cs)
+    ws = ws_buf(nb)
+    call('rcgan_sn_fwd_batched', n, ptrs(Wd), ptrs(ud), ms, cs, ptrs(wbar), ptrs(un), ptrs(save), ws.data_ptr(), nb, st())
+    call('rcgan_sn_bwd_batched', n, ptrs(Wd), ptrs(ud), ptrs(Gd), ms, cs, ptrs(save), ptrs(dW), acc, ws.data_ptr(), nb, st())
+    for i, (m, c) in enumerate(shapes):
+        Wr = Ws[i].double().requires_grad_(True)
+        Wb, u_new, sigma = O.spectral_normed_weight(Wr, us[i].double())
+        Wb.backward(Gs[i].double())
+        assert relerr(wbar[i], Wb) < 1e-5 and relerr(un[i], u_new) < 1e-5, i
+        ref = Wr.grad + (1.0 if i == 2 else 0.0)
+        assert relerr(dW[i], ref) < 2e-5, i
+
+
 # ----------------------------------------------------------------------------- losses
 def phi_ref(mode, l):
     if mode == _C.HINGE_D_REAL: return torch.relu(1 - l)
