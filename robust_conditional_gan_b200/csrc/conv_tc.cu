@@ -160,7 +160,7 @@ template <int BN, int ST> struct Cfg {
 // pieces.  Only the owning warp touches its slab, so __syncwarp() orders the two phases.
 template <int BN, int AVAIL, typename TO>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
-                                            int n0) {
+                                            int n0, uint32_t tempty_bar = 0) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   constexpr int PITCH = BN * (int)sizeof(TO) + 16;
   constexpr int LPR = BN / VEC;                       // 16-byte pieces per row
@@ -233,6 +233,12 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
       }
       *reinterpret_cast<uint4*>(dst + (j / VEC) * 16) = q;
     }
+  }
+  // persistent kernel: the accumulator is drained -> hand it back to the MMA warp before the (slow) global stores
+  if (tempty_bar) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar);
   }
   __syncwarp();
   if (p.dbg & 16) return;
@@ -432,6 +438,157 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ persistent kernel
+// One CTA per SM loops over output tiles (N tiles of one M tile adjacent).  The TMA producer and the MMA issuer run
+// ahead across tile boundaries through the same smem ring; the accumulator is double buffered in TMEM (2 x BN columns),
+// so the epilogue of tile i (TMEM -> registers -> private staging smem -> global) overlaps the main loop of tile i+1,
+// and TMEM allocation / barrier init / descriptor prefetch are paid once per SM instead of once per tile.
+// (Measured on the one-tile-per-CTA kernel above at 256x32x32x128 3x3: 89 us, of which 45 us were per-CTA prologue +
+// handshake skeleton and 18 us the exposed epilogue.)   TMA im2col operand only.
+template <int BN, int MT, int ST, typename TO>
+struct PCfg {
+  static constexpr int A_BYTES = MT * BM * BK * 2;     // MT stacked 128-row sub-tiles share one B tile
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int PITCH = BN * (int)sizeof(TO) + 16;
+  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 1024;
+  static constexpr int SMEM = ST * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "persistent conv tile does not fit shared memory");
+  static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
+};
+
+// Tile = (MT x 128) rows x BN columns.  The operand stream from L2 is what bounds this kernel (~50 B/clk/SM measured), so
+// the tile shapes are chosen for flops per staged byte: 128x256 (N >= 256) and 256x128 (N <= 128) both move 48 KB per
+// 4.2 MFLOP K block, against 32 KB per 2.1 MFLOP for 128x128.
+template <int BN, int MT, int ST, typename TO>
+__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ TcParams p,
+                                                                 const __grid_constant__ CUtensorMap wmap,
+                                                                 const __grid_constant__ CUtensorMap amap) {
+  using C = PCfg<BN, MT, ST, TO>;
+  constexpr int TM = MT * BM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + ST * C::A_BYTES;
+  uint8_t* epi = smB + ST * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::EPI_BYTES);
+  uint64_t* full = bars;               // [ST] 1 arrival (expect_tx) + TMA bytes
+  uint64_t* empty = bars + ST;         // [ST] 1 arrival (tcgen05.commit)
+  uint64_t* tfull = bars + 2 * ST;     // [2]  accumulator ready (tcgen05.commit)
+  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  accumulator drained (4 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles = ((p.M + TM - 1) / TM) * n_tiles_n;
+  const int nkb = p.ntaps * p.kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; s++) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(smem_u32(&tfull[a]), 1);
+      mbar_init(smem_u32(&tempty[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), 2 * MT * BN);
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =========================================================== epilogue warps
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+      const int a = ti & 1;
+      const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < MT; j++)
+        tc_epilogue<BN, C::EPI_BYTES, TO>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
+                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u);
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * BN;
+        int im_w[MT], im_h[MT], im_n[MT];
+        int nsub = 0;
+#pragma unroll
+        for (int j = 0; j < MT; j++) {
+          const int mj = m0 + j * BM;
+          if (mj < p.M) nsub = j + 1;
+          const int mb = mj % p.MW, mr = mj / p.MW;
+          im_w[j] = p.im_w_lo + mb * p.im_sw; im_h[j] = p.im_h_lo + (mr % p.MH) * p.im_sh; im_n[j] = mr / p.MH;
+        }
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % ST;
+          mbar_wait(smem_u32(&empty[s]), ((it / ST) & 1) ^ 1);
+          const int tap = kb / p.kb_per_tap;
+          const int k0 = (kb - tap * p.kb_per_tap) * BK;
+          const bool la = !(p.dbg & 6), lb = !(p.dbg & 10);
+          mbar_arrive_expect_tx(smem_u32(&full[s]), (lb ? C::B_BYTES : 0) + (la ? nsub * (BM * BK * 2) : 0));
+          if (la) {
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+              if (j < nsub)      // sub-tiles past the last row are not loaded (their accumulator rows are never stored)
+                tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)), &amap, smem_u32(&full[s]), k0, im_w[j],
+                                   im_h[j], im_n[j], p.toffw[tap], p.toffh[tap]);
+          }
+          if (lb) tma_load_3d(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0, p.twi[tap]);
+        }
+      }
+    }
+  } else {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
+        const int a = ti & 1;
+        mbar_wait(smem_u32(&tempty[a]), ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % ST;
+          mbar_wait(smem_u32(&full[s]), (it / ST) & 1);
+          tc_fence_after();
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + s * C::B_BYTES));
+          if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int j = 0; j < MT; j++) {
+              const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)));
+#pragma unroll
+              for (int k = 0; k < BK / 16; k++) umma_bf16(tacc + (uint32_t)(j * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(smem_u32(&empty[s]));
+        }
+        umma_commit(smem_u32(&tfull[a]));
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * MT * BN);
   }
 }
 
@@ -836,25 +993,49 @@ bool make_amap(CUtensorMap* map, const TcParams& p, int channels, int nimg) {
   return r == CUDA_SUCCESS;
 }
 
-// experiment switch (read per call): RCGAN_TC_VARIANT=1 -> BN=128 with 6 stages (1 CTA/SM), 2 -> BN=256 for N >= 256
-int tc_variant() {
-  const char* e = getenv("RCGAN_TC_VARIANT");
-  return e ? atoi(e) : 0;
+template <int BN, int MT, int ST, typename TO>
+int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap, cudaStream_t st) {
+  using C = PCfg<BN, MT, ST, TO>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, MT, ST, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+    attr_done = true;
+  }
+  const int n_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * ((p.N + BN - 1) / BN);
+  const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
+  conv_tc_persist_kernel<BN, MT, ST, TO><<<grid, 192, C::SMEM, st>>>(p, map, amap);
+  RCGAN_LAUNCH_CHECK("conv_tc_persist");
+  return 0;
+}
+
+// RCGAN_TC_PERSIST=0 selects the one-tile-per-CTA kernel everywhere (A/B comparisons); =2 forces the persistent kernel
+int persist_mode() {
+  const char* e = getenv("RCGAN_TC_PERSIST");
+  return e ? atoi(e) : 1;
 }
 
 int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int channels, int nimg, cudaStream_t st) {
-  const int var = tc_variant();
   { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap map, amap;
   const bool im2col = make_amap(&amap, p, channels, nimg);
-  const int bn = p.N <= 64 ? 64 : ((var == 2 && p.N >= 256 && im2col) ? 256 : 128);
-  if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
-  if (im2col) {
-    if (bn == 64) return launch_tc<64, 4, true>(p, map, amap, st);
-    if (bn == 256) return launch_tc<256, 4, true>(p, map, amap, st);
-    if (var == 1) return launch_tc<128, 6, true>(p, map, amap, st);
-    return launch_tc<128, 3, true>(p, map, amap, st);
+  // persistent big-tile kernel when it has at least ~3 tiles per SM to pipeline; below that the one-tile-per-CTA kernel
+  // with two resident CTAs per SM fills the machine better
+  const int pm = persist_mode();
+  const long big_tiles = (p.N > 128) ? (long)((p.M + 127) / 128) * ((p.N + 255) / 256) : (long)((p.M + 255) / 256);
+  const bool persist = im2col && p.N > 64 && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
+  if (persist) {
+    if (p.N > 128) {
+      if (int e = make_wmap(&map, wbase, kpad, rows, taps, 256)) return e;
+      // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs use 2 x (128x128)
+      if (!p.out_f32) return launch_tc_persist<256, 1, 3, bf16>(p, map, amap, st);
+    }
+    if (int e = make_wmap(&map, wbase, kpad, rows, taps, 128)) return e;
+    return p.out_f32 ? launch_tc_persist<128, 2, 3, float>(p, map, amap, st) : launch_tc_persist<128, 2, 3, bf16>(p, map, amap, st);
   }
+  const int bn = p.N <= 64 ? 64 : 128;
+  if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
+  if (im2col) return bn == 64 ? launch_tc<64, 4, true>(p, map, amap, st) : launch_tc<128, 3, true>(p, map, amap, st);
   return bn == 64 ? launch_tc<64, 4, false>(p, map, map, st) : launch_tc<128, 3, false>(p, map, map, st);
 }
 

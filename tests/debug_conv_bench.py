@@ -7,9 +7,13 @@ from robust_conditional_gan_b200 import _C
 
 SHAPES = [  # n, h, w, cin, cout, k
     (256, 8, 8, 128, 128, 3),
+    (256, 16, 16, 128, 128, 3),
     (256, 32, 32, 128, 128, 3),
+    (512, 16, 16, 256, 256, 3),
     (512, 32, 32, 256, 256, 1),
+    (256, 32, 32, 256, 256, 3),
     (512, 32, 32, 256, 256, 3),
+    (1024, 14, 14, 128, 128, 5),
 ]
 
 
@@ -42,7 +46,7 @@ def main():
         _C.call('rcgan_conv_wpack', ctypes.byref(d), wt.data_ptr(), None, pack.data_ptr(), st)
         ref = None
         for var in variants:
-            os.environ['RCGAN_TC_VARIANT'] = var.split(':')[0]
+            os.environ['RCGAN_TC_PERSIST'] = var.split(':')[0]
             os.environ['RCGAN_TC_DBG'] = var.split(':')[1] if ':' in var else '0'
             ts = []
             for it in range(6):
