@@ -13,7 +13,7 @@ import torch
 
 from .. import _C, scope as S
 from ..graph import I32, Program, VariableStore, tf_adam_lr
-from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
+from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, ConcatRowsOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
                      SoftmaxRowsOp, Upsample2Op, adam_step)
 from . import ops as lib_ops
 
@@ -245,8 +245,9 @@ class RCGANCifar(object):
             real32 = PreprocessCifarOp(raw, dq, _C.F32).y
             real = CastOp(real32, self.act_dtype).y
             fake = net.Generator(n, labels_random, noise=CastOp(noise, self.act_dtype).y)
-            h_r, psi_r = net.Discriminator(real, labels, update_collection=None)
-            h_f, psi_f = net.Discriminator(fake, labels_random, update_collection=None, reuse=True)
+            # one D pass over [real; fake] as the reference does (:558-583; D has no batch statistics, so the halves are
+            # independent): every kernel of the trunk sees 2n samples instead of two launches of n
+            h_all, psi_all = net.Discriminator(ConcatRowsOp(real, fake).y, None, update_collection=None)
             V = net.Discriminator_projection(None, update_collection=None)
             w_real = inv_w if alg == 'unbiased' else onehot(dp_, labels)
             if alg == 'rcgan-u':
@@ -255,8 +256,8 @@ class RCGANCifar(object):
                 w_fake = onehot(dp_, labels_biased)
             else:
                 w_fake = onehot(dp_, labels_random)
-            self.disc_real = ChannelLossOp(h_r, psi_r, V, w_real, _C.HINGE_D_REAL, 'disc_real_l').logits
-            self.disc_fake = ChannelLossOp(h_f, psi_f, V, w_fake, _C.HINGE_D_FAKE, 'disc_fake_l').logits
+            self.disc_real = ChannelLossOp(h_all, psi_all, V, w_real, _C.HINGE_D_REAL, 'disc_real_l', rows=(0, n)).logits
+            self.disc_fake = ChannelLossOp(h_all, psi_all, V, w_fake, _C.HINGE_D_FAKE, 'disc_fake_l', rows=(n, n)).logits
             if F.perm_classifier:
                 SigmoidCEOp(net.perm_classifier(real32), onehot(dp_, labels), 'perm_classifier_real_loss', 1.0)
         # ---------------- G step (:715-786)

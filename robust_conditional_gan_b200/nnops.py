@@ -503,12 +503,18 @@ class ChannelLossOp(Op):
     """L = coef * mean_b sum_j wgt[b,j] * phi(psi[b] + <h[b], V[j]>)   (SURVEY appendix B).
     The value stored in the program's loss slot is the un-weighted mean (coef applies to gradients)."""
 
-    def __init__(self, h, psi, V, wgt, mode, name, coef=1.0):
+    def __init__(self, h, psi, V, wgt, mode, name, coef=1.0, rows=None):
+        """rows=(row0, B): the term covers rows [row0, row0+B) of h / psi only -- D run once on [real; fake]
+        (cifar10/gan_resnet.py:563-590 slices disc_all the same way) with one loss term per half."""
         prog = cur()
         self.h, self.psi, self.V, self.wgt = h, psi, V, wgt
-        self.B, self.d, self.k = h.shape[0], h.c, V.shape[0]
+        self.row0, self.B = (0, h.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+        self.sliced = rows is not None
+        assert 0 <= self.row0 and self.row0 + self.B <= h.shape[0]
+        self.d, self.k = h.c, V.shape[0]
         assert h.ld == h.c and V.c == h.c and wgt.shape == (self.B, self.k)
-        assert psi is None or psi.numel() == self.B
+        assert psi is None or psi.numel() == h.shape[0]
+        assert not self.sliced or (h.dtype == _C.F32 and (psi is None or psi.dtype == _C.F32))
         self.mode, self.coef = mode, coef
         self.slot = prog.loss_slot(name)
         self.logits = prog.new((self.B, self.k), _C.F32)
@@ -521,18 +527,29 @@ class ChannelLossOp(Op):
     def plan_bwd(self, prog):
         nh, np_, nv, nw = self.need
         self.acc_h = self.claim(self.h) if nh else 0
+        self.zero_h = self.zero_psi = False
+        if self.sliced and nh and self.acc_h == 0:
+            self.zero_h, self.acc_h = True, 1        # first writer of a row-sliced gradient: clear it all, then everyone +=
         if np_:
-            assert self.claim(self.psi) == 0, 'psi gradient must have a single writer'
+            acc_psi = self.claim(self.psi)
+            if self.sliced:
+                self.zero_psi = acc_psi == 0
+            else:
+                assert acc_psi == 0, 'psi gradient must have a single writer'
         self.zero_v = False
         if nv:
             self.zero_v = (self.claim(self.V) == 0) and not self.V.is_variable
         if nw:
             assert self.claim(self.wgt) == 0, 'weight-matrix gradient must have a single writer'
 
+    def _off(self, ptr, per_row):
+        return None if ptr is None else ptr + 4 * self.row0 * per_row
+
     def forward(self, prog):
-        call('rcgan_channel_loss', dp(self.h), dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k, self.h.dtype,
-             self.mode, 1.0 / self.B, prog.losses.data_ptr() + 4 * self.slot, dp(self.logits), None, 0, None, None, None,
-             stream_ptr())
+        call('rcgan_channel_loss', self._off(dp(self.h), self.d) if self.sliced else dp(self.h),
+             self._off(dp(self.psi), 1) if self.sliced else dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k,
+             self.h.dtype, self.mode, 1.0 / self.B, prog.losses.data_ptr() + 4 * self.slot, dp(self.logits), None, 0, None, None,
+             None, stream_ptr())
 
     def backward(self, prog):
         nh, np_, nv, nw = self.need
@@ -541,9 +558,17 @@ class ChannelLossOp(Op):
         st = stream_ptr()
         if nv and self.zero_v:
             call('rcgan_zero', gp(self.V), self.V.grad.numel() * 4, st)
-        call('rcgan_channel_loss', dp(self.h), dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k, self.h.dtype,
-             self.mode, self.coef / self.B, None, None, gp(self.h) if nh else None, self.acc_h,
-             gp(self.psi) if np_ else None, gp(self.V) if nv else None, gp(self.wgt) if nw else None, st)
+        if self.zero_h:
+            call('rcgan_zero', gp(self.h), self.h.grad.numel() * self.h.grad.element_size(), st)
+        if self.zero_psi:
+            call('rcgan_zero', gp(self.psi), self.psi.grad.numel() * self.psi.grad.element_size(), st)
+        gh, gpsi = (gp(self.h) if nh else None), (gp(self.psi) if np_ else None)
+        if self.sliced:
+            gh, gpsi = self._off(gh, self.d), self._off(gpsi, 1)
+        call('rcgan_channel_loss', self._off(dp(self.h), self.d) if self.sliced else dp(self.h),
+             self._off(dp(self.psi), 1) if self.sliced else dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k,
+             self.h.dtype, self.mode, self.coef / self.B, None, None, gh, self.acc_h, gpsi, gp(self.V) if nv else None,
+             gp(self.wgt) if nw else None, st)
 
 
 class SigmoidCEOp(Op):
