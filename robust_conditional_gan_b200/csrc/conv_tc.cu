@@ -42,6 +42,7 @@ struct TcParams {
   // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
   int im_w_lo, im_h_lo, im_sw, im_sh;
   unsigned short toffw[MAX_TAPS], toffh[MAX_TAPS];
+  int bn_eff;   // persistent kernel: N-tile width actually computed (multiple of 16, <= the template's BN)
   int dbg;   // experiments only: 1 = skip MMA issue, 2 = skip TMA loads, 4 = skip A load, 8 = skip B load
 };
 
@@ -160,10 +161,9 @@ template <int BN, int ST> struct Cfg {
 // pieces.  Only the owning warp touches its slab, so __syncwarp() orders the two phases.
 template <int BN, int AVAIL, typename TO>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
-                                            int n0, uint32_t tempty_bar = 0) {
+                                            int n0, uint32_t tempty_bar = 0, int bn_lim = BN) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   constexpr int PITCH = BN * (int)sizeof(TO) + 16;
-  constexpr int LPR = BN / VEC;                       // 16-byte pieces per row
   static_assert(4 * 32 * PITCH + 1024 <= AVAIL, "staging must fit the drained pipeline buffers");
   uint8_t* slab = smem + warp * (32 * PITCH);
   unsigned long long* rowoff = reinterpret_cast<unsigned long long*>(smem + 4 * 32 * PITCH) + warp * 32;
@@ -174,9 +174,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
     ob = ((unsigned long long)(n * p.OH + a * p.oy_mul + p.oy_add) * p.OW + (b * p.ox_mul + p.ox_add)) * p.ld_out;
   }
   rowoff[lane] = ob;
-  const int ncols = min(BN, p.N - n0);
+  const int ncols = min(bn_lim, p.N - n0);
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 0; c0 < bn_lim; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);   // warp-collective: all lanes execute
     if (c0 >= ncols || (p.dbg & 16)) continue;
@@ -243,11 +243,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
   __syncwarp();
   if (p.dbg & 16) return;
   TO* out = reinterpret_cast<TO*>(p.out);
-  const bool fast = ncols == BN && p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0;
+  const bool fast = p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0 && ncols >= VEC;
   if (fast) {
+    // whole 16-byte pieces of every row, consecutive lanes on consecutive pieces; a ragged tail (ncols % VEC columns,
+    // e.g. 138 = 17 pieces + 2) is finished element-wise below
+    const int lpr = ncols / VEC;
+    // (row, piece) of idx = lane + 32*i advanced incrementally: no division in the loop (the 4 epilogue warps run one per
+    // scheduler, every instruction of this loop is exposed latency when K is short)
+    const int drow = 32 / lpr, dpiece = 32 - drow * lpr;
+    int row = lane / lpr, piece = lane - row * lpr;
 #pragma unroll 4
-    for (int idx = lane; idx < 32 * LPR; idx += 32) {
-      const int row = idx / LPR, piece = idx % LPR;
+    for (int idx = lane; idx < 32 * lpr; idx += 32, row += drow, piece += dpiece) {
+      if (piece >= lpr) { piece -= lpr; row++; }
       const unsigned long long o = rowoff[row];
       if (o == ~0ull) continue;
       uint4 q = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
@@ -270,6 +277,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
         }
       }
       *reinterpret_cast<uint4*>(g) = q;
+    }
+    const int tail0 = lpr * VEC, ntail = ncols - tail0;
+    if (ntail > 0) {
+      for (int idx = lane; idx < 32 * ntail; idx += 32) {
+        const int row = idx / ntail, c = tail0 + idx - row * ntail;
+        const unsigned long long o = rowoff[row];
+        if (o == ~0ull) continue;
+        TO* g = out + o + n0 + c;
+        float x = to_f(reinterpret_cast<const TO*>(slab + row * PITCH)[c]);
+        if (p.accumulate) x += to_f(*g);
+        *g = from_f<TO>(x);
+      }
     }
   } else {
     // ragged tile (N not a multiple of the tile, odd strides): element-wise, lanes along the row
@@ -481,7 +500,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int bn = p.bn_eff;                              // N-tile width of this launch: multiple of 16, <= BN
+  const int n_tiles_n = (p.N + bn - 1) / bn;
   const int n_tiles = ((p.M + TM - 1) / TM) * n_tiles_n;
   const int nkb = p.ntaps * p.kb_per_tap;
 
@@ -513,13 +533,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     int ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
       const int a = ti & 1;
-      const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * BN;
+      const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * bn;
       mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < MT; j++)
         tc_epilogue<BN, C::EPI_BYTES, TO>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
-                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u);
+                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u, bn);
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * BN;
+        const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * bn;
         int im_w[MT], im_h[MT], im_n[MT];
         int nsub = 0;
 #pragma unroll
@@ -543,7 +563,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
           const int tap = kb / p.kb_per_tap;
           const int k0 = (kb - tap * p.kb_per_tap) * BK;
           const bool la = !(p.dbg & 6), lb = !(p.dbg & 10);
-          mbar_arrive_expect_tx(smem_u32(&full[s]), (lb ? C::B_BYTES : 0) + (la ? nsub * (BM * BK * 2) : 0));
+          mbar_arrive_expect_tx(smem_u32(&full[s]), (lb ? bn * BK * 2 : 0) + (la ? nsub * (BM * BK * 2) : 0));
           if (la) {
 #pragma unroll
             for (int j = 0; j < MT; j++)
@@ -558,7 +578,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   } else {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, bn);
       uint32_t it = 0;
       int ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
@@ -1002,7 +1022,7 @@ int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorM
     if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
-  const int n_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * ((p.N + BN - 1) / BN);
+  const int n_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * ((p.N + p.bn_eff - 1) / p.bn_eff);
   const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
   conv_tc_persist_kernel<BN, MT, ST, TO><<<grid, 192, C::SMEM, st>>>(p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
@@ -1022,15 +1042,16 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
   // persistent big-tile kernel when it has at least ~3 tiles per SM to pipeline; below that the one-tile-per-CTA kernel
   // with two resident CTAs per SM fills the machine better
   const int pm = persist_mode();
-  const long big_tiles = (p.N > 128) ? (long)((p.M + 127) / 128) * ((p.N + 255) / 256) : (long)((p.M + 255) / 256);
+  const long big_tiles = (p.N > 128 && !p.out_f32) ? (long)((p.M + 127) / 128) * ((p.N + 255) / 256)
+                                                   : (long)((p.M + 255) / 256) * ((p.N + 127) / 128);
   const bool persist = im2col && p.N > 64 && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
   if (persist) {
-    if (p.N > 128) {
-      if (int e = make_wmap(&map, wbase, kpad, rows, taps, 256)) return e;
-      // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs use 2 x (128x128)
-      if (!p.out_f32) return launch_tc_persist<256, 1, 3, bf16>(p, map, amap, st);
-    }
-    if (int e = make_wmap(&map, wbase, kpad, rows, taps, 128)) return e;
+    // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs (and N <= 128) use 2 x (128 x <=128)
+    const bool wide = p.N > 128 && !p.out_f32;
+    const int cap = wide ? 256 : 128;
+    p.bn_eff = p.N >= cap ? cap : round_up(p.N, 16);      // e.g. N = 138 (g_h2's 128 + 10 label channels) -> one 144-wide tile
+    if (int e = make_wmap(&map, wbase, kpad, rows, taps, p.bn_eff)) return e;
+    if (wide) return launch_tc_persist<256, 1, 3, bf16>(p, map, amap, st);
     return p.out_f32 ? launch_tc_persist<128, 2, 3, float>(p, map, amap, st) : launch_tc_persist<128, 2, 3, bf16>(p, map, amap, st);
   }
   const int bn = p.N <= 64 ? 64 : 128;

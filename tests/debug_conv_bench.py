@@ -14,16 +14,18 @@ SHAPES = [  # n, h, w, cin, cout, k
     (256, 32, 32, 256, 256, 3),
     (512, 32, 32, 256, 256, 3),
     (1024, 14, 14, 128, 128, 5),
+    (200704, 1, 1, 32, 138, 1, 6),
+    (1024, 14, 14, 64, 138, 5, 6),
 ]
 
 
-def desc(n, h, w, cin, cout, k):
+def desc(n, h, w, cin, cout, k, pady=0):
     d = _C.ConvDesc()
     d.n, d.h, d.w, d.cin, d.ho, d.wo, d.cout = n, h, w, cin, h, w, cout
     d.kh = d.kw = k
     d.stride = 1
     d.pad_t = d.pad_l = (k - 1) // 2
-    d.ldx, d.ldy, d.dtype = cin, cout, _C.BF16
+    d.ldx, d.ldy, d.dtype = cin, cout + pady, _C.BF16
     return d
 
 
@@ -36,11 +38,12 @@ def main():
     for si, shp in enumerate(SHAPES):
         if only is not None and int(only) != si:
             continue
-        n, h, w, cin, cout, k = shp
+        n, h, w, cin, cout, k = shp[:6]
+        pady = shp[6] if len(shp) > 6 else 0
         d = desc(*shp)
         x = torch.randn(n, h, w, cin, device=dev).bfloat16()
         wt = torch.randn(k, k, cin, cout, device=dev) * 0.05
-        y = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+        y = torch.empty(n, h, w, cout + pady, device=dev, dtype=torch.bfloat16)
         nb = _C.load().rcgan_conv_wpack_bytes(ctypes.byref(d))
         pack = torch.empty(nb, dtype=torch.uint8, device=dev)
         _C.call('rcgan_conv_wpack', ctypes.byref(d), wt.data_ptr(), None, pack.data_ptr(), st)
@@ -74,7 +77,7 @@ def main():
                 err = float((y.float() - ref).abs().max())
             fl = 2.0 * n * h * w * cin * cout * k * k
             if os.environ.get('CONV_BENCH_BWD') and var == variants[0]:
-                dy = torch.randn(n, h, w, cout, device=dev).bfloat16()
+                dy = torch.randn(n, h, w, cout + pady, device=dev).bfloat16()
                 dx = torch.empty(n, h, w, cin, device=dev, dtype=torch.bfloat16)
                 dw = torch.empty(k, k, cin, cout, device=dev)
                 db = torch.empty(cout, device=dev)
