@@ -113,6 +113,15 @@ class ConvOp(Op):
             self.tdesc = ConvDesc(n, ho, wo, cout, h, wd, cin, kh, kw, 1, kh - 1 - pt, kw - 1 - pl, self.y.ld, x.ld, x.dtype)
             self.tpatch, self.tgdesc = make_patch(prog, self.tdesc, n * h * wd, x.ld)
         if self.tpatch is not None:
+            # ... and the forward as ONE dense GEMM T = x[M, cin] * W2[cin, kh*kw*cout] plus rcgan_col2im with the flipped tap
+            # order (x is read once instead of once per filter tap)
+            kp = kh * kw * cout
+            self.f_ldt = round_up(kp, 8)
+            self.f_g = ConvDesc(n * h * wd, 1, 1, cin, 1, 1, kp, 1, 1, 1, 0, 0, x.ld, self.f_ldt, x.dtype)
+            self.f_cdesc = ConvDesc(n, ho, wo, cout, h, wd, cin, kh, kw, 1, kh - 1 - pt, kw - 1 - pl, self.y.ld, x.ld, x.dtype)
+            self.f_w2 = torch.zeros(kp * cin, dtype=torch.float32, device=prog.device)
+            self.f_pack = torch.zeros(_C.load().rcgan_conv_wpack_bytes(self.f_g), dtype=torch.uint8, device=prog.device)
+            self.f_T = torch.zeros(n * h * wd * self.f_ldt, dtype=torch.float32, device=prog.device)
             nflip = kh * kw * cout * cin
             self.wflip = torch.zeros(nflip, dtype=torch.float32, device=prog.device)
             self.dwflip = torch.zeros(nflip, dtype=torch.float32, device=prog.device)
@@ -139,7 +148,19 @@ class ConvOp(Op):
             call('rcgan_conv2d_wgrad', self.tgdesc, dp(self.tpatch), dp(self.x), pp(self.dwflip), 0, prog.ws.ptr(), prog.ws.bytes, st)
             call('rcgan_wflip', pp(self.dwflip), gp(self.w), d.kh, d.kw, d.cout, d.cin, self.acc_w, st)
 
+    def _forward_scatter(self, prog):
+        d, st = self.desc, stream_ptr()
+        kp = d.kh * d.kw * d.cout
+        # wflip: [tap'][co][ci] = w[flipped tap'][ci][co]; transposed once more it is the GEMM filter [cin][tap'*cout + co]
+        call('rcgan_wflip', dp(self.w), pp(self.wflip), d.kh, d.kw, d.cin, d.cout, 0, st)
+        call('rcgan_wflip', pp(self.wflip), pp(self.f_w2), 1, 1, kp, d.cin, 0, st)
+        call('rcgan_conv_wpack', self.f_g, pp(self.f_w2), None, pp(self.f_pack), st)
+        call('rcgan_conv2d_fprop', self.f_g, dp(self.x), pp(self.f_w2), pp(self.f_pack), None, pp(self.f_T), _C.F32, _C.ACT_NONE, 0.0, st)
+        call('rcgan_col2im', self.f_cdesc, pp(self.f_T), self.f_ldt, dp(self.b), dp(self.y), self.y.dtype, self.act, self.leak, 0, st)
+
     def forward(self, prog):
+        if self.tpatch is not None and self.desc.kh == self.desc.kw and self.desc.pad_t == self.desc.pad_l:
+            return self._forward_scatter(prog)
         d, xin = self.desc, dp(self.x)
         if self.patch is not None:
             call('rcgan_im2col', self.desc, dp(self.x), dp(self.patch), self.patch.ld, stream_ptr())

@@ -340,3 +340,29 @@ def test_few_input_channel_dgrad_as_gemm_plus_col2im(lib, shape):
     call('rcgan_col2im', d, T.data_ptr(), ldt, keep(dev(bias)), out.data_ptr(), _C.F32, _C.ACT_SIGMOID, 0.0, 0, st())
     ref = torch.sigmoid(O.conv2d_transpose(dy.double(), wt.double(), (h, w), s) + bias.double())
     assert relerr(out[..., :cin], ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32, 256, 3, 3, 1, 0, 5), (3, 8, 8, 64, 2, 3, 1, 0, 6), (2, 16, 16, 128, 4, 5, 1, 0, 4)])
+def test_few_output_channel_forward_as_gemm_plus_col2im(lib, shape):
+    """G.Output forward (256 -> 3, tanh): T = x * W2 on the tensor cores + rcgan_col2im over the flipped taps, the call
+    sequence of ConvOp._forward_scatter, against the oracle conv."""
+    dtype = _C.BF16
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, h, w, cin, cout, k, s = shape[:7]
+    kp = k * k * cout
+    ldt = (kp + 7) // 8 * 8
+    g = ConvDesc(n * h * w, 1, 1, cin, 1, 1, kp, 1, 1, 1, 0, 0, ldx, ldt, dtype)
+    cd = ConvDesc(n, ho, wo, cout, h, w, cin, k, k, 1, k - 1 - d.pad_t, k - 1 - d.pad_l, ldy, ldx, dtype)
+    wdev = dev(wt)
+    w1 = torch.zeros(kp * cin, device='cuda'); w2 = torch.zeros(kp * cin, device='cuda')
+    call('rcgan_wflip', wdev.data_ptr(), w1.data_ptr(), k, k, cin, cout, 0, st())
+    call('rcgan_wflip', w1.data_ptr(), w2.data_ptr(), 1, 1, kp, cin, 0, st())
+    pack = torch.zeros(lib.rcgan_conv_wpack_bytes(g), dtype=torch.uint8, device='cuda')
+    call('rcgan_conv_wpack', g, w2.data_ptr(), None, pack.data_ptr(), st())
+    T = torch.zeros(n * h * w * ldt, device='cuda')
+    call('rcgan_conv2d_fprop', g, xd.data_ptr(), w2.data_ptr(), pack.data_ptr(), None, T.data_ptr(), _C.F32, _C.ACT_NONE, 0.0, st())
+    y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_col2im', cd, T.data_ptr(), ldt, keep(dev(b)), y.data_ptr(), dtype, _C.ACT_TANH, 0.0, 0, st())
+    ref = torch.tanh(O.conv2d(x.double(), wt.double(), s) + b.double())
+    assert relerr(y[..., :cout].float(), ref) < TOL[dtype]
+    assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0
