@@ -1044,7 +1044,7 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
   const int pm = persist_mode();
   const long big_tiles = (p.N > 128 && !p.out_f32) ? (long)((p.M + 127) / 128) * ((p.N + 255) / 256)
                                                    : (long)((p.M + 255) / 256) * ((p.N + 127) / 128);
-  const bool persist = im2col && p.N > 64 && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
+  const bool persist = im2col && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
   if (persist) {
     // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs (and N <= 128) use 2 x (128 x <=128)
     const bool wide = p.N > 128 && !p.out_f32;

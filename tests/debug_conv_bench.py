@@ -15,6 +15,8 @@ SHAPES = [  # n, h, w, cin, cout, k
     (512, 32, 32, 256, 256, 3),
     (1024, 14, 14, 128, 128, 5),
     (200704, 1, 1, 32, 138, 1, 6),
+    (524288, 1, 1, 256, 27, 1, 5),
+    (200704, 1, 1, 144, 25, 1, 7),
     (1024, 14, 14, 64, 138, 5, 6),
 ]
 
