@@ -218,7 +218,7 @@ def kernel_roofline(model, rows, pk):
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
     if os.path.exists(tp):
-        traffic = _json.load(open(tp)).get(name)
+        traffic = _json.load(open(tp)).get(name.split(' (')[0])
     return {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_burst'],
             'traffic': traffic, 'peak_source': pk['src'] + ' bf16 burst (kernel timed alone)', 'kernel': name,
             'launch_ms': ms / nl, 'flops_per_launch': flops / nl, 'launches_per_call': nl, 'conv_family_share_of_step': fam / tot}

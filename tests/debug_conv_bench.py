@@ -18,15 +18,19 @@ SHAPES = [  # n, h, w, cin, cout, k
     (524288, 1, 1, 256, 27, 1, 5),
     (200704, 1, 1, 144, 25, 1, 7),
     (1024, 14, 14, 64, 138, 5, 6),
+    (1024, 14, 14, 128, 138, 5, 6, 2),   # the conv g_h2 transposes (bench.py's MNIST roofline kernel is its dgrad)
 ]
 
 
-def desc(n, h, w, cin, cout, k, pady=0):
+def desc(n, h, w, cin, cout, k, pady=0, stride=1):
+    from robust_conditional_gan_b200.graph import same_pad
     d = _C.ConvDesc()
-    d.n, d.h, d.w, d.cin, d.ho, d.wo, d.cout = n, h, w, cin, h, w, cout
+    ho, pt = same_pad(h, k, stride)
+    wo, pl = same_pad(w, k, stride)
+    d.n, d.h, d.w, d.cin, d.ho, d.wo, d.cout = n, h, w, cin, ho, wo, cout
     d.kh = d.kw = k
-    d.stride = 1
-    d.pad_t = d.pad_l = (k - 1) // 2
+    d.stride = stride
+    d.pad_t, d.pad_l = pt, pl
     d.ldx, d.ldy, d.dtype = cin, cout + pady, _C.BF16
     return d
 
@@ -42,10 +46,12 @@ def main():
             continue
         n, h, w, cin, cout, k = shp[:6]
         pady = shp[6] if len(shp) > 6 else 0
+        stride = shp[7] if len(shp) > 7 else 1
+        ho, wo = -(-h // stride), -(-w // stride)
         d = desc(*shp)
         x = torch.randn(n, h, w, cin, device=dev).bfloat16()
         wt = torch.randn(k, k, cin, cout, device=dev) * 0.05
-        y = torch.empty(n, h, w, cout + pady, device=dev, dtype=torch.bfloat16)
+        y = torch.empty(n, ho, wo, cout + pady, device=dev, dtype=torch.bfloat16)
         nb = _C.load().rcgan_conv_wpack_bytes(ctypes.byref(d))
         pack = torch.empty(nb, dtype=torch.uint8, device=dev)
         _C.call('rcgan_conv_wpack', ctypes.byref(d), wt.data_ptr(), None, pack.data_ptr(), st)
@@ -77,9 +83,9 @@ def main():
                 err = 0.0
             else:
                 err = float((y.float() - ref).abs().max())
-            fl = 2.0 * n * h * w * cin * cout * k * k
+            fl = 2.0 * n * ho * wo * cin * cout * k * k
             if os.environ.get('CONV_BENCH_BWD') and var == variants[0]:
-                dy = torch.randn(n, h, w, cout + pady, device=dev).bfloat16()
+                dy = torch.randn(n, ho, wo, cout + pady, device=dev).bfloat16()
                 dx = torch.empty(n, h, w, cin, device=dev, dtype=torch.bfloat16)
                 dw = torch.empty(k, k, cin, cout, device=dev)
                 db = torch.empty(cout, device=dev)
@@ -89,7 +95,7 @@ def main():
                                                           None, dx.data_ptr(), _C.BF16, 0, 0.0, 0, st)),
                                ('wgrad', lambda: _C.call('rcgan_conv2d_wgrad', ctypes.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 0,
                                                           ws.data_ptr(), wsb, st)),
-                               ('colsum', lambda: _C.call('rcgan_colsum', dy.data_ptr(), n * h * w, cout, cout, _C.BF16, db.data_ptr(), 0, st))):
+                               ('colsum', lambda: _C.call('rcgan_colsum', dy.data_ptr(), n * ho * wo, cout, cout + pady, _C.BF16, db.data_ptr(), 0, st))):
                   for wv in os.environ.get('WG_WAVES', '2').split(','):
                     os.environ['RCGAN_WG_WAVES_X2'] = wv
                     if nm != 'wgrad' and wv != os.environ.get('WG_WAVES', '2').split(',')[0]:
