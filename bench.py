@@ -111,19 +111,45 @@ def oracle_iteration_timer(B, flags, threads):
     return step
 
 
+def oracle_iteration_timer_cifar(n, flags, threads):
+    """CIFAR arm of the CPU port: oracle/cifar.py's Trainer, one iteration = 1 G step (batch 2n) + 5 D steps (gan_resnet.py:919-947)."""
+    import torch
+    from oracle import cifar as OC
+    torch.set_num_threads(threads)
+    cfg = OC.default_config(alpha=0.5, **flags)
+    P = OC.init_params(cfg, seed=0, dtype=torch.float32)
+    b = OC.synthetic_batch(n, seed=0, dtype=torch.float32)
+    tr = OC.Trainer(P, cfg)
+
+    def step():
+        t = time.perf_counter()
+        tr.g_step(b, it=1)
+        for _ in range(5):
+            tr.d_step(b, it=1)
+        return time.perf_counter() - t
+    return step
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count()
-    B = 128                                  # bounded sample: one iteration at 1/8 of the workload batch
-    step = oracle_iteration_timer(B, wl['flags'], cores)
+    if wl.get('kind') == 'cifar':
+        B = 8                                # bounded sample: tower batch 8 (the workload's 256 would take minutes per step)
+        step = oracle_iteration_timer_cifar(B, wl['flags'], cores)
+        per_step = 5 * B
+        sample = 'oracle iteration (1 G step at 2n + 5 D steps, SN-ResNet dim 128) at tower batch %d, fp32, %d threads' % (B, cores)
+    else:
+        B = 128                              # bounded sample: one iteration at 1/8 of the workload batch
+        step = oracle_iteration_timer(B, wl['flags'], cores)
+        per_step = B
+        sample = 'oracle iteration (1 D + 2 G steps, literal reference graph) at batch %d, fp32, %d threads' % (B, cores)
     for _ in range(min(args.warmup, 2)):
         step()
     ts = [step() for _ in range(args.steps)]
     t = sum(ts) / len(ts)
-    v = B / t
-    sample = 'oracle iteration (1 D + 2 G steps, literal reference graph) at batch %d, fp32, %d threads' % (B, cores)
+    v = per_step / t
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -373,13 +399,21 @@ def run_ours(args, wl):
         with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
             json.dump(rows, f, indent=1)
         # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
-        if not args.no_cpu_baseline and wl.get('kind') != 'cifar':
+        if not args.no_cpu_baseline:
             cores = os.cpu_count()
-            step = oracle_iteration_timer(B, wl['flags'], cores)
-            step()
-            t = step()
-            result['cpu_baseline'] = {'value': B / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                      'sample': '1 warm-up + 1 timed oracle iteration (1 D + 2 G steps) at batch %d, fp32' % B}
+            if wl.get('kind') == 'cifar':
+                nb = 8
+                step = oracle_iteration_timer_cifar(nb, wl['flags'], cores)
+                step()
+                t = step()
+                result['cpu_baseline'] = {'value': 5 * nb / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                          'sample': '1 warm-up + 1 timed oracle iteration (1 G + 5 D steps) at tower batch %d, fp32' % nb}
+            else:
+                step = oracle_iteration_timer(B, wl['flags'], cores)
+                step()
+                t = step()
+                result['cpu_baseline'] = {'value': B / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                          'sample': '1 warm-up + 1 timed oracle iteration (1 D + 2 G steps) at batch %d, fp32' % B}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
