@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -16,6 +17,15 @@ void rcgan_set_error(const char* fmt, ...) {
 #include <atomic>
 static std::atomic<long> g_launches{0};
 void rcgan_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool rcgan_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RCGAN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 extern "C" long rcgan_launch_count(void) { return g_launches.load(); }
 
 extern "C" const char* rcgan_last_error(void) { return g_err; }

@@ -32,6 +32,30 @@ void rcgan_count_launch();  // every kernel launch of this library bumps rcgan_l
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL).  A training step is hundreds of short dependent kernels on one stream (422 per
+// MNIST iteration, ~12 us each), so the launch gap between them is a first-order cost.  Every kernel of the library is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with pdl_sync(): griddepcontrol.wait blocks
+// until the previous kernel has fully completed and flushed (so no dependency analysis is needed -- nothing is read or
+// written earlier), griddepcontrol.launch_dependents lets the NEXT kernel's CTAs be scheduled while this one drains.
+// The conv kernels run their prologue (barrier init, TMEM allocation, descriptor prefetch) before the wait.
+// Captured into the step's CUDA graph as programmatic edges.  RCGAN_PDL=0 launches without the attribute.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool rcgan_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = rcgan_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }

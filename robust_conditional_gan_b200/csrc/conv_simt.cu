@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p, const T* __rest
                                                         const float* __restrict__ wt,           // weights (fprop/dgrad)
                                                         const T* __restrict__ dy_in,            // dy (wgrad)
                                                         void* __restrict__ out_) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int TM = BM / 16, TN = BN / 16;
   constexpr int A_PER_T = BM * BK / 256, B_PER_T = BN * BK / 256 > 0 ? BN * BK / 256 : 1;
   __shared__ float As[BK][BM + 4];
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvP p, const T* __rest
 template <int MODE, int NOUT, typename T, typename TO>
 __global__ void __launch_bounds__(256) conv_narrow_kernel(ConvP p, const T* __restrict__ src, const float* __restrict__ wt,
                                                           TO* __restrict__ out) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int V = 16 / sizeof(T);                 // elements per 16-byte chunk
   extern __shared__ float wsm[];                    // [taps][NOUT][Cp], Cp = C rounded up to V, zero padded
   const int taps = p.kh * p.kw;
@@ -343,7 +345,7 @@ void launch_narrow_n(const ConvP& p, const void* src, const float* w, void* out,
   }
   long groups = ((long)p.M + 31) / 32;
   int grid = (int)(groups < 1 ? 1 : (groups > RCGAN_NUM_SMS * 16 ? RCGAN_NUM_SMS * 16 : groups));
-  conv_narrow_kernel<MODE, NOUT, T, TO><<<grid, 256, shb, st>>>(p, (const T*)src, w, (TO*)out);
+  launch_pdl(conv_narrow_kernel<MODE, NOUT, T, TO>, grid, 256, shb, st, p, (const T*)src, w, (TO*)out);
 }
 
 template <int MODE, typename T, typename TO>
@@ -372,6 +374,7 @@ bool launch_narrow(const ConvP& p, const void* src, const float* w, void* out, c
 template <bool XWIDE, int KS, int CN, typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_narrow_kernel(ConvP p, const T* __restrict__ x, const T* __restrict__ dy,
                                                                 float* __restrict__ dw, int pix_per_block) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int TAPS = KS * KS;
   const int cw = XWIDE ? p.cin : p.cout;       // wide channel count; CN = narrow channel count (<= 4)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
@@ -430,10 +433,10 @@ template <bool XW, int KS, typename T>
 void launch_wgrad_narrow_cn(const ConvP& p, int cn, const void* x, const void* dy, float* dw, dim3 grid, int bx, int ppb,
                             cudaStream_t st) {
   switch (cn) {
-    case 1: conv_wgrad_narrow_kernel<XW, KS, 1, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    case 2: conv_wgrad_narrow_kernel<XW, KS, 2, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    case 3: conv_wgrad_narrow_kernel<XW, KS, 3, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
-    default: conv_wgrad_narrow_kernel<XW, KS, 4, T><<<grid, bx, 0, st>>>(p, (const T*)x, (const T*)dy, dw, ppb); break;
+    case 1: launch_pdl(conv_wgrad_narrow_kernel<XW, KS, 1, T>, grid, bx, 0, st, p, (const T*)x, (const T*)dy, dw, ppb); break;
+    case 2: launch_pdl(conv_wgrad_narrow_kernel<XW, KS, 2, T>, grid, bx, 0, st, p, (const T*)x, (const T*)dy, dw, ppb); break;
+    case 3: launch_pdl(conv_wgrad_narrow_kernel<XW, KS, 3, T>, grid, bx, 0, st, p, (const T*)x, (const T*)dy, dw, ppb); break;
+    default: launch_pdl(conv_wgrad_narrow_kernel<XW, KS, 4, T>, grid, bx, 0, st, p, (const T*)x, (const T*)dy, dw, ppb); break;
   }
 }
 
@@ -466,6 +469,7 @@ bool launch_wgrad_narrow(const ConvP& p, const void* x, const void* dy, float* d
 
 // dw (=|+=) sum over splits
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long mn, int nsplit, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mn) return;
   float s = 0.f;
@@ -512,6 +516,7 @@ int wgrad_splits(const ConvP& p) {
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) linear_skinny_kernel(ConvP p, const T* __restrict__ x, const float* __restrict__ wt,
                                                             TO* __restrict__ out) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float wsk[];   // [K][17]
   for (int i = threadIdx.x; i < p.K * 16; i += 256) {
     const int k = i >> 4, j = i & 15;
@@ -554,7 +559,7 @@ bool launch_skinny(const ConvP& p, const void* x, const float* w, void* out, cud
   }
   int grid = ceil_div(p.M, 8);
   if (grid > RCGAN_NUM_SMS * 2) grid = RCGAN_NUM_SMS * 2;
-  linear_skinny_kernel<T, TO><<<grid, 256, shb, st>>>(p, (const T*)x, w, (TO*)out);
+  launch_pdl(linear_skinny_kernel<T, TO>, grid, 256, shb, st, p, (const T*)x, w, (TO*)out);
   return true;
 }
 
@@ -562,10 +567,10 @@ template <int MODE, typename T, typename TO>
 void launch(const ConvP& p, const void* a, const float* w, const void* dy, void* out, int nz, cudaStream_t st) {
   if (p.N <= 16 && MODE != MODE_WGRAD) {
     dim3 grid(ceil_div(p.M, 256), ceil_div(p.N, 16), nz);
-    conv_simt_kernel<MODE, T, TO, 256, 16><<<grid, 256, 0, st>>>(p, (const T*)a, w, (const T*)dy, out);
+    launch_pdl(conv_simt_kernel<MODE, T, TO, 256, 16>, grid, 256, 0, st, p, (const T*)a, w, (const T*)dy, out);
   } else {
     dim3 grid(ceil_div(p.M, 64), ceil_div(p.N, 64), nz);
-    conv_simt_kernel<MODE, T, TO, 64, 64><<<grid, 256, 0, st>>>(p, (const T*)a, w, (const T*)dy, out);
+    launch_pdl(conv_simt_kernel<MODE, T, TO, 64, 64>, grid, 256, 0, st, p, (const T*)a, w, (const T*)dy, out);
   }
 }
 
@@ -664,7 +669,7 @@ extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const
   else launch<MODE_WGRAD, bf16, float>(p, x, nullptr, dy, ws, ns, as_stream(stream));
   RCGAN_LAUNCH_CHECK("conv2d_wgrad");
   long mn = (long)p.M * p.N;
-  splitk_reduce_kernel<<<ceil_div(mn, 256), 256, 0, as_stream(stream)>>>((const float*)ws, dw, mn, ns, accumulate);
+  launch_pdl(splitk_reduce_kernel, ceil_div(mn, 256), 256, 0, as_stream(stream), (const float*)ws, dw, mn, ns, accumulate);
   RCGAN_LAUNCH_CHECK("conv2d_wgrad_reduce");
   return 0;
 }

@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // PDL: the prologue above overlapped the previous kernel's tail; its results are touched only from here on
 
   if (warp < 4) {
     // =========================================================== A producers (then epilogue)
@@ -527,6 +528,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // PDL: the prologue above overlapped the previous kernel's tail; its results are touched only from here on
 
   if (warp < 4) {
     // =========================================================== epilogue warps
@@ -697,6 +699,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // PDL: the prologue above overlapped the previous kernel's tail; its results are touched only from here on
   if (nkb <= 0) {            // empty split (cannot happen with the host's split choice; keep teardown well-formed)
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem_base, BN);
@@ -869,6 +872,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 // weights fp32 [taps][cin][cout] (* scale) -> bf16  F: [taps][cout][kpadF]   D: [taps][cin][kpadD]
 __global__ void wpack_kernel(const float* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ packF,
                              bf16* __restrict__ packD, int taps, int cin, int cout, int kpadF, int kpadD) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const float sc = scale ? *scale : 1.f;
   long nF = (long)taps * cout * kpadF, nD = (long)taps * cin * kpadD;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nF + nD; i += (long)gridDim.x * blockDim.x) {
@@ -985,7 +989,7 @@ int launch_tc(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap
     attr_done = true;
   }
   dim3 grid(((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN));
-  conv_tc_kernel<BN, ST, IM2COL><<<grid, 192, Cfg<BN, ST>::SMEM, st>>>(p, map, amap);
+  launch_pdl(conv_tc_kernel<BN, ST, IM2COL>, grid, 192, Cfg<BN, ST>::SMEM, st, p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc");
   return 0;
 }
@@ -1024,7 +1028,7 @@ int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorM
   }
   const int n_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * ((p.N + p.bn_eff - 1) / p.bn_eff);
   const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
-  conv_tc_persist_kernel<BN, MT, ST, TO><<<grid, 192, C::SMEM, st>>>(p, map, amap);
+  launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO>, grid, 192, C::SMEM, st, p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
   return 0;
 }
@@ -1083,7 +1087,7 @@ extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const 
   int grid = (int)((n + 255) / 256);
   if (grid > RCGAN_NUM_SMS * 8) grid = RCGAN_NUM_SMS * 8;
   bf16* pk = reinterpret_cast<bf16*>(pack);
-  wpack_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
+  launch_pdl(wpack_kernel, grid, 256, 0, as_stream(stream), w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
   RCGAN_LAUNCH_CHECK("conv_wpack");
   return 0;
 }
@@ -1157,7 +1161,7 @@ static int launch_wgrad_tc(const WgParams& p, const CUtensorMap& map, const CUte
     if (e != cudaSuccess) { rcgan_set_error("wgrad_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
-  wgrad_tc_kernel<BN, IM2COL><<<grid, 192, WgCfg<BN>::SMEM, st>>>(p, map, xmap);
+  launch_pdl(wgrad_tc_kernel<BN, IM2COL>, grid, 192, WgCfg<BN>::SMEM, st, p, map, xmap);
   RCGAN_LAUNCH_CHECK("wgrad_tc");
   return 0;
 }

@@ -51,6 +51,7 @@ template <typename T, int V> __device__ __forceinline__ void stv(T* p, const flo
 template <typename T, int V>
 __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
                                                            long rows, int c, int ldx, int ldy, int act, float leak) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   GRID_STRIDE(i, rows * cv) {
     long r = i / cv;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(const T* __restrict__
 template <typename T, int V>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long rows,
                                                       int c, int ld_dy, int ld_y, int ld_dx, int act, float leak, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   GRID_STRIDE(i, rows * cv) {
     long r = i / cv;
@@ -88,6 +90,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) concat_label_kernel(const T* __restrict__ a, int lda, const float* __restrict__ yb,
                                                            T* __restrict__ out, int ldo, long rows, int rows_per_sample, int c1,
                                                            int c2) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = ldo / V;
   GRID_STRIDE(i, rows * cv) {
     long r = i / cv;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) concat_label_kernel(const T* __restrict__
 template <typename T, int V>
 __global__ void __launch_bounds__(256) slice_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ da, int lda, long rows,
                                                         int c1, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c1 / V;
   GRID_STRIDE(i, rows * cv) {
     long r = i / cv;
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(256) slice_bwd_kernel(const T* __restrict__ do
 // one thread per (sample, channel vector); loops hw (coalesced over channels)
 template <typename T, int V>
 __global__ void __launch_bounds__(128) meanhw_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int samples, int hw, int c, int relu) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   GRID_STRIDE(i, (long)samples * cv) {
     long s = i / cv;
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(128) meanhw_fwd_kernel(const T* __restrict__ x
 template <typename T, int V>
 __global__ void __launch_bounds__(256) meanhw_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                                          int samples, int hw, int c, int relu, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   const float inv = 1.f / hw;
   GRID_STRIDE(i, (long)samples * hw * cv) {
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(256) meanhw_bwd_kernel(const T* __restrict__ d
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int ho = h / 2, wo = w / 2, cv = c / V;
   GRID_STRIDE(i, (long)n * ho * wo * cv) {
     int ch = (int)(i % cv) * V;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(256) avgpool2_fwd_kernel(const T* __restrict__
 template <typename T, int V>
 __global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
                                                            int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int ho = h / 2, wo = w / 2, cv = c / V;
   GRID_STRIDE(i, (long)n * h * w * cv) {
     int ch = (int)(i % cv) * V;
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const T* __restrict__
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   GRID_STRIDE(i, (long)n * (2 * h) * (2 * w) * cv) {
     int ch = (int)(i % cv) * V;
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(256) upsample2_fwd_kernel(const T* __restrict_
 template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c,
                                                             int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int cv = c / V;
   GRID_STRIDE(i, (long)n * h * w * cv) {
     int ch = (int)(i % cv) * V;
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict_
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long nvec) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   GRID_STRIDE(i, nvec) {
     float x[V], y[V];
     ldv<T, V>(a + i * V, x); ldv<T, V>(b + i * V, y);
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) copy_acc_kernel(const T* __restrict__ src, T* __restrict__ dst, long nvec, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   GRID_STRIDE(i, nvec) {
     float x[V], y[V];
     ldv<T, V>(src + i * V, x);
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(256) copy_acc_kernel(const T* __restrict__ src
 // 4 elements per thread (16-byte fp32 side, 8-byte bf16 side)
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long numel, int vec) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const long nv = vec ? numel / 4 : 0;
   GRID_STRIDE(i, nv) {
     float v[4];
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const S* __restrict__ src, D*
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld, float* __restrict__ db, int accumulate,
                               int use_atomic) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float sh[8][33];
   int ch = blockIdx.x * 32 + threadIdx.x;
   int rows_per = (rows + gridDim.y - 1) / gridDim.y;
@@ -333,6 +347,7 @@ __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld,
 template <typename T, int V>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, int rows, int cg, int ld, int LC,
                                                          float* __restrict__ db, int accumulate, int use_atomic) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float sh[256 * V];
   const int LR = 256 / LC;
   const int lc = threadIdx.x % LC, lr = threadIdx.x / LC;
@@ -371,6 +386,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ d
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n, int h, int w, int cin, int ho, int wo, int kh,
                               int kw, int stride, int pad_t, int pad_l, int ldx, int ldp) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int K = kh * kw * cin;
   long total = (long)n * ho * wo * ldp;
   GRID_STRIDE(i, total) {
@@ -394,6 +410,7 @@ __global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ P, int n,
 __global__ void __launch_bounds__(256) im2col_bf16x8_kernel(const bf16* __restrict__ x, bf16* __restrict__ P, int n, int h, int w,
                                                             int cin, int ho, int wo, int kh, int kw, int stride, int pad_t, int pad_l,
                                                             int ldx, int ldp) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int K = kh * kw * cin, pieces = ldp / 8;
   const long total = (long)n * ho * wo * pieces;
   GRID_STRIDE(i, total) {
@@ -427,6 +444,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ T, int ldt, const float* __restrict__ bias,
                                                      TO* __restrict__ x, int n, int h, int w, int cin, int ho, int wo, int kh, int kw,
                                                      int stride, int pad_t, int pad_l, int ldx, int act, float leak, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const long total = (long)n * h * w * cin;
   GRID_STRIDE(i, total) {
     const int ci = (int)(i % cin);
@@ -454,6 +472,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ T
 
 __global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ out, int kh, int kw, int cin, int cout,
                              int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   long total = (long)kh * kw * cin * cout;
   GRID_STRIDE(i, total) {      // i indexes out: [tap'][co][ci]
     int ci = (int)(i % cin);
@@ -467,6 +486,7 @@ __global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ ou
 
 __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   long total = (long)n * 3072;
   GRID_STRIDE(i, total) {
     // i indexes the NHWC output: ((nb*32 + y)*32 + x)*3 + ch ; source is CHW
@@ -509,8 +529,7 @@ extern "C" int rcgan_bias_act_fwd(const void* x, const float* bias, void* y, lon
   if (rows == 0) return 0;
   const int w = vw(dtype);
   const bool ok = c % w == 0 && ldx % w == 0 && ldy % w == 0 && aligned16(x) && aligned16(y);
-  DISPATCH_TV(dtype, ok, bias_act_fwd_kernel<T, V><<<grid_for(rows * c / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)x, bias, (T*)y, rows, c, ldx, ldy, act, leak));
+  DISPATCH_TV(dtype, ok, launch_pdl(bias_act_fwd_kernel<T, V>, grid_for(rows * c / V, 256), 256, 0, as_stream(stream), (const T*)x, bias, (T*)y, rows, c, ldx, ldy, act, leak));
   RCGAN_LAUNCH_CHECK("bias_act_fwd");
   return 0;
 }
@@ -521,8 +540,7 @@ extern "C" int rcgan_act_bwd(const void* dy, const void* y, void* dx, long rows,
   if (rows == 0) return 0;
   const int w = vw(dtype);
   const bool ok = c % w == 0 && ld_dy % w == 0 && ld_y % w == 0 && ld_dx % w == 0 && aligned16(dy) && aligned16(y) && aligned16(dx);
-  DISPATCH_TV(dtype, ok, act_bwd_kernel<T, V><<<grid_for(rows * c / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)dy, (const T*)y, (T*)dx, rows, c, ld_dy, ld_y, ld_dx, act, leak, accumulate));
+  DISPATCH_TV(dtype, ok, launch_pdl(act_bwd_kernel<T, V>, grid_for(rows * c / V, 256), 256, 0, as_stream(stream), (const T*)dy, (const T*)y, (T*)dx, rows, c, ld_dy, ld_y, ld_dx, act, leak, accumulate));
   RCGAN_LAUNCH_CHECK("act_bwd");
   return 0;
 }
@@ -533,8 +551,7 @@ extern "C" int rcgan_concat_label_fwd(const void* a, int lda, const float* yb, v
                   "concat_label_fwd: bad shape");
   const int w = vw(dtype);
   const bool ok = ldo % w == 0 && lda % w == 0 && aligned16(a) && aligned16(out);
-  DISPATCH_TV(dtype, ok, concat_label_kernel<T, V><<<grid_for(rows * ldo / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)a, lda, yb, (T*)out, ldo, rows, rows_per_sample, c1, c2));
+  DISPATCH_TV(dtype, ok, launch_pdl(concat_label_kernel<T, V>, grid_for(rows * ldo / V, 256), 256, 0, as_stream(stream), (const T*)a, lda, yb, (T*)out, ldo, rows, rows_per_sample, c1, c2));
   RCGAN_LAUNCH_CHECK("concat_label_fwd");
   return 0;
 }
@@ -544,8 +561,7 @@ extern "C" int rcgan_slice_bwd(const void* dout, int ldo, void* da, int lda, lon
   RCGAN_CHECK_ARG(rows > 0 && c1 > 0 && ldo >= c1 && lda >= c1, "slice_bwd: bad shape");
   const int w = vw(dtype);
   const bool ok = c1 % w == 0 && ldo % w == 0 && lda % w == 0 && aligned16(dout) && aligned16(da);
-  DISPATCH_TV(dtype, ok, slice_bwd_kernel<T, V><<<grid_for(rows * c1 / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)dout, ldo, (T*)da, lda, rows, c1, accumulate));
+  DISPATCH_TV(dtype, ok, launch_pdl(slice_bwd_kernel<T, V>, grid_for(rows * c1 / V, 256), 256, 0, as_stream(stream), (const T*)dout, ldo, (T*)da, lda, rows, c1, accumulate));
   RCGAN_LAUNCH_CHECK("slice_bwd");
   return 0;
 }
@@ -553,8 +569,7 @@ extern "C" int rcgan_slice_bwd(const void* dout, int ldo, void* da, int lda, lon
 extern "C" int rcgan_meanhw_fwd(const void* x, void* y, int samples, int hw, int c, int dtype, int relu, void* stream) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "meanhw_fwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
-  DISPATCH_TV(dtype, ok, meanhw_fwd_kernel<T, V><<<grid_for((long)samples * c / V, 128), 128, 0, as_stream(stream)>>>(
-                             (const T*)x, (T*)y, samples, hw, c, relu));
+  DISPATCH_TV(dtype, ok, launch_pdl(meanhw_fwd_kernel<T, V>, grid_for((long)samples * c / V, 128), 128, 0, as_stream(stream), (const T*)x, (T*)y, samples, hw, c, relu));
   RCGAN_LAUNCH_CHECK("meanhw_fwd");
   return 0;
 }
@@ -563,8 +578,7 @@ extern "C" int rcgan_meanhw_bwd(const void* dy, const void* x, void* dx, int sam
                                 int accumulate, void* stream) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "meanhw_bwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(x) && aligned16(dx);
-  DISPATCH_TV(dtype, ok, meanhw_bwd_kernel<T, V><<<grid_for((long)samples * hw * c / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)dy, (const T*)x, (T*)dx, samples, hw, c, relu, accumulate));
+  DISPATCH_TV(dtype, ok, launch_pdl(meanhw_bwd_kernel<T, V>, grid_for((long)samples * hw * c / V, 256), 256, 0, as_stream(stream), (const T*)dy, (const T*)x, (T*)dx, samples, hw, c, relu, accumulate));
   RCGAN_LAUNCH_CHECK("meanhw_bwd");
   return 0;
 }
@@ -572,8 +586,7 @@ extern "C" int rcgan_meanhw_bwd(const void* dy, const void* x, void* dx, int sam
 extern "C" int rcgan_avgpool2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "avgpool2_fwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
-  DISPATCH_TV(dtype, ok, avgpool2_fwd_kernel<T, V><<<grid_for((long)n * h * w * c / 4 / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)x, (T*)y, n, h, w, c));
+  DISPATCH_TV(dtype, ok, launch_pdl(avgpool2_fwd_kernel<T, V>, grid_for((long)n * h * w * c / 4 / V, 256), 256, 0, as_stream(stream), (const T*)x, (T*)y, n, h, w, c));
   RCGAN_LAUNCH_CHECK("avgpool2_fwd");
   return 0;
 }
@@ -581,16 +594,14 @@ extern "C" int rcgan_avgpool2_bwd(const void* dy, void* dx, int n, int h, int w,
                                   void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, "avgpool2_bwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(dx);
-  DISPATCH_TV(dtype, ok, avgpool2_bwd_kernel<T, V><<<grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)dy, (T*)dx, n, h, w, c, accumulate));
+  DISPATCH_TV(dtype, ok, launch_pdl(avgpool2_bwd_kernel<T, V>, grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream), (const T*)dy, (T*)dx, n, h, w, c, accumulate));
   RCGAN_LAUNCH_CHECK("avgpool2_bwd");
   return 0;
 }
 extern "C" int rcgan_upsample2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2_fwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(x) && aligned16(y);
-  DISPATCH_TV(dtype, ok, upsample2_fwd_kernel<T, V><<<grid_for((long)n * h * w * c * 4 / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)x, (T*)y, n, h, w, c));
+  DISPATCH_TV(dtype, ok, launch_pdl(upsample2_fwd_kernel<T, V>, grid_for((long)n * h * w * c * 4 / V, 256), 256, 0, as_stream(stream), (const T*)x, (T*)y, n, h, w, c));
   RCGAN_LAUNCH_CHECK("upsample2_fwd");
   return 0;
 }
@@ -598,15 +609,14 @@ extern "C" int rcgan_upsample2_bwd(const void* dy, void* dx, int n, int h, int w
                                    void* stream) {
   RCGAN_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2_bwd: bad shape");
   const bool ok = c % vw(dtype) == 0 && aligned16(dy) && aligned16(dx);
-  DISPATCH_TV(dtype, ok, upsample2_bwd_kernel<T, V><<<grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream)>>>(
-                             (const T*)dy, (T*)dx, n, h, w, c, accumulate));
+  DISPATCH_TV(dtype, ok, launch_pdl(upsample2_bwd_kernel<T, V>, grid_for((long)n * h * w * c / V, 256), 256, 0, as_stream(stream), (const T*)dy, (T*)dx, n, h, w, c, accumulate));
   RCGAN_LAUNCH_CHECK("upsample2_bwd");
   return 0;
 }
 extern "C" int rcgan_add(const void* a, const void* b, void* out, long numel, int dtype, void* stream) {
   RCGAN_CHECK_ARG(numel > 0, "add: bad shape");
   const bool ok = numel % vw(dtype) == 0 && aligned16(a) && aligned16(b) && aligned16(out);
-  DISPATCH_TV(dtype, ok, add_kernel<T, V><<<grid_for(numel / V, 256), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out,
+  DISPATCH_TV(dtype, ok, launch_pdl(add_kernel<T, V>, grid_for(numel / V, 256), 256, 0, as_stream(stream), (const T*)a, (const T*)b, (T*)out,
                                                                                                   numel / V));
   RCGAN_LAUNCH_CHECK("add");
   return 0;
@@ -614,7 +624,7 @@ extern "C" int rcgan_add(const void* a, const void* b, void* out, long numel, in
 extern "C" int rcgan_copy_acc(const void* src, void* dst, long numel, int dtype, int accumulate, void* stream) {
   RCGAN_CHECK_ARG(numel > 0, "copy_acc: bad shape");
   const bool ok = numel % vw(dtype) == 0 && aligned16(src) && aligned16(dst);
-  DISPATCH_TV(dtype, ok, copy_acc_kernel<T, V><<<grid_for(numel / V, 256), 256, 0, as_stream(stream)>>>((const T*)src, (T*)dst,
+  DISPATCH_TV(dtype, ok, launch_pdl(copy_acc_kernel<T, V>, grid_for(numel / V, 256), 256, 0, as_stream(stream), (const T*)src, (T*)dst,
                                                                                                        numel / V, accumulate));
   RCGAN_LAUNCH_CHECK("copy_acc");
   return 0;
@@ -624,10 +634,10 @@ extern "C" int rcgan_cast(const void* src, int src_dtype, void* dst, int dst_dty
   const int vec = aligned16(src) && aligned16(dst);
   int g = grid_for(numel / 4 + 1, 256);
   cudaStream_t st = as_stream(stream);
-  if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, numel, vec);
-  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, numel, vec);
-  else if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, numel, vec);
-  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, numel, vec);
+  if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_BF16) launch_pdl(cast_kernel<float, bf16>, g, 256, 0, st, (const float*)src, (bf16*)dst, numel, vec);
+  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_F32) launch_pdl(cast_kernel<bf16, float>, g, 256, 0, st, (const bf16*)src, (float*)dst, numel, vec);
+  else if (src_dtype == RCGAN_F32 && dst_dtype == RCGAN_F32) launch_pdl(cast_kernel<float, float>, g, 256, 0, st, (const float*)src, (float*)dst, numel, vec);
+  else if (src_dtype == RCGAN_BF16 && dst_dtype == RCGAN_BF16) launch_pdl(cast_kernel<bf16, bf16>, g, 256, 0, st, (const bf16*)src, (bf16*)dst, numel, vec);
   else { rcgan_set_error("cast: bad dtypes"); return RCGAN_EBADSHAPE; }
   RCGAN_LAUNCH_CHECK("cast");
   return 0;
@@ -660,12 +670,12 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
   }
   if (vec) {
     dim3 grid(gx, gy);
-    if (dtype == RCGAN_F32) colsum_vec_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)dy, rows, c / 4, ld, LC, db, accumulate, gy > 1);
-    else if (dtype == RCGAN_BF16) colsum_vec_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)dy, rows, c / 8, ld, LC, db, accumulate, gy > 1);
+    if (dtype == RCGAN_F32) launch_pdl(colsum_vec_kernel<float, 4>, grid, 256, 0, st, (const float*)dy, rows, c / 4, ld, LC, db, accumulate, gy > 1);
+    else if (dtype == RCGAN_BF16) launch_pdl(colsum_vec_kernel<bf16, 8>, grid, 256, 0, st, (const bf16*)dy, rows, c / 8, ld, LC, db, accumulate, gy > 1);
     else { rcgan_set_error("bad dtype %d", dtype); return RCGAN_EBADSHAPE; }
   } else {
     dim3 grid(gx, gy), block(32, 8);
-    DISPATCH_T(dtype, colsum_kernel<T><<<grid, block, 0, st>>>((const T*)dy, rows, c, ld, db, accumulate, gy > 1));
+    DISPATCH_T(dtype, launch_pdl(colsum_kernel<T>, grid, block, 0, st, (const T*)dy, rows, c, ld, db, accumulate, gy > 1));
   }
   RCGAN_LAUNCH_CHECK("colsum");
   return 0;
@@ -675,14 +685,12 @@ extern "C" int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patch
   RCGAN_CHECK_ARG(d && x && patches && ldp >= d->kh * d->kw * d->cin, "im2col: bad args");
   long total = (long)d->n * d->ho * d->wo * ldp;
   if (d->dtype == RCGAN_BF16 && ldp % 8 == 0 && aligned16(patches)) {
-    im2col_bf16x8_kernel<<<grid_for(total / 8, 256), 256, 0, as_stream(stream)>>>(
-        (const bf16*)x, (bf16*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx,
+    launch_pdl(im2col_bf16x8_kernel, grid_for(total / 8, 256), 256, 0, as_stream(stream), (const bf16*)x, (bf16*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx,
         ldp);
     RCGAN_LAUNCH_CHECK("im2col");
     return 0;
   }
-  DISPATCH_T(d->dtype, im2col_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-                           (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
+  DISPATCH_T(d->dtype, launch_pdl(im2col_kernel<T>, grid_for(total, 256), 256, 0, as_stream(stream), (const T*)x, (T*)patches, d->n, d->h, d->w, d->cin, d->ho, d->wo, d->kh, d->kw, d->stride, d->pad_t,
                            d->pad_l, d->ldx, ldp));
   RCGAN_LAUNCH_CHECK("im2col");
   return 0;
@@ -694,11 +702,11 @@ extern "C" int rcgan_col2im(const rcgan_conv_desc* d, const float* T, int ldt, c
   const long total = (long)d->n * d->h * d->w * d->cin;
   RCGAN_CHECK_ARG(total > 0, "col2im: empty");
   if (out_dtype == RCGAN_F32)
-    col2im_kernel<float><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(T, ldt, bias, (float*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
+    launch_pdl(col2im_kernel<float>, grid_for(total, 256), 256, 0, as_stream(stream), T, ldt, bias, (float*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
                                                                             d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
                                                                             accumulate);
   else if (out_dtype == RCGAN_BF16)
-    col2im_kernel<bf16><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(T, ldt, bias, (bf16*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
+    launch_pdl(col2im_kernel<bf16>, grid_for(total, 256), 256, 0, as_stream(stream), T, ldt, bias, (bf16*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
                                                                            d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
                                                                            accumulate);
   else { rcgan_set_error("col2im: bad dtype %d", out_dtype); return RCGAN_EBADSHAPE; }
@@ -708,14 +716,14 @@ extern "C" int rcgan_col2im(const rcgan_conv_desc* d, const float* T, int ldt, c
 
 extern "C" int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream) {
   RCGAN_CHECK_ARG(w && out && kh > 0 && kw > 0 && cin > 0 && cout > 0, "wflip: bad args");
-  wflip_kernel<<<grid_for((long)kh * kw * cin * cout, 256), 256, 0, as_stream(stream)>>>(w, out, kh, kw, cin, cout, accumulate);
+  launch_pdl(wflip_kernel, grid_for((long)kh * kw * cin * cout, 256), 256, 0, as_stream(stream), w, out, kh, kw, cin, cout, accumulate);
   RCGAN_LAUNCH_CHECK("wflip");
   return 0;
 }
 
 extern "C" int rcgan_preprocess_cifar(const int32_t* chw, const float* noise, void* out, int n, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && (dtype == RCGAN_F32 || dtype == RCGAN_BF16), "preprocess_cifar: bad args");
-  preprocess_cifar_kernel<<<grid_for((long)n * 3072, 256), 256, 0, as_stream(stream)>>>(chw, noise, out, n, dtype == RCGAN_BF16);
+  launch_pdl(preprocess_cifar_kernel, grid_for((long)n * 3072, 256), 256, 0, as_stream(stream), chw, noise, out, n, dtype == RCGAN_BF16);
   RCGAN_LAUNCH_CHECK("preprocess_cifar");
   return 0;
 }

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) channel_loss_kernel(const T* __restrict__
                                                            int d, int k, int mode, float scale, float* loss_acc,
                                                            float* __restrict__ logits, T* __restrict__ dh, int accumulate_dh,
                                                            float* __restrict__ dpsi, float* dV, float* __restrict__ dwgt) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float sh[];  // V[k*d] then dV accumulators [k*d] then 8 loss partials
   float* Vs = sh;
   float* dVs = sh + k * d;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) channel_loss_kernel(const T* __restrict__
 
 __global__ void __launch_bounds__(256) sigmoid_ce_kernel(const float* __restrict__ logits, const float* __restrict__ targets,
                                                          long numel, float scale, float* loss_acc, float* __restrict__ dl) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float red[33];
   float s = 0.f;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < numel; i += (long)gridDim.x * 256) {
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) sigmoid_ce_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) logit_loss_kernel(const float* __restrict__ logits, long B, int mode, float scale,
                                                         float* loss_acc, float* __restrict__ dl) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float red[33];
   float s = 0.f;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < B; i += (long)gridDim.x * 256) {
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(256) logit_loss_kernel(const float* __restrict
 }
 
 __global__ void softmax_rows_fwd_kernel(const float* __restrict__ L, float* __restrict__ C, int rows, int k) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float mx = -INFINITY;
@@ -149,6 +153,7 @@ __global__ void softmax_rows_fwd_kernel(const float* __restrict__ L, float* __re
 
 __global__ void softmax_rows_bwd_kernel(const float* __restrict__ C, const float* __restrict__ dC, float* __restrict__ dL,
                                         int rows, int k, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float dot = 0.f;
@@ -161,6 +166,7 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ C, const float
 
 __global__ void gather_rows_fwd_kernel(const float* __restrict__ C, const int* __restrict__ y, float* __restrict__ wgt, int B,
                                        int k) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * k) return;
   int b = i / k, j = i - b * k;
@@ -170,6 +176,7 @@ __global__ void gather_rows_fwd_kernel(const float* __restrict__ C, const int* _
 // deterministic: one block per destination row, thread j < k scans the batch
 __global__ void gather_rows_bwd_kernel(const float* __restrict__ dwgt, const int* __restrict__ y, float* __restrict__ dC,
                                        int B, int k, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float red[33];
   int r = blockIdx.x;
   for (int j = 0; j < k; j++) {
@@ -195,7 +202,7 @@ extern "C" int rcgan_channel_loss(const void* h, const float* psi, const float* 
   if (grid > RCGAN_NUM_SMS * 2) grid = RCGAN_NUM_SMS * 2;
   size_t shb = ((size_t)2 * k * d + 8) * sizeof(float);
 #define CL_LAUNCH(T, DPL)                                                                                             \
-  channel_loss_kernel<T, DPL><<<grid, 256, shb, st>>>((const T*)h, psi, V, wgt, B, d, k, mode, scale, loss_acc, logits, \
+  launch_pdl(channel_loss_kernel<T, DPL>, grid, 256, shb, st, (const T*)h, psi, V, wgt, B, d, k, mode, scale, loss_acc, logits, \
                                                       (T*)dh, accumulate_dh, dpsi, dV, dwgt)
   if (dtype == RCGAN_F32) {
     if (d == 32) CL_LAUNCH(float, 1); else if (d == 64) CL_LAUNCH(float, 2); else if (d == 128) CL_LAUNCH(float, 4); else CL_LAUNCH(float, 8);
@@ -215,7 +222,7 @@ extern "C" int rcgan_sigmoid_ce(const float* logits, const float* targets, long 
   RCGAN_CHECK_ARG(logits && targets && numel > 0, "sigmoid_ce: bad args");
   int grid = (int)((numel + 255) / 256);
   if (grid > RCGAN_NUM_SMS) grid = RCGAN_NUM_SMS;
-  sigmoid_ce_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, targets, numel, scale, loss_acc, dlogits);
+  launch_pdl(sigmoid_ce_kernel, grid, 256, 0, as_stream(stream), logits, targets, numel, scale, loss_acc, dlogits);
   RCGAN_LAUNCH_CHECK("sigmoid_ce");
   return 0;
 }
@@ -225,34 +232,34 @@ extern "C" int rcgan_logit_loss(const float* logits, long B, int mode, float sca
   RCGAN_CHECK_ARG(logits && B > 0 && mode >= 0 && mode <= RCGAN_CE_G, "logit_loss: bad args");
   int grid = (int)((B + 255) / 256);
   if (grid > RCGAN_NUM_SMS) grid = RCGAN_NUM_SMS;
-  logit_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, B, mode, scale, loss_acc, dlogits);
+  launch_pdl(logit_loss_kernel, grid, 256, 0, as_stream(stream), logits, B, mode, scale, loss_acc, dlogits);
   RCGAN_LAUNCH_CHECK("logit_loss");
   return 0;
 }
 
 extern "C" int rcgan_softmax_rows_fwd(const float* logits, float* C, int rows, int k, void* stream) {
   RCGAN_CHECK_ARG(logits && C && rows > 0 && k > 0, "softmax_rows_fwd: bad args");
-  softmax_rows_fwd_kernel<<<ceil_div(rows, 32), 32, 0, as_stream(stream)>>>(logits, C, rows, k);
+  launch_pdl(softmax_rows_fwd_kernel, ceil_div(rows, 32), 32, 0, as_stream(stream), logits, C, rows, k);
   RCGAN_LAUNCH_CHECK("softmax_rows_fwd");
   return 0;
 }
 extern "C" int rcgan_softmax_rows_bwd(const float* C, const float* dC, float* dlogits, int rows, int k, int accumulate,
                                       void* stream) {
   RCGAN_CHECK_ARG(C && dC && dlogits && rows > 0 && k > 0, "softmax_rows_bwd: bad args");
-  softmax_rows_bwd_kernel<<<ceil_div(rows, 32), 32, 0, as_stream(stream)>>>(C, dC, dlogits, rows, k, accumulate);
+  launch_pdl(softmax_rows_bwd_kernel, ceil_div(rows, 32), 32, 0, as_stream(stream), C, dC, dlogits, rows, k, accumulate);
   RCGAN_LAUNCH_CHECK("softmax_rows_bwd");
   return 0;
 }
 extern "C" int rcgan_gather_rows_fwd(const float* C, const int* y, float* wgt, int B, int k, void* stream) {
   RCGAN_CHECK_ARG(C && y && wgt && B > 0 && k > 0, "gather_rows_fwd: bad args");
-  gather_rows_fwd_kernel<<<ceil_div((long)B * k, 256), 256, 0, as_stream(stream)>>>(C, y, wgt, B, k);
+  launch_pdl(gather_rows_fwd_kernel, ceil_div((long)B * k, 256), 256, 0, as_stream(stream), C, y, wgt, B, k);
   RCGAN_LAUNCH_CHECK("gather_rows_fwd");
   return 0;
 }
 extern "C" int rcgan_gather_rows_bwd(const float* dwgt, const int* y, float* dC, int B, int k, int rows, int accumulate,
                                      void* stream) {
   RCGAN_CHECK_ARG(dwgt && y && dC && B > 0 && k > 0 && rows > 0, "gather_rows_bwd: bad args");
-  gather_rows_bwd_kernel<<<rows, 128, 0, as_stream(stream)>>>(dwgt, y, dC, B, k, accumulate);
+  launch_pdl(gather_rows_bwd_kernel, rows, 128, 0, as_stream(stream), dwgt, y, dC, B, k, accumulate);
   RCGAN_LAUNCH_CHECK("gather_rows_bwd");
   return 0;
 }

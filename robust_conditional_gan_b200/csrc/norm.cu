@@ -91,6 +91,7 @@ Geo make_geo(int samples, int hw, int c, bool per_sample, int vmax = 4) {
 // ws layout (floats): [0, nchunk*c) = P1 ; [nchunk*c, 2*nchunk*c) = P2 ; then 2*c floats (A, B) for bwd
 template <typename TX, int V>
 __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const TX* __restrict__ x, Geo g, float* __restrict__ ws) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float sh[];  // [LR][LC*V] x 2
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) bn_stats_partial_kernel(const TX* __restr
 // one warp per channel: lanes stride over the chunks, Chan-merge their partials, then merge across lanes by shuffle
 __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(Geo g, const float* __restrict__ ws, float eps, float decay,
                                                                float* mm, float* mv, float* __restrict__ save) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (ch >= g.c) return;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(Geo g, const flo
 
 __global__ void bn_infer_stats_kernel(int c, const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                       float* __restrict__ save) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   save[ch] = mm[ch];
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
                                                        const float* __restrict__ scale, const float* __restrict__ offset,
                                                        const int* __restrict__ labels, const float* __restrict__ save,
                                                        int act, float leak) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
   if (cv >= g.cg) return;
@@ -224,6 +228,7 @@ template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
                                                              const TY* __restrict__ y, Geo g, const float* __restrict__ save,
                                                              int act, float leak, float* __restrict__ ws) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float sh[];
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(Geo g, float* __re
                                                              const int* __restrict__ labels, int n_labels,
                                                              float* __restrict__ dscale, float* __restrict__ doffset,
                                                              int accumulate_param) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (ch >= g.c) return;
@@ -338,6 +344,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
                                                         const float* __restrict__ scale, const int* __restrict__ labels,
                                                         const float* __restrict__ save, const float* __restrict__ AB,
                                                         int act, float leak, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
   if (cv >= g.cg) return;
@@ -432,19 +439,18 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
     RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_fwd: workspace too small");
     dim3 grid(g.gx, g.nchunk);
     size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
-    BN_DISPATCH(xdtype, ydtype, g.V, bn_stats_partial_kernel<TX, VV><<<grid, 256, shb, st>>>((const TX*)x, g, (float*)ws));
+    BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(bn_stats_partial_kernel<TX, VV>, grid, 256, shb, st, (const TX*)x, g, (float*)ws));
     RCGAN_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_finalize_kernel<<<ceil_div(c, 8), 256, 0, st>>>(g, (const float*)ws, eps, decay, moving_mean, moving_var, save);
+    launch_pdl(bn_stats_finalize_kernel, ceil_div(c, 8), 256, 0, st, g, (const float*)ws, eps, decay, moving_mean, moving_var, save);
     RCGAN_LAUNCH_CHECK("bn_stats_finalize");
   } else {
     RCGAN_CHECK_ARG(moving_mean && moving_var, "bn_fwd: inference needs moving statistics");
-    bn_infer_stats_kernel<<<ceil_div(c, 128), 128, 0, st>>>(c, moving_mean, moving_var, eps, save);
+    launch_pdl(bn_infer_stats_kernel, ceil_div(c, 128), 128, 0, st, c, moving_mean, moving_var, eps, save);
     RCGAN_LAUNCH_CHECK("bn_infer_stats");
   }
   // streaming geometry: 16-byte vectors when x and y are both bf16
   const Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
-  BN_DISPATCH(xdtype, ydtype, ga.V, bn_apply_kernel<TX, TY, VV><<<dim3(ga.gx, ga.nchunk), 256, 0, st>>>(
-                                        (const TX*)x, (TY*)y, ga, scale, offset, labels, save, act, leak));
+  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_apply_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TX*)x, (TY*)y, ga, scale, offset, labels, save, act, leak));
   RCGAN_LAUNCH_CHECK("bn_apply");
   return 0;
 }
@@ -462,16 +468,14 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
-  BN_DISPATCH(xdtype, ydtype, g.V, bn_bwd_partial_kernel<TX, TY, VV><<<grid, 256, shb, st>>>(
-                                       (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws));
+  BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(bn_bwd_partial_kernel<TX, TY, VV>, grid, 256, shb, st, (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws));
   RCGAN_LAUNCH_CHECK("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<ceil_div(c, 8), 256, 0, st>>>(g, (float*)ws, scale, labels, n_labels, dscale, doffset,
+  launch_pdl(bn_bwd_finalize_kernel, ceil_div(c, 8), 256, 0, st, g, (float*)ws, scale, labels, n_labels, dscale, doffset,
                                                             accumulate_param);
   RCGAN_LAUNCH_CHECK("bn_bwd_finalize");
   const float* AB = (const float*)ws + (size_t)2 * g.nchunk * c;
   const Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
-  BN_DISPATCH(xdtype, ydtype, ga.V, bn_bwd_dx_kernel<TX, TY, VV><<<dim3(ga.gx, ga.nchunk), 256, 0, st>>>(
-                                        (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
+  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
                                         leak, accumulate_dx));
   RCGAN_LAUNCH_CHECK("bn_bwd_dx");
   return 0;

@@ -10,6 +10,7 @@ struct ClipRanges { long lo[8]; long hi[8]; int n; };
 __global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                       float* __restrict__ v, long numel, float lr_t, const float* __restrict__ lr_t_dev,
                                                       float b1, float b2, float eps, float gs, ClipRanges cr) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   if (lr_t_dev) lr_t = *lr_t_dev;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < numel; i += (long)gridDim.x * 256) {
     float gi = g[i] * gs;
@@ -32,7 +33,7 @@ extern "C" int rcgan_adam_tf(float* p, const float* g, float* m, float* v, long 
   for (int k = 0; k < n_clip; k++) { cr.lo[k] = clip_lo[k]; cr.hi[k] = clip_hi[k]; }
   int grid = (int)((numel + 255) / 256);
   if (grid > RCGAN_NUM_SMS * 8) grid = RCGAN_NUM_SMS * 8;
-  adam_tf_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, m, v, numel, lr_t, lr_t_dev, b1, b2, eps, grad_scale, cr);
+  launch_pdl(adam_tf_kernel, grid, 256, 0, as_stream(stream), p, g, m, v, numel, lr_t, lr_t_dev, b1, b2, eps, grad_scale, cr);
   RCGAN_LAUNCH_CHECK("adam_tf");
   return 0;
 }

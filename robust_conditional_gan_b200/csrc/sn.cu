@@ -167,26 +167,32 @@ __device__ __forceinline__ void sn_bwd_dw_body(const float* __restrict__ G, cons
 
 __global__ void __launch_bounds__(256) sn_pass1_kernel(const float* __restrict__ W, const float* __restrict__ u, int m, int c,
                                                        float* __restrict__ a_out, float* __restrict__ ws) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_pass1_body(W, u, m, c, a_out, ws, blockIdx.x);
 }
 __global__ void __launch_bounds__(256) sn_finalize_kernel(int m, int c, int nblk, const float* __restrict__ ws,
                                                           float* __restrict__ u_new, float* __restrict__ save) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_finalize_body(m, c, nblk, ws, u_new, save);
 }
 __global__ void __launch_bounds__(256) sn_pass3_kernel(const float* __restrict__ W, int m, int c, float* __restrict__ w_bar,
                                                        float* __restrict__ save, float* __restrict__ ws2) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_pass3_body(W, m, c, w_bar, save, ws2, blockIdx.x);
 }
 __global__ void __launch_bounds__(256) sn_ta_kernel(int nblk, const float* __restrict__ ws2, float* __restrict__ save) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_ta_body(nblk, ws2, save);
 }
 __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ W, const float* __restrict__ G, long numel,
                                                          float* __restrict__ ws) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_bwd_dot_body(W, G, numel, ws, blockIdx.x, gridDim.x);
 }
 __global__ void __launch_bounds__(256) sn_bwd_dw_kernel(const float* __restrict__ G, const float* __restrict__ u, int m, int c,
                                                         const float* __restrict__ save, const float* __restrict__ ws,
                                                         int nparts, float* __restrict__ dW, int accumulate) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   sn_bwd_dw_body(G, u, m, c, save, ws, nparts, dW, accumulate, blockIdx.x, gridDim.x);
 }
 
@@ -201,26 +207,32 @@ struct SnItem {
 struct SnBatch { SnItem it[SN_MAX_BATCH]; };
 
 __global__ void __launch_bounds__(256) sn_pass1_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.y];
   if ((int)blockIdx.x < t.nblk) sn_pass1_body(t.W, t.u, t.m, t.c, t.save + 5, t.ws, blockIdx.x);
 }
 __global__ void __launch_bounds__(256) sn_finalize_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.x];
   sn_finalize_body(t.m, t.c, t.nblk, t.ws, t.u_new, t.save);
 }
 __global__ void __launch_bounds__(256) sn_pass3_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.y];
   if ((int)blockIdx.x < t.nblk) sn_pass3_body(t.W, t.m, t.c, t.w_bar, t.save, t.ws2, blockIdx.x);
 }
 __global__ void __launch_bounds__(256) sn_ta_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.x];
   sn_ta_body(t.nblk, t.ws2, t.save);
 }
 __global__ void __launch_bounds__(256) sn_bwd_dot_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.y];
   if ((int)blockIdx.x < t.nparts) sn_bwd_dot_body(t.W, t.G, (long)t.m * t.c, t.ws, blockIdx.x, t.nparts);
 }
 __global__ void __launch_bounds__(256) sn_bwd_dw_batched(const __grid_constant__ SnBatch b) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const SnItem& t = b.it[blockIdx.y];
   if ((int)blockIdx.x < t.g2) sn_bwd_dw_body(t.G, t.u, t.m, t.c, t.save, t.ws, t.nparts, t.dW, t.accumulate, blockIdx.x, t.g2);
 }
@@ -244,13 +256,13 @@ extern "C" int rcgan_sn_fwd(const float* W, const float* u, int m, int c, float*
   int nblk = sn_nblk(m);
   float* wsf = (float*)ws;
   float* ws2 = wsf + (size_t)nblk * (c + 1);
-  sn_pass1_kernel<<<nblk, 256, 0, st>>>(W, u, m, c, save + 5, wsf);
+  launch_pdl(sn_pass1_kernel, nblk, 256, 0, st, W, u, m, c, save + 5, wsf);
   RCGAN_LAUNCH_CHECK("sn_pass1");
-  sn_finalize_kernel<<<1, 256, 0, st>>>(m, c, nblk, wsf, u_new, save);
+  launch_pdl(sn_finalize_kernel, 1, 256, 0, st, m, c, nblk, wsf, u_new, save);
   RCGAN_LAUNCH_CHECK("sn_finalize");
-  sn_pass3_kernel<<<nblk, 256, 0, st>>>(W, m, c, w_bar, save, ws2);
+  launch_pdl(sn_pass3_kernel, nblk, 256, 0, st, W, m, c, w_bar, save, ws2);
   RCGAN_LAUNCH_CHECK("sn_pass3");
-  sn_ta_kernel<<<1, 256, 0, st>>>(nblk, ws2, save);
+  launch_pdl(sn_ta_kernel, 1, 256, 0, st, nblk, ws2, save);
   RCGAN_LAUNCH_CHECK("sn_ta");
   return 0;
 }
@@ -263,11 +275,11 @@ extern "C" int rcgan_sn_bwd(const float* W, const float* u, const float* G, int 
   long numel = (long)m * c;
   int nparts = (int)((numel + 255) / 256);
   if (nparts > 2 * RCGAN_NUM_SMS) nparts = 2 * RCGAN_NUM_SMS;
-  sn_bwd_dot_kernel<<<nparts, 256, 0, st>>>(W, G, numel, (float*)ws);
+  launch_pdl(sn_bwd_dot_kernel, nparts, 256, 0, st, W, G, numel, (float*)ws);
   RCGAN_LAUNCH_CHECK("sn_bwd_dot");
   int g2 = (int)((numel + 255) / 256);
   if (g2 > 4 * RCGAN_NUM_SMS) g2 = 4 * RCGAN_NUM_SMS;
-  sn_bwd_dw_kernel<<<g2, 256, 0, st>>>(G, u, m, c, save, (const float*)ws, nparts, dW, accumulate);
+  launch_pdl(sn_bwd_dw_kernel, g2, 256, 0, st, G, u, m, c, save, (const float*)ws, nparts, dW, accumulate);
   RCGAN_LAUNCH_CHECK("sn_bwd_dw");
   return 0;
 }
@@ -318,13 +330,13 @@ extern "C" int rcgan_sn_fwd_batched(int count, const float* const* W, const floa
       RCGAN_CHECK_ARG(b.it[k].u_new, "sn_fwd_batched: null u_new");
       wsf += sn_ws_floats(m[i0 + k], c[i0 + k]);
     }
-    sn_pass1_batched<<<dim3(mb, n), 256, 0, st>>>(b);
+    launch_pdl(sn_pass1_batched, dim3(mb, n), 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_pass1_batched");
-    sn_finalize_batched<<<n, 256, 0, st>>>(b);
+    launch_pdl(sn_finalize_batched, n, 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_finalize_batched");
-    sn_pass3_batched<<<dim3(mb, n), 256, 0, st>>>(b);
+    launch_pdl(sn_pass3_batched, dim3(mb, n), 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_pass3_batched");
-    sn_ta_batched<<<n, 256, 0, st>>>(b);
+    launch_pdl(sn_ta_batched, n, 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_ta_batched");
   }
   return 0;
@@ -346,9 +358,9 @@ extern "C" int rcgan_sn_bwd_batched(int count, const float* const* W, const floa
       RCGAN_CHECK_ARG(b.it[k].G && b.it[k].dW, "sn_bwd_batched: null gradient pointer");
       wsf += sn_ws_floats(m[i0 + k], c[i0 + k]);
     }
-    sn_bwd_dot_batched<<<dim3(mp, n), 256, 0, st>>>(b);
+    launch_pdl(sn_bwd_dot_batched, dim3(mp, n), 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_bwd_dot_batched");
-    sn_bwd_dw_batched<<<dim3(mg, n), 256, 0, st>>>(b);
+    launch_pdl(sn_bwd_dw_batched, dim3(mg, n), 256, 0, st, b);
     RCGAN_LAUNCH_CHECK("sn_bwd_dw_batched");
   }
   return 0;
