@@ -233,9 +233,8 @@ def kernel_roofline(model, rows, pk):
         ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * d.n * d.ho * d.wo * d.cout * d.kh * d.kw * d.cin
-    # a stride-s transposed conv is s*s launches of the kernel (one per output parity class): per-launch flops and time
-    # both divide by s*s, the ratio is unchanged
-    nl = d.stride * d.stride if form == 'dgrad' else 1
+    # a stride-2 transposed conv is ONE persistent launch whose tile list covers the 4 output parity classes
+    nl = 1
     ach = flops / (ms * 1e-3) / 1e12
     fam = sum(r['ms'] for r in rows if r['op'] in ('ConvOp', 'DeconvOp'))
     tot = sum(r['ms'] for r in rows)

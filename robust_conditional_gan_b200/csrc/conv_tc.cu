@@ -46,6 +46,15 @@ struct TcParams {
   int dbg;   // experiments only: 1 = skip MMA issue, 2 = skip TMA loads, 4 = skip A load, 8 = skip B load
 };
 
+// up to 4 problems that share operands, N and the epilogue but differ in geometry / taps (the 4 output parity classes of a
+// stride-2 transposed conv), scheduled as one persistent launch
+struct TcMulti {
+  TcParams p[4];
+  int tile_start[5];          // first (TM x bn) tile of each problem; tile_start[nprob] = total
+  int nprob;
+};
+struct TcMaps { CUtensorMap a[4]; };
+
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -483,9 +492,9 @@ struct PCfg {
 // the tile shapes are chosen for flops per staged byte: 128x256 (N >= 256) and 256x128 (N <= 128) both move 48 KB per
 // 4.2 MFLOP K block, against 32 KB per 2.1 MFLOP for 128x128.
 template <int BN, int MT, int ST, typename TO>
-__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ TcParams p,
+__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ TcMulti mp,
                                                                  const __grid_constant__ CUtensorMap wmap,
-                                                                 const __grid_constant__ CUtensorMap amap) {
+                                                                 const __grid_constant__ TcMaps amaps) {
   using C = PCfg<BN, MT, ST, TO>;
   constexpr int TM = MT * BM;
   extern __shared__ uint8_t smem_raw[];
@@ -501,10 +510,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bn = p.bn_eff;                              // N-tile width of this launch: multiple of 16, <= BN
-  const int n_tiles_n = (p.N + bn - 1) / bn;
-  const int n_tiles = ((p.M + TM - 1) / TM) * n_tiles_n;
-  const int nkb = p.ntaps * p.kb_per_tap;
+  const TcParams& p0 = mp.p[0];                          // N, operands, output, bias/act are common to all problems
+  const int bn = p0.bn_eff;                              // N-tile width of this launch: multiple of 16, <= BN
+  const int n_tiles_n = (p0.N + bn - 1) / bn;
+  const int n_tiles = mp.tile_start[mp.nprob];
+  // tile -> (problem q, tile inside q): the stride-2 transposed conv's 4 output parity classes are 4 problems of ONE launch
+  auto locate = [&](int tile, int& q) {
+    q = 0;
+    while (q + 1 < mp.nprob && tile >= mp.tile_start[q + 1]) q++;
+    return tile - mp.tile_start[q];
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; s++) {
@@ -521,7 +536,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     tmem_alloc(smem_u32(tmem_slot), 2 * MT * BN);
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+      for (int q = 0; q < mp.nprob; q++) asm volatile("prefetch.tensormap [%0];" ::"l"(&amaps.a[q]) : "memory");
     }
   }
   tc_fence_before();
@@ -535,7 +550,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     int ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
       const int a = ti & 1;
-      const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * bn;
+      int q;
+      const int lt = locate(tile, q);
+      const TcParams& p = mp.p[q];
+      const int m0 = (lt / n_tiles_n) * TM, n0 = (lt % n_tiles_n) * bn;
       mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -549,7 +567,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * TM, n0 = (tile % n_tiles_n) * bn;
+        int q;
+        const int lt = locate(tile, q);
+        const TcParams& p = mp.p[q];
+        const CUtensorMap* amap = &amaps.a[q];
+        const int nkb = p.ntaps * p.kb_per_tap;
+        const int m0 = (lt / n_tiles_n) * TM, n0 = (lt % n_tiles_n) * bn;
         int im_w[MT], im_h[MT], im_n[MT];
         int nsub = 0;
 #pragma unroll
@@ -570,7 +593,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < MT; j++)
               if (j < nsub)      // sub-tiles past the last row are not loaded (their accumulator rows are never stored)
-                tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)), &amap, smem_u32(&full[s]), k0, im_w[j],
+                tma_load_im2col_4d(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)), amap, smem_u32(&full[s]), k0, im_w[j],
                                    im_h[j], im_n[j], p.toffw[tap], p.toffh[tap]);
           }
           if (lb) tma_load_3d(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0, p.twi[tap]);
@@ -585,6 +608,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       int ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
         const int a = ti & 1;
+        int q;
+        locate(tile, q);
+        const TcParams& p = mp.p[q];
+        const int nkb = p.ntaps * p.kb_per_tap;
         mbar_wait(smem_u32(&tempty[a]), ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
@@ -1018,7 +1045,7 @@ bool make_amap(CUtensorMap* map, const TcParams& p, int channels, int nimg) {
 }
 
 template <int BN, int MT, int ST, typename TO>
-int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap, cudaStream_t st) {
+int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, cudaStream_t st) {
   using C = PCfg<BN, MT, ST, TO>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1026,9 +1053,13 @@ int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorM
     if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
-  const int n_tiles = ((p.M + MT * BM - 1) / (MT * BM)) * ((p.N + p.bn_eff - 1) / p.bn_eff);
+  const int bn = mp.p[0].bn_eff, n_tiles_n = (mp.p[0].N + bn - 1) / bn;
+  mp.tile_start[0] = 0;
+  for (int q = 0; q < mp.nprob; q++)
+    mp.tile_start[q + 1] = mp.tile_start[q] + ((mp.p[q].M + MT * BM - 1) / (MT * BM)) * n_tiles_n;
+  const int n_tiles = mp.tile_start[mp.nprob];
   const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
-  launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO>, grid, 192, C::SMEM, st, p, map, amap);
+  launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO>, grid, 192, C::SMEM, st, mp, map, amaps);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
   return 0;
 }
@@ -1037,6 +1068,23 @@ int launch_tc_persist(const TcParams& p, const CUtensorMap& map, const CUtensorM
 int persist_mode() {
   const char* e = getenv("RCGAN_TC_PERSIST");
   return e ? atoi(e) : 1;
+}
+
+// persistent launch of nprob problems (common N / operands); tile shape by output width and by how many tiles there are
+int run_tc_persist(TcMulti& mp, const TcMaps& amaps, const bf16* wbase, int kpad, int rows, int taps, cudaStream_t st) {
+  TcParams& p = mp.p[0];
+  // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs (and N <= 128) use (1|2) x (128 x <=128)
+  const bool wide = p.N > 128 && !p.out_f32;
+  const int cap = wide ? 256 : 128;
+  const int bn_eff = p.N >= cap ? cap : round_up(p.N, 16);   // e.g. N = 138 (g_h2's 128 + 10 label channels) -> one 144-wide tile
+  long tiles256 = 0;
+  for (int q = 0; q < mp.nprob; q++) { mp.p[q].bn_eff = bn_eff; tiles256 += (long)((mp.p[q].M + 255) / 256) * ((p.N + bn_eff - 1) / bn_eff); }
+  CUtensorMap map;
+  if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn_eff)) return e;
+  if (wide) return launch_tc_persist<256, 1, 3, bf16>(mp, map, amaps, st);
+  if (tiles256 >= 2 * RCGAN_NUM_SMS)     // enough work for 256-row tiles (one B tile feeds two MMAs)
+    return p.out_f32 ? launch_tc_persist<128, 2, 3, float>(mp, map, amaps, st) : launch_tc_persist<128, 2, 3, bf16>(mp, map, amaps, st);
+  return p.out_f32 ? launch_tc_persist<128, 1, 4, float>(mp, map, amaps, st) : launch_tc_persist<128, 1, 5, bf16>(mp, map, amaps, st);
 }
 
 int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int channels, int nimg, cudaStream_t st) {
@@ -1050,13 +1098,10 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
                                                    : (long)((p.M + 255) / 256) * ((p.N + 127) / 128);
   const bool persist = im2col && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
   if (persist) {
-    // fp32 staging of a 128x256 tile does not fit next to the ring: fp32 outputs (and N <= 128) use 2 x (128 x <=128)
-    const bool wide = p.N > 128 && !p.out_f32;
-    const int cap = wide ? 256 : 128;
-    p.bn_eff = p.N >= cap ? cap : round_up(p.N, 16);      // e.g. N = 138 (g_h2's 128 + 10 label channels) -> one 144-wide tile
-    if (int e = make_wmap(&map, wbase, kpad, rows, taps, p.bn_eff)) return e;
-    if (wide) return launch_tc_persist<256, 1, 3, bf16>(p, map, amap, st);
-    return p.out_f32 ? launch_tc_persist<128, 2, 3, float>(p, map, amap, st) : launch_tc_persist<128, 2, 3, bf16>(p, map, amap, st);
+    TcMulti mp;
+    TcMaps amaps;
+    mp.p[0] = p; mp.nprob = 1; amaps.a[0] = amap;
+    return run_tc_persist(mp, amaps, wbase, kpad, rows, taps, st);
   }
   const int bn = p.N <= 64 ? 64 : 128;
   if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn)) return e;
@@ -1121,6 +1166,10 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
   PackGeo g = pack_geo(d);
   const bf16* wD = reinterpret_cast<const bf16*>(wpack) + g.offD;
   const int s = d->stride;
+  TcMulti mp;
+  TcMaps amaps;
+  mp.nprob = 0;
+  bool all_im2col = s == 2 && persist_mode() != 0;     // the 4 parity classes as ONE persistent launch when all are encodable
   for (int py = 0; py < s; py++)
     for (int px = 0; px < s; px++) {
       TcParams p;
@@ -1147,8 +1196,22 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
       p.oy_mul = s; p.oy_add = py; p.ox_mul = s; p.ox_add = px; p.N = d->cin;
       p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate;
       if (nt == 0) { rcgan_set_error("conv_tc dgrad: parity class without taps"); return RCGAN_EUNSUPPORTED; }
-      if (int e = run_tc(p, wD, g.kpadD, d->cin, g.taps, d->cout, d->n, st)) return e;
+      if (s == 2) {
+        { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+        all_im2col = all_im2col && mp.nprob < 4 && make_amap(&amaps.a[mp.nprob], p, d->cout, d->n);
+        if (mp.nprob < 4) mp.p[mp.nprob++] = p;
+      } else {
+        if (int e = run_tc(p, wD, g.kpadD, d->cin, g.taps, d->cout, d->n, st)) return e;
+      }
     }
+  if (s == 2) {
+    if (all_im2col && mp.nprob > 0) {
+      if (int e = run_tc_persist(mp, amaps, wD, g.kpadD, d->cin, g.taps, st)) return e;
+    } else {
+      for (int q = 0; q < mp.nprob; q++)
+        if (int e = run_tc(mp.p[q], wD, g.kpadD, d->cin, g.taps, d->cout, d->n, st)) return e;
+    }
+  }
   *handled = 1;
   return 0;
 }
