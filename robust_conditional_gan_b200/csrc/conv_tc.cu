@@ -491,7 +491,7 @@ struct PCfg {
 // Tile = (MT x 128) rows x BN columns.  The operand stream from L2 is what bounds this kernel (~50 B/clk/SM measured), so
 // the tile shapes are chosen for flops per staged byte: 128x256 (N >= 256) and 256x128 (N <= 128) both move 48 KB per
 // 4.2 MFLOP K block, against 32 KB per 2.1 MFLOP for 128x128.
-template <int BN, int MT, int ST, typename TO>
+template <int BN, int MT, int ST, typename TO, bool MULTI>
 __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ TcMulti mp,
                                                                  const __grid_constant__ CUtensorMap wmap,
                                                                  const __grid_constant__ TcMaps amaps) {
@@ -515,8 +515,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   const int n_tiles_n = (p0.N + bn - 1) / bn;
   const int n_tiles = mp.tile_start[mp.nprob];
   // tile -> (problem q, tile inside q): the stride-2 transposed conv's 4 output parity classes are 4 problems of ONE launch
+  // (MULTI = false: one problem, q is the compile-time constant 0 and every parameter access keeps its immediate offset)
   auto locate = [&](int tile, int& q) {
     q = 0;
+    if (!MULTI) return tile;
     while (q + 1 < mp.nprob && tile >= mp.tile_start[q + 1]) q++;
     return tile - mp.tile_start[q];
   };
@@ -1049,7 +1051,9 @@ int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, 
   using C = PCfg<BN, MT, ST, TO>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, MT, ST, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, MT, ST, TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, MT, ST, TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) { rcgan_set_error("conv_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
     attr_done = true;
   }
@@ -1059,7 +1063,8 @@ int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, 
     mp.tile_start[q + 1] = mp.tile_start[q] + ((mp.p[q].M + MT * BM - 1) / (MT * BM)) * n_tiles_n;
   const int n_tiles = mp.tile_start[mp.nprob];
   const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
-  launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO>, grid, 192, C::SMEM, st, mp, map, amaps);
+  if (mp.nprob > 1) launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, true>, grid, 192, C::SMEM, st, mp, map, amaps);
+  else launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, false>, grid, 192, C::SMEM, st, mp, map, amaps);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
   return 0;
 }
