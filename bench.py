@@ -249,6 +249,31 @@ def kernel_roofline(model, rows, pk):
             'launch_ms': ms / nl, 'flops_per_launch': flops / nl, 'launches_per_call': nl, 'conv_family_share_of_step': fam / tot}
 
 
+def sampler_bench(n=70000):
+    """Label-noise sampler (mnist/model.py:795-834) on the full 70 000-sample MNIST label set: CUDA kernel (device time of
+    the sampling launch, labels resident) against the reference's literal numpy loop (oracle port) on a 7 000-sample slice
+    scaled to 70 000; outputs compared element by element (bit-exact)."""
+    import numpy as np
+    import torch
+    from oracle import sampler as OS
+    from robust_conditional_gan_b200.sampler import LabelNoiseSampler, one_coin_confusion
+    C = one_coin_confusion(0.5)
+    y = np.random.RandomState(1).randint(10, size=n)
+    smp = LabelNoiseSampler('cuda')
+    smp.load_mnist_labels(y, C)                     # warm-up (table upload, allocations)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = smp.load_mnist_labels(y, C); e1.record(); e1.synchronize()
+    gpu_ms = e0.elapsed_time(e1)
+    m = n // 10
+    t = time.perf_counter(); ref = OS.mnist_labels_numpy(y[:m], C); cpu_s = (time.perf_counter() - t) * (n / m)
+    small = smp.load_mnist_labels(y[:m], C)
+    exact = bool((small['real'] == ref['y_real'].argmax(1)).all() and (small['fake'] == ref['y_fake'].argmax(1)).all()
+                 and (small['gen'] == ref['y_gen'].argmax(1)).all() and (small['perm'] == ref['perm']).all())
+    return {'samples': n, 'gpu_ms_incl_shuffles_and_readback': gpu_ms, 'cpu_numpy_loop_s_scaled_from_%d' % m: cpu_s,
+            'bit_exact_vs_numpy': exact}
+
+
 class CifarBench:
     """adapter giving RCGANCifar the same (feed / train_iteration / programs) surface bench.py drives for DCGAN"""
 
@@ -397,6 +422,8 @@ def run_ours(args, wl):
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
             json.dump(rows, f, indent=1)
+        if wl.get('kind') != 'cifar' and not args.no_cpu_baseline:
+            result['sampler'] = sampler_bench()
         # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
         if not args.no_cpu_baseline:
             cores = os.cpu_count()

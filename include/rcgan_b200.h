@@ -213,7 +213,7 @@ int rcgan_zero(void* ptr, size_t bytes, void* stream);
  * `table` (device, doubles) comes from rcgan_sampler_table_host(): per confusion-matrix row and
  * class index the binomial-inversion constants, computed on the HOST with libm exactly as numpy does. */
 #define RCGAN_MT_STATE_WORDS 625
-#define RCGAN_SAMPLER_TABLE_DOUBLES(k) ((k) * ((k) - 1) * 4)
+#define RCGAN_SAMPLER_TABLE_DOUBLES(k) ((k) * ((k) - 1) * 8)   /* (mode, qn, px1, p, T, T_safe, 0, 0) per (row, class) */
 void rcgan_sampler_table_host(const double* C, int k, double* table);
 int rcgan_mt_seed(uint32_t* state, uint32_t seed, void* stream);
 /* Fisher-Yates permutation exactly as np.random.shuffle draws it; perm[n] int32 */

@@ -41,7 +41,7 @@ class LabelNoiseSampler:
         key = C.tobytes()
         if key not in self._tables:
             k = C.shape[0]
-            tab = np.zeros(k * (k - 1) * 4, dtype=np.float64)
+            tab = np.zeros(k * (k - 1) * 8, dtype=np.float64)      # RCGAN_SAMPLER_TABLE_DOUBLES(k)
             _C.load().rcgan_sampler_table_host(C.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), k,
                                                tab.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
             self._tables[key] = torch.from_numpy(tab).to(self.device)
@@ -60,9 +60,8 @@ class LabelNoiseSampler:
         self.seed(seed)
         if shuffle:
             perm = self.shuffle_perm(n)
-            self.seed(seed)
-            perm2 = self.shuffle_perm(n)     # the second shuffle (of y) replays the same stream
-            yd = torch.as_tensor(np.asarray(y), dtype=torch.int32, device=self.device)[perm2.long()].contiguous()
+            # the reference re-seeds and shuffles y: the same stream, hence the same permutation and the same final state
+            yd = torch.as_tensor(np.asarray(y), dtype=torch.int32, device=self.device)[perm.long()].contiguous()
         else:
             perm = torch.arange(n, dtype=torch.int32, device=self.device)
             yd = torch.as_tensor(np.asarray(y), dtype=torch.int32, device=self.device)

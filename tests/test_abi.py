@@ -40,15 +40,16 @@ def test_sampler_table_host_matches_numpy_thresholds(lib):
     import math
     from oracle import sampler as S
     C = S.one_coin_confusion(0.3)
-    tab = np.zeros(10 * 9 * 4)
+    tab = np.zeros(10 * 9 * 8)
     lib.rcgan_sampler_table_host(np.ascontiguousarray(C).ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 10,
                                  tab.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
-    tab = tab.reshape(10, 9, 4)
+    tab = tab.reshape(10, 9, 8)
     Sum = 1.0
     for j in range(9):
         p = C[0, j] / Sum
         pp = p if p <= 0.5 else 1 - p
         assert tab[0, j, 1] == math.exp(math.log(1 - pp)) and tab[0, j, 3] == p
+        assert tab[0, j, 4] == math.floor(math.ldexp(tab[0, j, 1], 53)) and tab[0, j, 5] >= tab[0, j, 4]
         Sum -= C[0, j]
 
 

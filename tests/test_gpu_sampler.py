@@ -44,3 +44,21 @@ def test_renoise_and_cifar(lib):
     lab, rnd, biased = LabelNoiseSampler('cuda').cifar_labels(gold['cifar_in'], one_coin_confusion(0.5), seed=547)
     assert np.array_equal(lab, gold['cifar_labels']) and np.array_equal(rnd, gold['cifar_random'])
     assert np.array_equal(biased, gold['cifar_biased'])
+
+
+def test_integer_threshold_path_equals_literal_double_path(lib, monkeypatch):
+    """The sampler decides binomial(1,p) on 53-bit integers against floor(qn*2^53) and falls back to numpy's literal
+    double-precision inversion loop only next to U = 1.  With RCGAN_SAMPLER_LITERAL=1 every success takes the literal
+    loop: both must reproduce numpy bit for bit (golden vectors), on the one-coin and class-dependent matrices."""
+    gold = np.load(os.path.join(GOLD, 'sampler_mnist_a0.5_rm0.npz'))
+    y = np.random.RandomState(5).randint(10, size=20000)
+    outs = []
+    for literal in ('0', '1'):
+        monkeypatch.setenv('RCGAN_SAMPLER_LITERAL', literal)
+        s = LabelNoiseSampler('cuda')                # fresh table cache: the env var is read when the table is built
+        out = s.load_mnist_labels(gold['y_in'], one_coin_confusion(0.5), seed=547)
+        for k in ('perm', 'y', 'real', 'gen', 'fake'):
+            assert np.array_equal(out[k], gold[k]), (literal, k)
+        outs.append(LabelNoiseSampler('cuda').load_mnist_labels(y, class_dependent_confusion(0.4), seed=3))
+    for k in ('real', 'gen', 'fake'):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
