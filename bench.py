@@ -26,10 +26,17 @@ WORKLOADS = {
     'cifar_rcganu_b256': dict(kind='cifar', batch=256, flags=dict(algorithm='rcgan-u', perm_classifier=True, confuse_init=True)),
     'mnist_rcganu_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=True)),
     'mnist_rcgan_b64': dict(batch=64, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False)),
+    # DCGAN.recover_labels (model.py:494-640), recover_batch_size 500 -> 5000 generated images per step;
+    # a step = one gradient-descent step on (z_recover, y_logit_recover); value counts the R real images per step
+    'mnist_recover_r500': dict(kind='recover', batch=500, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=True)),
     'mnist_rcgany_b1024': dict(batch=1024, flags=dict(algorithm='rcgan', disc_type='projection', estimate_confuse=False,
                                                       concat_y=True, concat_y_layers=[1])),
 }
 METRIC = 'RCGAN G+D train images/sec'
+
+
+def metric_of(wl):
+    return 'recover_labels real images x steps/sec' if wl.get('kind') == 'recover' else METRIC
 
 
 class ClockSampler:
@@ -130,12 +137,37 @@ def oracle_iteration_timer_cifar(n, flags, threads):
     return step
 
 
+def oracle_recover_timer(R, flags, threads):
+    """CPU port of one recover_labels step (oracle/mnist.py recover_step)."""
+    import torch
+    from oracle import mnist as OM
+    torch.set_num_threads(threads)
+    cfg = OM.default_config(batch_size=64, alpha=0.5, perm_regularizer=True, **flags)
+    P = OM.init_params(cfg, 0, torch.float32)
+    g = torch.Generator().manual_seed(0)
+    z = torch.rand(R * 10, 100, generator=g) - 0.5
+    yl = torch.randn(R, 10, generator=g)
+    actual = torch.rand(R, 28, 28, 1, generator=g)
+    st = {'z': z, 'yl': yl}
+
+    def step():
+        t = time.perf_counter()
+        st['z'], st['yl'], _, _ = OM.recover_step(P, st['z'], st['yl'], actual, cfg, lr=500.0)
+        return time.perf_counter() - t
+    return step
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count()
-    if wl.get('kind') == 'cifar':
+    if wl.get('kind') == 'recover':
+        B = 50
+        step = oracle_recover_timer(B, wl['flags'], cores)
+        per_step = B
+        sample = 'oracle recover_step at recover_batch_size %d (%d generated images), fp32, %d threads' % (B, 10 * B, cores)
+    elif wl.get('kind') == 'cifar':
         B = 8                                # bounded sample: tower batch 8 (the workload's 256 would take minutes per step)
         step = oracle_iteration_timer_cifar(B, wl['flags'], cores)
         per_step = 5 * B
@@ -151,7 +183,7 @@ def run_reference(args, wl):
     t = sum(ts) / len(ts)
     v = per_step / t
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'impl': 'reference', 'metric': metric_of(wl), 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_step': B},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -165,7 +197,7 @@ def op_profile(model, reps=5):
     from robust_conditional_gan_b200 import nnops
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     rows = []
-    for prog in (model.d_prog, model.g_prog):
+    for prog in ((model.d_prog,) if model.d_prog is model.g_prog else (model.d_prog, model.g_prog)):
         prog.run_forward(); prog.run_backward()
         for op in prog.ops:
             for direction in ('forward', 'backward'):
@@ -201,7 +233,7 @@ def kernel_roofline(model, rows, pk):
     from robust_conditional_gan_b200.nnops import dp, pp
     lib = _C.load()
     cands = []
-    for prog in (model.d_prog, model.g_prog):
+    for prog in ((model.d_prog,) if model.d_prog is model.g_prog else (model.d_prog, model.g_prog)):
         for op in prog.ops:
             if isinstance(op, nnops.ConvOp) and op.patch is None and op.pack is not None and lib.rcgan_conv_uses_tensor_cores(op.desc, 0):
                 cands.append((prog, op, 'fprop'))
@@ -310,6 +342,36 @@ class CifarBench:
         return self.m.train_iteration(None, None, fetch=False)
 
 
+class RecoverBench:
+    """DCGAN.recover_labels steps: R real images against R*10 gen_sampler images, SGD on z_recover / y_logit_recover."""
+
+    def __init__(self, R, flags_kw, precision, world, rank):
+        import torch
+        from robust_conditional_gan_b200.model import DCGAN, default_flags
+        flags = default_flags(batch_size=64, alpha=0.5, **flags_kw)
+        self.m = DCGAN(batch_size=64, algorithm=flags.algorithm, estimate_confuse=flags.estimate_confuse, perm_regularizer=True,
+                       alpha=0.5, disc_type=flags.disc_type, config=flags, precision=precision, world_size=1, rank=0, seed=0)
+        self.m.build_recover(R, seed=rank)
+        self.d_prog = self.g_prog = self.m.r_prog
+        g = torch.Generator().manual_seed(rank)
+        self.actual = torch.rand(R, 28, 28, 1, generator=g).contiguous().pin_memory()
+        self.images_per_step = R
+        self.h2d = self.actual.numel() * 4
+        self.d2h = 4
+
+    def set_graph(self, on):
+        self.m.use_cuda_graph = on
+
+    def resident(self):
+        self.m.recover_step(self.actual, 500.0, fetch=False)
+
+    def step(self, e2e):
+        if e2e:
+            return {'mse_loss': self.m.recover_step(self.actual, 500.0, fetch=True)}
+        self.m.recover_step(None, 500.0, fetch=False)
+        return None
+
+
 class MnistBench:
     def __init__(self, B, flags_kw, precision, world, rank):
         from robust_conditional_gan_b200.model import DCGAN, default_flags
@@ -347,7 +409,7 @@ def run_ours(args, wl):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     B = wl['batch']
     lib = _C.load()
-    bench = (CifarBench if wl.get('kind') == 'cifar' else MnistBench)(B, wl['flags'], args.precision, world, rank)
+    bench = {'cifar': CifarBench, 'recover': RecoverBench}.get(wl.get('kind'), MnistBench)(B, wl['flags'], args.precision, world, rank)
     model = bench
     # launches per iteration: count once with eager (uncaptured) launches
     bench.set_graph(False)
@@ -396,11 +458,13 @@ def run_ours(args, wl):
     ms_step = ms / args.steps
     value = world * bench.images_per_step / (ms_step / 1e3)
     result = {
-        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'metric': metric_of(wl), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': world * B,
-                   'step': '1 G step (batch 2B) + 5 D steps (B real + B fake)' if wl.get('kind') == 'cifar' else '1 D step + 2 G(+C) steps',
+                   'step': {'cifar': '1 G step (batch 2B) + 5 D steps (B real + B fake)',
+                            'recover': '1 recover_labels step: gen_sampler on 10 B images, mse, SGD on z_recover / y_logit_recover'
+                            }.get(wl.get('kind'), '1 D step + 2 G(+C) steps'),
                    'parallelism': 'dp%d' % world,
                    'l2': 'no explicit flush: one iteration touches ~1.5 GB of activations/gradients, >> 126 MB L2'},
         'clocks': clk,
@@ -422,12 +486,18 @@ def run_ours(args, wl):
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
             json.dump(rows, f, indent=1)
-        if wl.get('kind') != 'cifar' and not args.no_cpu_baseline:
+        if wl.get('kind') is None and not args.no_cpu_baseline:
             result['sampler'] = sampler_bench()
         # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
         if not args.no_cpu_baseline:
             cores = os.cpu_count()
-            if wl.get('kind') == 'cifar':
+            if wl.get('kind') == 'recover':
+                step = oracle_recover_timer(50, wl['flags'], cores)
+                step()
+                t = step()
+                result['cpu_baseline'] = {'value': 50 / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                          'sample': '1 warm-up + 1 timed oracle recover_step at recover_batch_size 50 (500 generated images), fp32'}
+            elif wl.get('kind') == 'cifar':
                 nb = 8
                 step = oracle_iteration_timer_cifar(nb, wl['flags'], cores)
                 step()

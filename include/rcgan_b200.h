@@ -204,6 +204,24 @@ int rcgan_gather_rows_bwd(const float* dwgt, const int* y, float* dC, int B, int
 int rcgan_adam_tf(float* p, const float* g, float* m, float* v, long numel, float lr_t, const float* lr_t_dev, float b1,
                   float b2, float eps, float grad_scale, const long* clip_lo, const long* clip_hi, int n_clip,
                   void* stream);
+/* ---------------------------------------------------------------- label recovery
+ * DCGAN.recover_labels, mnist/model.py:494-640: gradient descent on z_recover [R*k, z_dim] and y_logit_recover [R, k] through
+ * gen_sampler (the generator with batch norm in INFERENCE mode) against R real images.
+ *
+ * rcgan_bn_infer_bwd: backward of y = act(scale*(x - moving_mean)*rsqrt(moving_var + eps) + offset) with respect to x only
+ *   (model.py:733-757 runs the norms with train=False): dx (=|+=) dy * act'(y) * scale[label] * save[c + ch].
+ *   `save` is what rcgan_bn_fwd(train = 0) wrote; ws: 2*c floats.
+ * rcgan_recover_mse (model.py:538-541): sq[r,j] = mean_p (actual[r,p] - sample[r*k + j, p])^2,
+ *   loss_acc[0] += (1/R) sum_r sum_j sq[r,j] * y_rec[r,j];   dsample (=) (2/npix) (sample - actual) y_rec[r,j] / R;
+ *   dyrec[r,j] (=) sq[r,j] / R.   fp32; any output may be NULL.
+ * rcgan_sgd: tf.train.GradientDescentOptimizer (model.py:612-617): p -= lr * grad_scale * g. */
+int rcgan_bn_infer_bwd(const void* dy, const void* y, void* dx, int samples, int hw, int c, int dtype, const float* scale,
+                       const int* labels, const float* save, int act, float leak, int accumulate_dx, void* ws, size_t ws_bytes,
+                       void* stream);
+int rcgan_recover_mse(const float* sample, const float* actual, const float* y_rec, int R, int k, int npix, float* loss_acc,
+                      float* sq, float* dsample, float* dyrec, void* stream);
+int rcgan_sgd(float* p, const float* g, long numel, float lr, float grad_scale, void* stream);
+
 /* cudaMemsetAsync(ptr, 0, bytes) on the caller's stream (zeroing gradient arenas / loss slots inside a captured step) */
 int rcgan_zero(void* ptr, size_t bytes, void* stream);
 

@@ -327,3 +327,34 @@ def synthetic_batch(B, seed=0, dtype=torch.float64, C=None, cfg=None):
     t = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype)
     return dict(x=t(x), z=t(z), y_real=t(lab['y_real']), y_gen=t(lab['y_gen']), y_fake=t(lab['y_fake']),
                 y_real_weights=t(lab['y_real_weights']))
+
+
+# ----------------------------------------------------------------------------- label recovery
+def recover_loss(P, z_recover, y_logit_recover, sample_actual, cfg):
+    """mnist/model.py:516-541.  z_recover [R*k, z_dim], y_logit_recover [R, k], sample_actual [R, H, W, c].
+    gen_sampler (:733-757: batch norm with the MOVING statistics) on (z_recover, tile(eye(k), R)); returns
+    (mse_loss, y_recover [R,k], sq_sum [R,k])."""
+    R, k = y_logit_recover.shape
+    y_recover = torch.softmax(1 * y_logit_recover, dim=-1)                      # bignum = 1 (:516,520)
+    hard_y = torch.eye(k, dtype=z_recover.dtype).repeat(R, 1)                   # tf.tile(eye, [R, 1]) (:524-525)
+    samples = generator(P, z_recover, hard_y, cfg, train=False)                 # [R*k, H, W, c]
+    samples = samples.reshape((R, k) + tuple(sample_actual.shape[1:]))          # (:532-535)
+    sq_sum = ((sample_actual.unsqueeze(1) - samples) ** 2).mean(-1).mean(-1).mean(-1)   # (:537-540)
+    mse_loss = (sq_sum * y_recover).sum(-1).mean()                              # (:541)
+    return mse_loss, y_recover, sq_sum
+
+
+def recover_step(P, z_recover, y_logit_recover, sample_actual, cfg, lr=500.0):
+    """One GradientDescentOptimizer(lr).minimize(mse_loss, var_list=[z_recover, y_logit_recover]) step (:612-617, 626-629).
+    Returns (new z_recover, new y_logit_recover, mse_loss before the update, (dz, dlogit))."""
+    z = z_recover.detach().clone().requires_grad_(True)
+    yl = y_logit_recover.detach().clone().requires_grad_(True)
+    loss, _, _ = recover_loss({n: v.detach() for n, v in P.items()}, z, yl, sample_actual, cfg)
+    dz, dyl = torch.autograd.grad(loss, [z, yl])
+    return (z - lr * dz).detach(), (yl - lr * dyl).detach(), loss.detach(), (dz, dyl)
+
+
+def zero_one_loss(y_actual, y_recover):
+    """tf.losses.cosine_distance(y_actual, one_hot(argmax y_recover), dim=-1) (:545-546) = mean(1 - <a, b>)."""
+    onehot = torch.eye(y_recover.shape[1], dtype=y_recover.dtype)[y_recover.argmax(-1)]
+    return (1 - (y_actual * onehot).sum(-1)).mean()

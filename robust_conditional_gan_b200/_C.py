@@ -63,6 +63,9 @@ _SIGS = {
                              P, P, c_size_t, P]),
     'rcgan_bn_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_int,
                              c_int, P, c_size_t, P]),
+    'rcgan_bn_infer_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
+    'rcgan_recover_mse': (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
+    'rcgan_sgd': (c_int, [P, P, c_long, c_float, c_float, P]),
     'rcgan_sn_save_floats': (c_size_t, [c_int, c_int]),
     'rcgan_sn_workspace': (c_size_t, [c_int, c_int]),
     'rcgan_sn_fwd': (c_int, [P, P, c_int, c_int, P, P, P, P, c_size_t, P]),

@@ -263,3 +263,40 @@ extern "C" int rcgan_gather_rows_bwd(const float* dwgt, const int* y, float* dC,
   RCGAN_LAUNCH_CHECK("gather_rows_bwd");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ label recovery
+namespace {
+// one block per (r, j): sq = mean_p (actual[r] - sample[r*k+j])^2, then the sample gradient in a second sweep (L1/L2 hits)
+__global__ void __launch_bounds__(128) recover_mse_kernel(const float* __restrict__ sample, const float* __restrict__ actual,
+                                                          const float* __restrict__ y_rec, int R, int k, int npix,
+                                                          float* __restrict__ loss_acc, float* __restrict__ sq,
+                                                          float* __restrict__ dsample, float* __restrict__ dyrec) {
+  pdl_sync();
+  __shared__ float red[33];
+  const int rj = blockIdx.x, r = rj / k;
+  const float* s = sample + (size_t)rj * npix;
+  const float* a = actual + (size_t)r * npix;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < npix; p += 128) { const float d = a[p] - s[p]; acc = fmaf(d, d, acc); }
+  acc = block_sum(acc, red);
+  const float m = acc / (float)npix, w = y_rec[rj], invR = 1.f / (float)R;
+  if (threadIdx.x == 0) {
+    if (sq) sq[rj] = m;
+    if (dyrec) dyrec[rj] = m * invR;
+    if (loss_acc) atomicAdd(loss_acc, m * w * invR);
+  }
+  if (dsample) {
+    const float g = 2.f / (float)npix * w * invR;
+    float* ds = dsample + (size_t)rj * npix;
+    for (int p = threadIdx.x; p < npix; p += 128) ds[p] = g * (s[p] - a[p]);
+  }
+}
+}  // namespace
+
+extern "C" int rcgan_recover_mse(const float* sample, const float* actual, const float* y_rec, int R, int k, int npix,
+                                 float* loss_acc, float* sq, float* dsample, float* dyrec, void* stream) {
+  RCGAN_CHECK_ARG(sample && actual && y_rec && R > 0 && k > 0 && npix > 0, "recover_mse: bad args");
+  launch_pdl(recover_mse_kernel, R * k, 128, 0, as_stream(stream), sample, actual, y_rec, R, k, npix, loss_acc, sq, dsample, dyrec);
+  RCGAN_LAUNCH_CHECK("recover_mse");
+  return 0;
+}

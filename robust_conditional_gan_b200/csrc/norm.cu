@@ -484,3 +484,23 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
   RCGAN_LAUNCH_CHECK("bn_bwd_dx");
   return 0;
 }
+
+extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, void* dx, int samples, int hw, int c, int dtype, const float* scale,
+                                  const int* labels, const float* save, int act, float leak, int accumulate_dx, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "bn_infer_bwd: bad shape");
+  RCGAN_CHECK_ARG(dtype == RCGAN_F32 || dtype == RCGAN_BF16, "bn_infer_bwd: bad dtype");
+  RCGAN_CHECK_ARG(dy && dx && scale && save && (act == RCGAN_ACT_NONE || y), "bn_infer_bwd: null pointer");
+  RCGAN_CHECK_ARG(ws && ws_bytes >= (size_t)2 * c * sizeof(float), "bn_infer_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  // the statistics are constants, so the two batch-projection terms vanish: the training dx kernel with A = B = 0
+  // (c2 = c3 = 0; its x operand is only multiplied by 0 -- dy stands in for it)
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)2 * c * sizeof(float), st);
+  if (e != cudaSuccess) { rcgan_set_error("bn_infer_bwd: memset failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+  const Geo ga = make_geo(samples, hw, c, labels != nullptr, dtype == RCGAN_BF16 ? 8 : 4);
+  BN_DISPATCH(dtype, dtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy,
+                                             (const TX*)dy, (const TY*)y, (TY*)dx, ga, scale, labels, save, (const float*)ws, act,
+                                             leak, accumulate_dx));
+  RCGAN_LAUNCH_CHECK("bn_infer_bwd");
+  return 0;
+}

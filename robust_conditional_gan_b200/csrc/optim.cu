@@ -45,3 +45,19 @@ extern "C" int rcgan_zero(void* ptr, size_t bytes, void* stream) {
   if (e != cudaSuccess) { rcgan_set_error("zero: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
   return 0;
 }
+
+namespace {
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long numel, float step) {
+  pdl_sync();
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < numel; i += (long)gridDim.x * 256) p[i] -= step * g[i];
+}
+}  // namespace
+
+extern "C" int rcgan_sgd(float* p, const float* g, long numel, float lr, float grad_scale, void* stream) {
+  RCGAN_CHECK_ARG(p && g && numel > 0, "sgd: bad args");
+  long grid = (numel + 255) / 256;
+  if (grid > 8L * RCGAN_NUM_SMS) grid = 8L * RCGAN_NUM_SMS;
+  launch_pdl(sgd_kernel, (int)grid, 256, 0, as_stream(stream), p, g, numel, lr * grad_scale);
+  RCGAN_LAUNCH_CHECK("sgd");
+  return 0;
+}

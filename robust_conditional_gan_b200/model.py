@@ -22,7 +22,7 @@ import torch
 
 from . import _C, ops, scope as S
 from .graph import Program, VariableStore, tf_adam_lr
-from .nnops import (CastOp, ChannelLossOp, ConvOp, LogitLossOp, MeanHWOp, SigmoidCEOp, SoftmaxRowsOp, adam_step)
+from .nnops import (CastOp, ChannelLossOp, ConvOp, LogitLossOp, MeanHWOp, RecoverMSEOp, SigmoidCEOp, SoftmaxRowsOp, adam_step)
 from .sampler import LabelNoiseSampler, class_dependent_confusion, one_coin_confusion
 
 LOSS_MODES = {'hinge': (_C.HINGE_D_REAL, _C.HINGE_D_FAKE, _C.HINGE_G), 'ce': (_C.CE_D_REAL, _C.CE_D_FAKE, _C.CE_G)}
@@ -376,14 +376,20 @@ class DCGAN(object):
             self._graphs[name] = g
         g.replay()
 
+    def _all_vars(self):
+        v = dict(self.store.vars)
+        if getattr(self, 'r_store', None) is not None:
+            v.update(self.r_store.vars)
+        return v
+
     def _snapshot(self):
-        snap = {n: v.data.clone() for n, v in self.store.vars.items()}
+        snap = {n: v.data.clone() for n, v in self._all_vars().items()}
         for k, g in self.groups.items():
             snap['__m_' + k], snap['__v_' + k] = g.m.clone(), g.v.clone()
         return snap
 
     def _restore(self, snap):
-        for n, v in self.store.vars.items():
+        for n, v in self._all_vars().items():
             v.data.copy_(snap[n])
         for k, g in self.groups.items():
             g.m.copy_(snap['__m_' + k]); g.v.copy_(snap['__v_' + k])
@@ -460,6 +466,78 @@ class DCGAN(object):
         self.s_prog.inputs['y_gen'].data.copy_(torch.as_tensor(y_gen, dtype=torch.float32).reshape(-1), non_blocking=True)
         self.s_prog.run_forward()
         return self.sampler.torch().clone()
+
+    # ------------------------------------------------------------------ label recovery (mnist/model.py:494-640)
+    def build_recover(self, recover_batch_size, seed=0):
+        """Graph of DCGAN.recover_labels for R = recover_batch_size real images: variables z_recover [R*y_dim, z_dim] and
+        y_logit_recover [R, y_dim] (tf.get_variable default = Glorot uniform), gen_sampler (batch norm in inference mode) on
+        the R*y_dim (z, one-hot) pairs, mse_loss (:538-541), plain gradient descent on the two variables (:612-617)."""
+        R, k, dev = int(recover_batch_size), self.y_dim, self.device
+        self.recover_R = R
+        self.r_store = rs = VariableStore(dev, lambda name: 'r')
+        gen = torch.Generator().manual_seed(seed)
+
+        def glorot(shape):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            return (torch.rand(tuple(shape), generator=gen, dtype=torch.float32) * 2 - 1) * lim
+        self.y_logit_recover = rs.get('y_logit_recover', (R, k), glorot)
+        self.z_recover = rs.get('z_recover', (R * k, self.z_dim), glorot)
+        rs.finalize()
+        self.r_prog = rp = Program('recover', dev, self.act_dtype)
+        saved_B = self.batch_size
+        self.batch_size = R * k                       # the reference re-purposes self.batch_size the same way (:526)
+        try:
+            with rp:
+                actual = rp.input('sample_actual', [R, self.output_height * self.output_width * self.c_dim])
+                hard_y = rp.input('hard_y_recover', [R * k, k])
+                hard_y.data.copy_(torch.eye(k, device=dev).repeat(R, 1).reshape(-1))
+                self.y_recover = SoftmaxRowsOp(self.y_logit_recover).y
+                img = self.gen_sampler(CastOp(self.z_recover, self.act_dtype).y, hard_y)
+                img32 = CastOp(img, _C.F32).y
+                self.sample_recover_each_y = img32.view([R * k, self.output_height * self.output_width * self.c_dim])
+                self.recover_loss_op = RecoverMSEOp(self.sample_recover_each_y, actual, self.y_recover, 'mse_loss')
+        finally:
+            self.batch_size = saved_B
+        rp.finalize([self.z_recover, self.y_logit_recover])
+        self._r_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        return rp
+
+    def _r_body(self, lr):
+        g = self.r_store.groups['r']
+        _C.call('rcgan_zero', g.grads.data_ptr(), g.numel * 4, _C.stream_ptr())
+        self.r_prog.run_forward()
+        self.r_prog.run_backward()
+        _C.call('rcgan_sgd', g.params.data_ptr(), g.grads.data_ptr(), g.numel, float(lr), 1.0, _C.stream_ptr())
+
+    def recover_step(self, sample_actual=None, learning_rate=500.0, fetch=True):
+        """One `sess.run(recover_optim)` (:626-629): returns mse_loss evaluated BEFORE the update, like the reference's fetch."""
+        if sample_actual is not None:
+            src = torch.as_tensor(sample_actual, dtype=torch.float32)
+            self.r_prog.inputs['sample_actual'].data.copy_(src.reshape(-1), non_blocking=True)
+        self._run('recover_%g' % learning_rate, lambda: self._r_body(learning_rate))
+        if not fetch:
+            return None
+        self._r_host.copy_(self.r_prog.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._r_host[0])
+
+    def recover_labels(self, sample_actual, y_actual=None, recover_epoch=1000, learning_rate=500.0, log_every=100):
+        """The reference's loop (:622-640) on a given batch of real images; returns (y_recover [R,k], mse_loss,
+        zero_one_loss = tf.losses.cosine_distance(y_actual, one_hot(argmax y_recover)) = 1 - accuracy)."""
+        if not hasattr(self, 'r_prog') or self.recover_R != len(sample_actual):
+            self.build_recover(len(sample_actual))
+        mse = None
+        for epoch in range(recover_epoch):
+            mse = self.recover_step(sample_actual if epoch == 0 else None, learning_rate,
+                                    fetch=(epoch + 1) % log_every == 0 or epoch == recover_epoch - 1)
+        self.r_prog.run_forward()
+        y_rec = self.y_recover.torch().clone().cpu()
+        zero_one = None
+        if y_actual is not None:
+            ya = torch.as_tensor(y_actual, dtype=torch.float32)
+            onehot = torch.eye(self.y_dim)[y_rec.argmax(-1)]
+            zero_one = float((1.0 - (ya * onehot).sum(-1)).mean())
+        return y_rec, mse, zero_one
 
     def train(self, config=None, max_iters=None, log_every=100):
         """mnist/model.py:249-491 hot loop over self.data_* (logging evals, checkpoints, sample grids and the

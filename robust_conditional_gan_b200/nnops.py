@@ -305,7 +305,14 @@ class BatchNormOp(Op):
         if not needs(self.y):
             return
         nx, ns, no = self.need
-        assert self.train, 'backward through inference-mode batch norm is not part of the training path'
+        if not self.train:
+            # gen_sampler's norms (moving statistics are constants): only dL/dx exists -- the label-recovery path
+            assert not (ns or no), 'inference-mode batch norm has no parameter gradients on any reference path'
+            if nx:
+                call('rcgan_bn_infer_bwd', gp(self.y), dp(self.y), gp(self.x), self.samples, self.hw, self.c, self.y.dtype,
+                     dp(self.scale), dp(self.labels), self.save.data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
+                     prog.ws.bytes, stream_ptr())
+            return
         if self.dummy is not None:
             dsc, dof = self.dummy.data_ptr(), self.dummy.data_ptr() + 4 * self.n_labels * self.c
             accp = 0
@@ -590,6 +597,41 @@ class ChannelLossOp(Op):
              self._off(dp(self.psi), 1) if self.sliced else dp(self.psi), dp(self.V), dp(self.wgt), self.B, self.d, self.k,
              self.h.dtype, self.mode, self.coef / self.B, None, None, gh, self.acc_h, gpsi, gp(self.V) if nv else None,
              gp(self.wgt) if nw else None, st)
+
+
+class RecoverMSEOp(Op):
+    """mse_loss of DCGAN.recover_labels (mnist/model.py:538-541): mean_r sum_j y_rec[r,j] * mean_p (actual[r,p] - sample[r*k+j,p])^2."""
+
+    def __init__(self, sample, actual, y_rec, name):
+        prog = cur()
+        assert sample.dtype == _C.F32 and actual.dtype == _C.F32 and y_rec.dtype == _C.F32 and sample.ld == sample.c
+        self.sample, self.actual, self.y_rec = sample, actual, y_rec
+        self.R, self.k = y_rec.shape
+        self.npix = sample.numel() // (self.R * self.k)
+        assert actual.numel() == self.R * self.npix
+        self.slot = prog.loss_slot(name)
+        self.sq = prog.new((self.R, self.k), _C.F32)
+        self.inputs, self.outputs = (sample, y_rec), ()
+        prog.add(self)
+
+    def plan(self, prog):
+        pass
+
+    def plan_bwd(self, prog):
+        for i, t in enumerate((self.sample, self.y_rec)):
+            if self.need[i]:
+                assert self.claim(t) == 0, 'recover-loss gradients must have a single writer'
+
+    def forward(self, prog):
+        call('rcgan_recover_mse', dp(self.sample), dp(self.actual), dp(self.y_rec), self.R, self.k, self.npix,
+             prog.losses.data_ptr() + 4 * self.slot, dp(self.sq), None, None, stream_ptr())
+
+    def backward(self, prog):
+        ns, ny = self.need
+        if not (ns or ny):
+            return
+        call('rcgan_recover_mse', dp(self.sample), dp(self.actual), dp(self.y_rec), self.R, self.k, self.npix, None, None,
+             gp(self.sample) if ns else None, gp(self.y_rec) if ny else None, stream_ptr())
 
 
 class SigmoidCEOp(Op):

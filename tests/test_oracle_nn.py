@@ -145,3 +145,30 @@ def test_bf16_conditioning_of_bn_backward_is_inherent():
         OM._bn = orig
     errs = [float((a - b).norm() / b.norm()) for a, b in zip(grads[True], grads[False])]
     assert min(errs) > 2e-2, errs
+
+
+def test_recover_loss_restates_the_reference_formula():
+    """oracle/mnist.py recover_loss (mnist/model.py:516-541) against literal loops; one gradient step lowers the loss;
+    zero_one_loss = 1 - accuracy of argmax(y_recover)."""
+    from oracle import mnist as OM
+    cfg = OM.default_config(batch_size=4, alpha=0.5, perm_regularizer=True, algorithm='rcgan', disc_type='projection',
+                            estimate_confuse=True)
+    P = OM.init_params(cfg, seed=0, dtype=torch.float64)
+    g = torch.Generator().manual_seed(1)
+    R, k = 3, 10
+    z = torch.rand(R * k, 100, generator=g, dtype=torch.float64) - 0.5
+    yl = torch.randn(R, k, generator=g, dtype=torch.float64)
+    actual = torch.rand(R, 28, 28, 1, generator=g, dtype=torch.float64)
+    loss, y_rec, sq = OM.recover_loss(P, z, yl, actual, cfg)
+    imgs = OM.generator(P, z, torch.eye(k, dtype=torch.float64).repeat(R, 1), cfg, train=False)
+    ref = 0.0
+    for r in range(R):
+        for j in range(k):
+            ref += float(((actual[r] - imgs[r * k + j]) ** 2).mean()) * float(torch.softmax(yl[r], -1)[j])
+    assert abs(float(loss) - ref / R) < 1e-12
+    z1, yl1, l0, _ = OM.recover_step(P, z, yl, actual, cfg, lr=5.0)
+    l1, _, _ = OM.recover_loss(P, z1, yl1, actual, cfg)
+    assert float(l1) < float(l0) == float(loss)
+    ya = torch.eye(k, dtype=torch.float64)[torch.tensor([1, 2, 3])]
+    acc = float((y_rec.argmax(-1) == torch.tensor([1, 2, 3])).double().mean())
+    assert abs(float(OM.zero_one_loss(ya, y_rec)) - (1 - acc)) < 1e-12
