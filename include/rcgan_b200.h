@@ -70,6 +70,11 @@ int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scal
  * bf16-rounded inputs). */
 int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
                        const float* bias, void* y, int out_dtype, int act, float leak, void* stream);
+/* y = act(conv2d(x, w) + bias) + res: the ResidualBlock's `shortcut + output` (cifar10/gan_resnet.py:328) fused into the
+ * producing conv's epilogue; res has exactly y's layout and dtype.  (bf16: conv result rounded, then bf16 + bf16 in fp32,
+ * rounded -- bit-identical to running rcgan_conv2d_fprop followed by rcgan_add.) */
+int rcgan_conv2d_fprop_res(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack, const float* bias,
+                           const void* res, void* y, int out_dtype, int act, float leak, void* stream);
 /* dx (=|+=) act(conv_dgrad(dy, w) + bias): the backward-data op; with bias/act it is the
  * forward of deconv2d (mnist/ops.py:69-92).  bias may be NULL. */
 int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, const float* w, const void* wpack,

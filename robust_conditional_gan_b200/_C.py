@@ -38,6 +38,7 @@ _SIGS = {
     'rcgan_conv_uses_tensor_cores': (c_int, [DP, c_int]),
     'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
     'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
+    'rcgan_conv2d_fprop_res': (c_int, [DP, P, P, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_conv2d_dgrad': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, c_int, P]),
     'rcgan_conv2d_wgrad_workspace': (c_size_t, [DP]),
     'rcgan_conv2d_wgrad': (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),

@@ -594,20 +594,20 @@ int launch_io(const ConvP& p, int dtype, int out_dtype, const void* a, const flo
 }  // namespace
 
 // Implemented in conv_tc.cu (tcgen05 path); return 1 when they handled the call.
-int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
-                   int act, float leak, cudaStream_t st, int* handled);
+int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, const void* res, void* y,
+                   int out_dtype, int act, float leak, cudaStream_t st, int* handled);
 int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
                    int act, float leak, int accumulate, cudaStream_t st, int* handled);
 
 int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st,
                    int* handled);
 
-extern "C" int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
-                                  const float* bias, void* y, int out_dtype, int act, float leak, void* stream) {
+static int conv2d_fprop_impl(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack, const float* bias,
+                            const void* res, void* y, int out_dtype, int act, float leak, void* stream) {
   if (int e = check_desc(d, "conv2d_fprop")) return e;
   if (wpack) {
     int handled = 0;
-    int e = rcgan_tc_fprop(d, x, wpack, bias, y, out_dtype, act, leak, as_stream(stream), &handled);
+    int e = rcgan_tc_fprop(d, x, wpack, bias, res, y, out_dtype, act, leak, as_stream(stream), &handled);
     if (e || handled) return e;
   }
   RCGAN_CHECK_ARG(w, "conv2d_fprop: null fp32 weights");
@@ -616,7 +616,24 @@ extern "C" int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const
   p.bias = bias; p.act = act; p.leak = leak; p.klen = ((p.K + BK - 1) / BK) * BK;
   if (int e = launch_io<MODE_FPROP>(p, d->dtype, out_dtype, x, w, y, as_stream(stream))) return e;
   RCGAN_LAUNCH_CHECK("conv2d_fprop");
+  if (res) {
+    // CUDA-core path (fp32 parity mode, odd shapes): the residual is a separate in-place add over the dense output
+    RCGAN_CHECK_ARG(d->ldy == d->cout, "conv2d_fprop_res: the CUDA-core path needs a dense output (ldy == cout)");
+    return rcgan_add(y, res, y, (long)d->n * d->ho * d->wo * d->cout, out_dtype, stream);
+  }
   return 0;
+}
+
+extern "C" int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
+                                  const float* bias, void* y, int out_dtype, int act, float leak, void* stream) {
+  return conv2d_fprop_impl(d, x, w, wpack, bias, nullptr, y, out_dtype, act, leak, stream);
+}
+
+extern "C" int rcgan_conv2d_fprop_res(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
+                                      const float* bias, const void* res, void* y, int out_dtype, int act, float leak,
+                                      void* stream) {
+  RCGAN_CHECK_ARG(res, "conv2d_fprop_res: null residual");
+  return conv2d_fprop_impl(d, x, w, wpack, bias, res, y, out_dtype, act, leak, stream);
 }
 
 extern "C" int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, const float* w, const void* wpack,

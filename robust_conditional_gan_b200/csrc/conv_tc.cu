@@ -38,6 +38,7 @@ struct TcParams {
   int act;
   float leak;
   int accumulate;
+  const void* res;            // fused residual: out = act(conv + bias) + res, res laid out exactly like out (NULL = none)
   // TMA im2col A loader (one cp.async.bulk.tensor.im2col per K block instead of 1024 cp.async):
   // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
   int im_w_lo, im_h_lo, im_sw, im_sh;
@@ -252,7 +253,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
   __syncwarp();
   if (p.dbg & 16) return;
   TO* out = reinterpret_cast<TO*>(p.out);
-  const bool fast = p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0 && ncols >= VEC;
+  // the tile is added onto `addsrc` (same layout as out): out itself when accumulating, the residual input when fusing the
+  // ResidualBlock's shortcut add (gan_resnet.py:328); both round like the separate add kernel did (bf16 + bf16 in fp32 -> bf16)
+  const TO* addsrc = p.accumulate ? out : reinterpret_cast<const TO*>(p.res);
+  const bool fast = p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0 && ncols >= VEC &&
+                    (reinterpret_cast<uintptr_t>(addsrc) & 15) == 0;
   if (fast) {
     // whole 16-byte pieces of every row, consecutive lanes on consecutive pieces; a ragged tail (ncols % VEC columns,
     // e.g. 138 = 17 pieces + 2) is finished element-wise below
@@ -268,8 +273,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
       if (o == ~0ull) continue;
       uint4 q = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
       TO* g = out + o + n0 + piece * VEC;
-      if (p.accumulate) {
-        const uint4 old = *reinterpret_cast<const uint4*>(g);
+      if (addsrc) {
+        const uint4 old = *reinterpret_cast<const uint4*>(addsrc + o + n0 + piece * VEC);
         if (sizeof(TO) == 4) {
           const float* a = reinterpret_cast<const float*>(&old);
           float* c = reinterpret_cast<float*>(&q);
@@ -295,7 +300,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
         if (o == ~0ull) continue;
         TO* g = out + o + n0 + c;
         float x = to_f(reinterpret_cast<const TO*>(slab + row * PITCH)[c]);
-        if (p.accumulate) x += to_f(*g);
+        if (addsrc) x += to_f(addsrc[o + n0 + c]);
         *g = from_f<TO>(x);
       }
     }
@@ -308,7 +313,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
       for (int c = lane; c < ncols; c += 32) {
         TO* g = out + o + n0 + c;
         float x = to_f(srow[c]);
-        if (p.accumulate) x += to_f(*g);
+        if (addsrc) x += to_f(addsrc[o + n0 + c]);
         *g = from_f<TO>(x);
       }
     }
@@ -1142,8 +1147,8 @@ extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const 
   return 0;
 }
 
-int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
-                   int act, float leak, cudaStream_t st, int* handled) {
+int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, const void* res, void* y,
+                   int out_dtype, int act, float leak, cudaStream_t st, int* handled) {
   *handled = 0;
   if (!fprop_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
   PackGeo g = pack_geo(d);
@@ -1156,7 +1161,7 @@ int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, c
   for (int t = 0; t < g.taps; t++) { p.tdy[t] = (short)(t / d->kw); p.tdx[t] = (short)(t % d->kw); p.twi[t] = (short)t; }
   p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->ho; p.OW = d->wo;
   p.oy_mul = 1; p.oy_add = 0; p.ox_mul = 1; p.ox_add = 0; p.N = d->cout;
-  p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0;
+  p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0; p.res = res;
   p.im_w_lo = -d->pad_l; p.im_h_lo = -d->pad_t; p.im_sw = d->stride; p.im_sh = d->stride;
   for (int t = 0; t < g.taps; t++) { p.toffh[t] = (unsigned short)(t / d->kw); p.toffw[t] = (unsigned short)(t % d->kw); }
   if (int e = run_tc(p, reinterpret_cast<const bf16*>(wpack), g.kpadF, d->cout, g.taps, d->cin, d->n, st)) return e;
@@ -1199,7 +1204,7 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
       p.ntaps = nt; p.kb_per_tap = g.kpadD / BK;
       p.out = dx; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldx; p.OH = d->h; p.OW = d->w;
       p.oy_mul = s; p.oy_add = py; p.ox_mul = s; p.ox_add = px; p.N = d->cin;
-      p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate;
+      p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate; p.res = nullptr;
       if (nt == 0) { rcgan_set_error("conv_tc dgrad: parity class without taps"); return RCGAN_EUNSUPPORTED; }
       if (s == 2) {
         { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }

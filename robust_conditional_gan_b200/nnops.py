@@ -80,8 +80,9 @@ class ConvOp(Op):
     cifar10/common/ops/conv2d.py:181-216); with a 2-D x it is tf.matmul + bias
     (mnist/ops.py:97-116; cifar10/common/ops/linear.py:161-180).  w: [kh,kw,cin,cout] or [cin,cout]."""
 
-    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False):
-        """pre_norm: the output feeds a batch norm -> stored in fp32 even in bf16 mode (gradient stays bf16)."""
+    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False, residual=None):
+        """pre_norm: the output feeds a batch norm -> stored in fp32 even in bf16 mode (gradient stays bf16).
+        residual: y = conv(x) + b + residual, the ResidualBlock's shortcut add fused into this conv's epilogue."""
         prog = cur()
         n, h, wd = spatial(x)
         if len(w.shape) == 2:
@@ -92,13 +93,15 @@ class ConvOp(Op):
         assert cin == x.c, 'conv: weight cin %d != input channels %d' % (cin, x.c)
         ho, pt = same_pad(h, kh, stride)
         wo, pl = same_pad(wd, kw, stride)
-        self.x, self.w, self.b = x, w, b
+        self.x, self.w, self.b, self.res = x, w, b, residual
         self.act, self.leak = ACT[act], leak
         oshape = (n, cout) if len(x.shape) == 2 else (n, ho, wo, cout)
         assert not (pre_norm and self.act != _C.ACT_NONE)
+        assert residual is None or (self.act == _C.ACT_NONE and not pre_norm and tuple(residual.shape) == tuple(oshape)
+                                    and residual.ld == residual.c and residual.dtype == x.dtype)
         self.y = prog.new(oshape, _C.F32 if pre_norm else x.dtype, grad_dtype=x.dtype)
         self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
-        self.inputs, self.outputs = (x, w, b), (self.y,)
+        self.inputs, self.outputs = (x, w, b, residual), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
@@ -130,7 +133,9 @@ class ConvOp(Op):
         prog.add(self)
 
     def plan_bwd(self, prog):
-        nx, nw, nb = self.need
+        nx, nw, nb, nr = self.need
+        # (reverse program order: the residual's gradient is claimed first, as the separate AddOp used to do)
+        self.acc_r = self.claim(self.res) if (nr and self.res is not None) else 0
         self.acc_x = self.claim(self.x) if nx else 0
         self.acc_w = self.claim(self.w) if nw else 0
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
@@ -167,15 +172,21 @@ class ConvOp(Op):
             d, xin = self.gdesc, dp(self.patch)
         if self.pack_owner:
             call('rcgan_conv_wpack', d, dp(self.w), None, pp(self.pack), stream_ptr())
+        if self.res is not None:
+            call('rcgan_conv2d_fprop_res', d, xin, dp(self.w), pp(self.pack), dp(self.b), dp(self.res), dp(self.y), self.y.dtype,
+                 self.act, self.leak, stream_ptr())
+            return
         call('rcgan_conv2d_fprop', d, xin, dp(self.w), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act,
              self.leak, stream_ptr())
 
     def backward(self, prog):
         if not needs(self.y):
             return
-        nx, nw, nb = self.need
+        nx, nw, nb, nr = self.need
         st = stream_ptr()
         y, dy = self.y, gp(self.y)
+        if nr and self.res is not None:
+            call('rcgan_copy_acc', dy, gp(self.res), self.res.numel(), self.res.grad_dtype, self.acc_r, st)
         if self.act != _C.ACT_NONE:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):

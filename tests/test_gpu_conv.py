@@ -366,3 +366,29 @@ def test_few_output_channel_forward_as_gemm_plus_col2im(lib, shape):
     ref = torch.tanh(O.conv2d(x.double(), wt.double(), s) + b.double())
     assert relerr(y[..., :cout].float(), ref) < TOL[dtype]
     assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('shape', [SHAPES[7], (2, 32, 32, 256, 256, 3, 1, 0, 0), (600, 8, 8, 128, 128, 3, 1, 0, 0)])
+def test_fprop_with_fused_residual(lib, shape, dtype):
+    """rcgan_conv2d_fprop_res == conv + bias + residual (ResidualBlock's shortcut add, gan_resnet.py:328), bit-identical
+    to the unfused fprop + add sequence; the last shape takes the persistent kernel."""
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
+    n, cout = shape[0], shape[4]
+    res = torch.randn(n, ho, wo, cout, generator=torch.Generator().manual_seed(9)).to(TD[dtype])
+    resd = res.cuda()
+    wdev, bdev = dev(wt), dev(b)
+    pack = None
+    if dtype == _C.BF16:
+        pack = torch.zeros(lib.rcgan_conv_wpack_bytes(d), dtype=torch.uint8, device='cuda')
+        call('rcgan_conv_wpack', d, wdev.data_ptr(), None, pack.data_ptr(), st())
+    pp_ = pack.data_ptr() if pack is not None else None
+    y = torch.zeros(n, ho, wo, cout, device='cuda', dtype=TD[dtype])
+    call('rcgan_conv2d_fprop_res', d, xd.data_ptr(), wdev.data_ptr(), pp_, bdev.data_ptr(), resd.data_ptr(), y.data_ptr(), dtype,
+         _C.ACT_NONE, 0.0, st())
+    ref = O.conv2d(x.double(), wt.double(), shape[6]) + b.double() + res.double()
+    assert relerr(y.float(), ref) < TOL[dtype]
+    y2 = torch.zeros_like(y)
+    call('rcgan_conv2d_fprop', d, xd.data_ptr(), wdev.data_ptr(), pp_, bdev.data_ptr(), y2.data_ptr(), dtype, _C.ACT_NONE, 0.0, st())
+    call('rcgan_add', y2.data_ptr(), resd.data_ptr(), y2.data_ptr(), y2.numel(), dtype, st())
+    assert torch.equal(y, y2)
