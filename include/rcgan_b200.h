@@ -70,6 +70,16 @@ int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scal
  * bf16-rounded inputs). */
 int rcgan_conv2d_fprop(const rcgan_conv_desc* d, const void* x, const float* w, const void* wpack,
                        const float* bias, void* y, int out_dtype, int act, float leak, void* stream);
+/* UpsampleConv forward (cifar10/gan_resnet.py:259-272: nearest-neighbour 2x upsample, then 3x3 SAME conv) WITHOUT the
+ * upsampled tensor: each of the 4 output parity classes is a 2x2-tap conv of the small input with pre-summed filter taps
+ * (4/9 of the flops).  d describes the 3x3 conv at the OUTPUT resolution (h, w even; cin, ldx multiples of 8); x_small is
+ * [n, h/2, w/2, cin] with channel stride d->ldx.  rcgan_upconv2d_fold builds the folded fp32 filter (16*cin*cout floats)
+ * and its bf16 pack (rcgan_upconv2d_pack_bytes; 0 = unsupported shape) -- once per weight update.  Forward only: the
+ * reference needs no gradient through the generator in its discriminator step, where this runs. */
+size_t rcgan_upconv2d_pack_bytes(const rcgan_conv_desc* d);
+int rcgan_upconv2d_fold(const rcgan_conv_desc* d, const float* w, float* wfold, void* pack, void* stream);
+int rcgan_upconv2d_fprop(const rcgan_conv_desc* d, const void* x_small, const void* pack, const float* bias, void* y,
+                         int out_dtype, int act, float leak, void* stream);
 /* y = act(conv2d(x, w) + bias) + res: the ResidualBlock's `shortcut + output` (cifar10/gan_resnet.py:328) fused into the
  * producing conv's epilogue; res has exactly y's layout and dtype.  (bf16: conv result rounded, then bf16 + bf16 in fp32,
  * rounded -- bit-identical to running rcgan_conv2d_fprop followed by rcgan_add.) */

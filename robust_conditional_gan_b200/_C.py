@@ -38,6 +38,9 @@ _SIGS = {
     'rcgan_conv_uses_tensor_cores': (c_int, [DP, c_int]),
     'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
     'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
+    'rcgan_upconv2d_pack_bytes': (c_size_t, [DP]),
+    'rcgan_upconv2d_fold': (c_int, [DP, P, P, P, P]),
+    'rcgan_upconv2d_fprop': (c_int, [DP, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_conv2d_fprop_res': (c_int, [DP, P, P, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_conv2d_dgrad': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, c_int, P]),
     'rcgan_conv2d_wgrad_workspace': (c_size_t, [DP]),

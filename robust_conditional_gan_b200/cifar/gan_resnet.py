@@ -72,9 +72,10 @@ class Net:
     def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
                      inputs_norm=False, he_init=True, biases=True, pre_norm=False):
         """:259-272"""
-        out = Upsample2Op(inputs).y
+        up = Upsample2Op(inputs)
+        out = up.y
         return lib_ops.Conv2D(out, out.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
-                              update_collection=update_collection, he_init=he_init, biases=biases, pre_norm=pre_norm)
+                              update_collection=update_collection, he_init=he_init, biases=biases, pre_norm=pre_norm, up_op=up)
 
     def ResidualBlock(self, inputs, input_dim, output_dim, filter_size, name, spectral_normed=False, update_collection=None,
                       inputs_norm=False, resample=None, labels=None, biases=True):

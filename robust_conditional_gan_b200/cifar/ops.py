@@ -21,7 +21,7 @@ def _const(v):
 
 def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name=None, conv_type='conv2d', channel_multiplier=0,
            padding='SAME', spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True, mask_type=None,
-           weightnorm=None, biases=True, gain=1., fuse_act=None, pre_norm=False, residual=None):
+           weightnorm=None, biases=True, gain=1., fuse_act=None, pre_norm=False, residual=None, up_op=None):
     """cifar10/common/ops/conv2d.py:31-218, plain conv2d branch: uniform He/Glorot init (:83-127), spectral norm under
     scope `filters` (:169-171), stride-`stride` SAME conv (:181-187), + Biases (:212-216)."""
     if conv_type != 'conv2d' or channel_multiplier or mask_type is not None or weightnorm or inputs_norm or padding != 'SAME':
@@ -37,7 +37,7 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name=None, co
             with S.variable_scope('filters'):
                 w = sn.spectral_normed_weight(filters, update_collection=update_collection)
         b = S.get_variable('Biases', [output_dim], _const(0.)) if biases else None
-    return ConvOp(inputs, w, b, stride, fuse_act, pre_norm=pre_norm, residual=residual).y
+    return ConvOp(inputs, w, b, stride, fuse_act, pre_norm=pre_norm, residual=residual, up_op=up_op).y
 
 
 def Linear(inputs, input_dim, output_dim, name=None, spectral_normed=False, update_collection=None, reuse=None,

@@ -925,6 +925,27 @@ __global__ void wpack_kernel(const float* __restrict__ w, const float* __restric
   }
 }
 
+// UpsampleConv (gan_resnet.py:259-272) = 3x3 SAME conv of the 2x nearest-neighbour upsampled input.  For output pixel
+// (2a+py, 2b+px) the three filter rows read source rows {a-1: ky 0; a: ky 1,2} (py = 0) or {a: ky 0,1; a+1: ky 2} (py = 1), and
+// likewise for columns: each output parity class is a 2x2-tap conv of the SMALL input with pre-summed filter taps
+// -- 4/9 of the multiply-adds and no materialised upsampled tensor.  wf: [class(4)][r(2)][c(2)][cin][cout] fp32.
+__global__ void upconv_fold_kernel(const float* __restrict__ w, float* __restrict__ wf, int cin, int cout) {
+  pdl_sync();
+  const long per = (long)cin * cout, total = 16 * per;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / per);
+    const long e = i - (long)t * per;
+    const int cls = t >> 2, r = (t >> 1) & 1, c = t & 1, py = cls >> 1, px = cls & 1;
+    // taps of the 3x3 filter that land on source offset index r (resp. c) for parity py (resp. px)
+    const int ky0 = py == 0 ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = py == 0 ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+    const int kx0 = px == 0 ? (c == 0 ? 0 : 1) : (c == 0 ? 0 : 2), kx1 = px == 0 ? (c == 0 ? 0 : 2) : (c == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ky++)
+      for (int kx = kx0; kx <= kx1; kx++) acc += w[(size_t)(ky * 3 + kx) * per + e];
+    wf[i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
                                    const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1224,6 +1245,70 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
   }
   *handled = 1;
   return 0;
+}
+
+extern "C" size_t rcgan_upconv2d_pack_bytes(const rcgan_conv_desc* d) {
+  // d: the 3x3 stride-1 conv at the OUTPUT resolution (h x w); folded filter = a 16-tap pack
+  if (!d || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->dtype != RCGAN_BF16 || d->h % 2 ||
+      d->w % 2 || d->cin < 32 || d->cin % 8 || d->ldx % 8 || d->cout < 32)
+    return 0;
+  rcgan_conv_desc f = *d;
+  f.kh = 4; f.kw = 4;
+  return pack_geo(&f).bytes;
+}
+
+extern "C" int rcgan_upconv2d_fold(const rcgan_conv_desc* d, const float* w, float* wfold, void* pack, void* stream) {
+  RCGAN_CHECK_ARG(d && w && wfold && pack && rcgan_upconv2d_pack_bytes(d) > 0, "upconv2d_fold: unsupported shape");
+  const long total = 16L * d->cin * d->cout;
+  int grid = (int)((total + 255) / 256);
+  if (grid > RCGAN_NUM_SMS * 8) grid = RCGAN_NUM_SMS * 8;
+  launch_pdl(upconv_fold_kernel, grid, 256, 0, as_stream(stream), w, wfold, d->cin, d->cout);
+  RCGAN_LAUNCH_CHECK("upconv_fold");
+  rcgan_conv_desc f = *d;
+  f.kh = 4; f.kw = 4;
+  return rcgan_conv_wpack(&f, wfold, nullptr, pack, stream);
+}
+
+extern "C" int rcgan_upconv2d_fprop(const rcgan_conv_desc* d, const void* x_small, const void* pack, const float* bias, void* y,
+                                    int out_dtype, int act, float leak, void* stream) {
+  RCGAN_CHECK_ARG(d && x_small && pack && y && rcgan_upconv2d_pack_bytes(d) > 0, "upconv2d_fprop: unsupported shape");
+  RCGAN_CHECK_ARG(out_dtype == RCGAN_BF16 || out_dtype == RCGAN_F32, "upconv2d_fprop: bad output dtype");
+  rcgan_conv_desc f = *d;
+  f.kh = 4; f.kw = 4;
+  PackGeo g = pack_geo(&f);
+  const int hs = d->h / 2, ws = d->w / 2;
+  TcMulti mp;
+  TcMaps amaps;
+  mp.nprob = 0;
+  for (int py = 0; py < 2; py++)
+    for (int px = 0; px < 2; px++) {
+      TcParams p;
+      p.src = reinterpret_cast<const bf16*>(x_small);
+      p.SH = hs; p.SW = ws; p.ld_src = d->ldx; p.cvalid = round_up(d->cin, 8);
+      p.MH = hs; p.MW = ws; p.M = d->n * hs * ws;
+      const int oy0 = py == 0 ? -1 : 0, ox0 = px == 0 ? -1 : 0;       // first source offset of this parity class
+      p.by_mul = 1; p.by_add = 0; p.bx_mul = 1; p.bx_add = 0;
+      int nt = 0;
+      for (int r = 0; r < 2; r++)
+        for (int c = 0; c < 2; c++) {
+          p.tdy[nt] = (short)(oy0 + r); p.tdx[nt] = (short)(ox0 + c);
+          p.twi[nt] = (short)((py * 2 + px) * 4 + r * 2 + c);
+          p.toffh[nt] = (unsigned short)r; p.toffw[nt] = (unsigned short)c;
+          nt++;
+        }
+      p.im_h_lo = oy0; p.im_w_lo = ox0; p.im_sh = 1; p.im_sw = 1;
+      p.ntaps = nt; p.kb_per_tap = g.kpadF / BK;
+      p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->h; p.OW = d->w;
+      p.oy_mul = 2; p.oy_add = py; p.ox_mul = 2; p.ox_add = px; p.N = d->cout;
+      p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0; p.res = nullptr;
+      { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+      if (!make_amap(&amaps.a[mp.nprob], p, d->cin, d->n)) {
+        rcgan_set_error("upconv2d_fprop: im2col tensor map not encodable for this shape");
+        return RCGAN_EUNSUPPORTED;
+      }
+      mp.p[mp.nprob++] = p;
+    }
+  return run_tc_persist(mp, amaps, reinterpret_cast<const bf16*>(pack), g.kpadF, d->cout, g.taps, as_stream(stream));
 }
 
 template <int BN, bool IM2COL>

@@ -80,9 +80,11 @@ class ConvOp(Op):
     cifar10/common/ops/conv2d.py:181-216); with a 2-D x it is tf.matmul + bias
     (mnist/ops.py:97-116; cifar10/common/ops/linear.py:161-180).  w: [kh,kw,cin,cout] or [cin,cout]."""
 
-    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False, residual=None):
+    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False, residual=None, up_op=None):
         """pre_norm: the output feeds a batch norm -> stored in fp32 even in bf16 mode (gradient stays bf16).
-        residual: y = conv(x) + b + residual, the ResidualBlock's shortcut add fused into this conv's epilogue."""
+        residual: y = conv(x) + b + residual, the ResidualBlock's shortcut add fused into this conv's epilogue.
+        up_op: the Upsample2Op that produced x (UpsampleConv): in programs that need no gradient through this conv the
+        pair runs as ONE folded launch on the small input (rcgan_upconv2d_fprop) and the upsample is skipped."""
         prog = cur()
         n, h, wd = spatial(x)
         if len(w.shape) == 2:
@@ -103,6 +105,12 @@ class ConvOp(Op):
         self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b, residual), (self.y,)
         prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.desc))
+        self.up_op = None
+        if up_op is not None and residual is None and not pre_norm and _C.load().rcgan_upconv2d_pack_bytes(self.desc) > 0:
+            self.up_op = up_op
+            up_op.consumer = self
+            self.up_wfold = torch.zeros(16 * cin * cout, dtype=torch.float32, device=prog.device)
+            self.up_pack = torch.zeros(_C.load().rcgan_upconv2d_pack_bytes(self.desc), dtype=torch.uint8, device=prog.device)
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
@@ -163,7 +171,17 @@ class ConvOp(Op):
         call('rcgan_conv2d_fprop', self.f_g, dp(self.x), pp(self.f_w2), pp(self.f_pack), None, pp(self.f_T), _C.F32, _C.ACT_NONE, 0.0, st)
         call('rcgan_col2im', self.f_cdesc, pp(self.f_T), self.f_ldt, dp(self.b), dp(self.y), self.y.dtype, self.act, self.leak, 0, st)
 
+    def folds_upsample(self):
+        """UpsampleConv without the upsampled tensor: legal when nothing of this conv is differentiated in this program."""
+        return self.up_op is not None and not any(self.need) and not needs(self.y)
+
     def forward(self, prog):
+        if self.folds_upsample():
+            st = stream_ptr()
+            call('rcgan_upconv2d_fold', self.desc, dp(self.w), pp(self.up_wfold), pp(self.up_pack), st)
+            call('rcgan_upconv2d_fprop', self.desc, dp(self.up_op.x), pp(self.up_pack), dp(self.b), dp(self.y), self.y.dtype,
+                 self.act, self.leak, st)
+            return
         if self.tpatch is not None and self.desc.kh == self.desc.kw and self.desc.pad_t == self.desc.pad_l:
             return self._forward_scatter(prog)
         d, xin = self.desc, dp(self.x)
@@ -789,12 +807,15 @@ class Upsample2Op(Op):
         self.x = x
         self.y = prog.new((n, 2 * h, 2 * w, x.c), x.dtype)
         self.inputs, self.outputs = (x,), (self.y,)
+        self.consumer = None      # set by the ConvOp of an UpsampleConv pair that can fold this op away
         prog.add(self)
 
     def plan_bwd(self, prog):
         self.acc = self.claim(self.x) if self.need[0] else 0
 
     def forward(self, prog):
+        if self.consumer is not None and self.consumer.folds_upsample():
+            return                # the only reader runs on self.x directly (rcgan_upconv2d_fprop)
         n, h, w = spatial(self.x)
         call('rcgan_upsample2_fwd', dp(self.x), dp(self.y), n, h, w, self.x.c, self.x.dtype, stream_ptr())
 

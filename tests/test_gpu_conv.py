@@ -392,3 +392,30 @@ def test_fprop_with_fused_residual(lib, shape, dtype):
     call('rcgan_conv2d_fprop', d, xd.data_ptr(), wdev.data_ptr(), pp_, bdev.data_ptr(), y2.data_ptr(), dtype, _C.ACT_NONE, 0.0, st())
     call('rcgan_add', y2.data_ptr(), resd.data_ptr(), y2.data_ptr(), y2.numel(), dtype, st())
     assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(2, 16, 16, 64, 64), (3, 8, 8, 256, 128), (2, 32, 32, 128, 256), (40, 32, 32, 64, 160)])
+def test_upsample_conv_folded_forward(lib, n, h, w, cin, cout):
+    """rcgan_upconv2d_fprop (4 parity classes x 2x2 pre-summed taps on the small input) == 3x3 SAME conv of the 2x
+    nearest-neighbour upsampled input (UpsampleConv, gan_resnet.py:259-272), bias + relu fused."""
+    g = torch.Generator().manual_seed(n + h)
+    xs = torch.randn(n, h // 2, w // 2, cin, generator=g).bfloat16()
+    wt = torch.randn(3, 3, cin, cout, generator=g) * 0.05
+    b = torch.randn(cout, generator=g)
+    d = ConvDesc(n, h, w, cin, h, w, cout, 3, 3, 1, 1, 1, cin, cout, _C.BF16)
+    nb = lib.rcgan_upconv2d_pack_bytes(d)
+    assert nb > 0
+    wdev, bdev, xd = dev(wt), dev(b), xs.cuda()
+    wf = torch.zeros(16 * cin * cout, device='cuda')
+    pack = torch.zeros(nb, dtype=torch.uint8, device='cuda')
+    call('rcgan_upconv2d_fold', d, wdev.data_ptr(), wf.data_ptr(), pack.data_ptr(), st())
+    y = torch.zeros(n, h, w, cout, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_upconv2d_fprop', d, xd.data_ptr(), pack.data_ptr(), bdev.data_ptr(), y.data_ptr(), _C.BF16, _C.ACT_RELU, 0.0, st())
+    up = xs.double().repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    ref = torch.relu(O.conv2d(up, wt.double(), 1) + b.double())
+    assert relerr(y.float(), ref) < TOL[_C.BF16]
+    # unsupported shapes are refused loudly, not silently mis-computed
+    bad = ConvDesc(n, h, w, cin, h, w, cout, 5, 5, 1, 2, 2, cin, cout, _C.BF16)
+    assert lib.rcgan_upconv2d_pack_bytes(bad) == 0
+    with pytest.raises(_C.RcganError):
+        call('rcgan_upconv2d_fprop', bad, xd.data_ptr(), pack.data_ptr(), None, y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, st())
