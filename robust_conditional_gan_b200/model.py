@@ -22,7 +22,7 @@ import torch
 
 from . import _C, ops, scope as S
 from .graph import Program, VariableStore, tf_adam_lr
-from .nnops import (CastOp, ChannelLossOp, ConvOp, LogitLossOp, MeanHWOp, RecoverMSEOp, SigmoidCEOp, SoftmaxRowsOp, adam_step)
+from .nnops import (CastOp, ChannelLossOp, ConcatRowsOp, ConvOp, LogitLossOp, MeanHWOp, RecoverMSEOp, SigmoidCEOp, SoftmaxRowsOp, adam_step)
 from .sampler import LabelNoiseSampler, class_dependent_confusion, one_coin_confusion
 
 LOSS_MODES = {'hinge': (_C.HINGE_D_REAL, _C.HINGE_D_FAKE, _C.HINGE_G), 'ce': (_C.CE_D_REAL, _C.CE_D_FAKE, _C.CE_G)}
@@ -147,19 +147,37 @@ class DCGAN(object):
     def gen_sampler(self, z, y=None):
         return self.generator(z, y, train=False)
 
-    def _d_trunk(self, image, y):
-        """Label-independent part of the projection discriminator (mnist/model.py:649-678) -> h3 [B, df_dim]."""
+    def _d_trunk(self, image, y, groups=1):
+        """Label-independent part of the projection discriminator (mnist/model.py:649-678) -> h3 [B, df_dim].
+        groups=2: `image` is [real; fake] and every batch norm keeps separate statistics per half."""
         cfg = self.config
         cc = lambda l, t: ops.conv_cond_concat(t, y) if (cfg.concat_y and l in cfg.concat_y_layers) else t
         sn = cfg.spectral_norm
         h0 = ops.conv2d(cc(1, image), self.df_dim, spectral_norm=sn, name='d_h0_conv', fuse_act='lrelu')
         h1 = self.d_bn1(ops.conv2d(cc(2, h0), self.df_dim, spectral_norm=sn, name='d_h1_conv', pre_norm=self.pre_norm_fp32), fuse_act='lrelu',
-                        track_moving=False)
+                        track_moving=False, groups=groups)
         h2 = self.d_bn2(ops.conv2d(cc(3, h1), self.df_dim, spectral_norm=sn, name='d_h2_conv', pre_norm=self.pre_norm_fp32), fuse_act='lrelu',
-                        track_moving=False)
+                        track_moving=False, groups=groups)
         h3 = self.d_bn3(ops.conv2d(cc(4, h2), self.df_dim, spectral_norm=sn, name='d_h3_conv', pre_norm=self.pre_norm_fp32), fuse_act='lrelu',
-                        track_moving=False)
+                        track_moving=False, groups=groups)
         return MeanHWOp(h3).y
+
+    def discriminator_pair(self, x_real, x_fake, y_real, y_fake, wgt_real, wgt_fake, modes, names):
+        """The D step's two projection-discriminator calls (mnist/model.py:150-207: D(x, .) and D(G(z), .)) as ONE pass over
+        [real; fake]: convs, linears and their weight gradients see 2B samples per launch, the batch norms keep the two
+        calls' separate batch statistics (groups=2), and each half gets its own loss term / channel weights.
+        Mathematically identical to two calls (every other op is per-sample).  Returns (logits_real, logits_fake)."""
+        B = self.batch_size
+        with S.variable_scope("discriminator"):
+            x_all = ConcatRowsOp(x_real, x_fake).y
+            y_all = ConcatRowsOp(y_real, y_fake).y if self.config.concat_y else None
+            h3 = self._d_trunk(x_all, y_all, groups=2)
+            h3f = CastOp(h3, _C.F32).y                       # fp32 head
+            h4 = ops.linear(h3f, 1, 'd_h4_lin', max_norm=self.config.max_norm)
+            V = ops.linear(self._eye(Program.current), self.df_dim, 'd_h5_y_lin', max_norm=self.config.max_norm)
+            op_r = ChannelLossOp(h3f, h4, V, wgt_real, modes[0], names[0], rows=(0, B))
+            op_f = ChannelLossOp(h3f, h4, V, wgt_fake, modes[1], names[1], rows=(B, B))
+            return op_r.logits, op_f.logits
 
     def discriminator(self, image, y=None, reuse=False, wgt=None, mode=None, loss_name=None, coef=1.0):
         """mnist/model.py:644-703.  Records the discriminator on `image` and its GAN loss term.
@@ -258,17 +276,22 @@ class DCGAN(object):
             x = CastOp(x32, self.act_dtype).y
             zc = CastOp(z, self.act_dtype).y
             G = self.generator(zc, y_gen)
-            if self.algorithm == 'unbiased':
-                if not proj:
-                    raise NotImplementedError('unbiased needs the projection discriminator (run_unbiased.sh)')
-                self.D_logits = self.discriminator(x, y_real, wgt=y_rw, mode=m_real, loss_name='d_loss_real')
-            else:
-                self.D_logits = self.discriminator(x, y_real, mode=m_real, loss_name='d_loss_real')
             if learned and not proj:
                 raise NotImplementedError('estimate_confuse needs the projection discriminator (run_rcganu.sh)')
+            if self.algorithm == 'unbiased' and not proj:
+                raise NotImplementedError('unbiased needs the projection discriminator (run_unbiased.sh)')
             wf = fake_weights(dp_, y_gen, y_fake)
-            self.D_logits_ = self.discriminator(G, None if learned else wf, reuse=True, wgt=wf, mode=m_fake,
-                                                loss_name='d_loss_fake')
+            w_real = y_rw if self.algorithm == 'unbiased' else y_real
+            if proj and not (learned and cfg.concat_y):
+                self.D_logits, self.D_logits_ = self.discriminator_pair(x, G, y_real, wf, w_real, wf, (m_real, m_fake),
+                                                                        ('d_loss_real', 'd_loss_fake'))
+            else:
+                if self.algorithm == 'unbiased':
+                    self.D_logits = self.discriminator(x, y_real, wgt=y_rw, mode=m_real, loss_name='d_loss_real')
+                else:
+                    self.D_logits = self.discriminator(x, y_real, mode=m_real, loss_name='d_loss_real')
+                self.D_logits_ = self.discriminator(G, None if learned else wf, reuse=True, wgt=wf, mode=m_fake,
+                                                    loss_name='d_loss_fake')
             if self.perm_regularizer:
                 self.classifier_logits = self.classifier(x32)
                 SigmoidCEOp(self.classifier_logits, y_real, 'class_loss_real', 1.0)

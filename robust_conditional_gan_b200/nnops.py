@@ -296,18 +296,21 @@ class BatchNormOp(Op):
     """y = act(BN(x)).  labels None: tf.contrib.layers.batch_norm (mnist/ops.py:30-44), scale/offset [c];
     labels int32 [n]: cond_batchnorm (cifar10/common/ops/normalization.py:27-59), tables [n_labels,c]."""
 
-    def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2):
+    def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2, groups=1):
+        """groups > 1: the batch is `groups` equal sample ranges with INDEPENDENT batch statistics (the reference's separate
+        discriminator calls on the real and on the generated batch, mnist/model.py:150-207, run here as one pass)."""
         prog = cur()
         n, h, w = spatial(x)
         self.x, self.scale, self.offset, self.labels = x, scale, offset, labels
-        self.samples, self.hw, self.c = n, h * w, x.c
+        assert n % groups == 0 and (groups == 1 or labels is None)
+        self.groups, self.samples, self.hw, self.c = groups, n // groups, h * w, x.c
         assert x.ld == x.c
         self.n_labels = scale.numel() // x.c
         self.moving, self.train, self.eps, self.decay = moving, train, eps, decay
         self.act, self.leak = ACT[act], leak
         assert x.grad_dtype == prog.act_dtype or x.dtype == x.grad_dtype
         self.y = prog.new(x.shape, x.grad_dtype)
-        self.save = torch.zeros(2 * x.c, dtype=torch.float32, device=prog.device)
+        self.save = [torch.zeros(2 * x.c, dtype=torch.float32, device=prog.device) for _ in range(groups)]
         self.inputs, self.outputs = (x, scale, offset), (self.y,)
         self.ws_bytes = _C.load().rcgan_bn_workspace(self.samples, self.hw, self.c)
         prog.ws.request(self.ws_bytes)
@@ -322,13 +325,19 @@ class BatchNormOp(Op):
         elif needs(self.y):
             self.dummy = torch.zeros(2 * self.n_labels * self.c, dtype=torch.float32, device=prog.device)
 
+    def _off(self, ptr, g, esz):
+        """pointer to sample range g of a [groups*samples*hw, c] buffer"""
+        return None if ptr is None else ptr + g * self.samples * self.hw * self.c * esz
+
     def forward(self, prog):
         mm = mv = None
         if self.moving is not None:
             mm, mv = dp(self.moving[0]), dp(self.moving[1])
-        call('rcgan_bn_fwd', dp(self.x), dp(self.y), self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale),
-             dp(self.offset), dp(self.labels), self.eps, self.act, self.leak, 1 if self.train else 0, self.decay, mm, mv,
-             self.save.data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+        xs, ys = self.x.data.element_size(), self.y.data.element_size()
+        for g in range(self.groups):
+            call('rcgan_bn_fwd', self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), self.samples, self.hw, self.c,
+                 self.x.dtype, self.y.dtype, dp(self.scale), dp(self.offset), dp(self.labels), self.eps, self.act, self.leak,
+                 1 if self.train else 0, self.decay, mm, mv, self.save[g].data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
 
     def backward(self, prog):
         if not needs(self.y):
@@ -338,23 +347,29 @@ class BatchNormOp(Op):
             # gen_sampler's norms (moving statistics are constants): only dL/dx exists -- the label-recovery path
             assert not (ns or no), 'inference-mode batch norm has no parameter gradients on any reference path'
             if nx:
-                call('rcgan_bn_infer_bwd', gp(self.y), dp(self.y), gp(self.x), self.samples, self.hw, self.c, self.y.dtype,
-                     dp(self.scale), dp(self.labels), self.save.data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
-                     prog.ws.bytes, stream_ptr())
+                ys, gs = self.y.data.element_size(), self.y.grad.element_size()
+                for g in range(self.groups):
+                    call('rcgan_bn_infer_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.y), g, ys),
+                         self._off(gp(self.x), g, self.x.grad.element_size()), self.samples, self.hw, self.c, self.y.dtype,
+                         dp(self.scale), dp(self.labels), self.save[g].data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
+                         prog.ws.bytes, stream_ptr())
             return
         if self.dummy is not None:
             dsc, dof = self.dummy.data_ptr(), self.dummy.data_ptr() + 4 * self.n_labels * self.c
             accp = 0
         else:
             dsc, dof, accp = gp(self.scale), gp(self.offset), 1
-        if not nx:
-            # only parameter gradients wanted: dx still has to go somewhere -> reuse y.grad in place
-            dxp, accx = gp(self.y), 0
-        else:
-            dxp, accx = gp(self.x), self.acc_x
-        call('rcgan_bn_bwd', gp(self.y), dp(self.x), dp(self.y), dxp, self.samples, self.hw, self.c, self.x.dtype, self.y.dtype,
-             dp(self.scale), dp(self.labels), self.n_labels, self.save.data_ptr(), self.act, self.leak, dsc, dof, accx,
-             accp, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+        xs, ys, gs = self.x.data.element_size(), self.y.data.element_size(), self.y.grad.element_size()
+        for g in range(self.groups):
+            if not nx:
+                # only parameter gradients wanted: dx still has to go somewhere -> reuse y.grad in place
+                dxp, accx = self._off(gp(self.y), g, gs), 0
+            else:
+                dxp, accx = self._off(gp(self.x), g, self.x.grad.element_size()), self.acc_x
+            call('rcgan_bn_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), dxp,
+                 self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels,
+                 self.save[g].data_ptr(), self.act, self.leak, dsc, dof, accx, accp if g == 0 else 1, prog.ws.ptr(),
+                 prog.ws.bytes, stream_ptr())
 
 
 class ActOp(Op):

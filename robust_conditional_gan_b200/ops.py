@@ -35,7 +35,7 @@ class batch_norm(object):
         self.momentum = momentum
         self.name = name
 
-    def __call__(self, x, train=True, fuse_act=None, track_moving=True):
+    def __call__(self, x, train=True, fuse_act=None, track_moving=True, groups=1):
         c = x.shape[-1]
         with S.variable_scope(self.name):
             beta = S.get_variable('beta', [c], _const(0.0))
@@ -43,7 +43,8 @@ class batch_norm(object):
             mm = S.get_variable('moving_mean', [c], _const(0.0), trainable=False)
             mv = S.get_variable('moving_variance', [c], _const(1.0), trainable=False)
         moving = (mm, mv) if (track_moving or not train) else None
-        return BatchNormOp(x, gamma, beta, None, moving, train, self.epsilon, self.momentum, fuse_act).y
+        # groups: equal sample ranges normalised with their own batch statistics (one pass over [real; fake])
+        return BatchNormOp(x, gamma, beta, None, moving, train, self.epsilon, self.momentum, fuse_act, groups=groups).y
 
 
 def conv_cond_concat(x, y):
