@@ -1041,9 +1041,9 @@ bool wgrad_ok(const rcgan_conv_desc* d) {
          d->ho * d->wo <= 1024 && d->wo <= 255 && d->ho <= 255;
 }
 bool dgrad_ok(const rcgan_conv_desc* d) {
-  // narrow outputs (cin < 16): stride 1 streams well through the TMA im2col path; the stride-2 parity classes of the
-  // MNIST deconvs are 4 small launches and were measured slower than the gather-dot kernel (0.43 vs 0.28 ms for g_h3)
-  return d->dtype == RCGAN_BF16 && d->ldy % 8 == 0 && d->cout >= 32 && (d->cin >= 16 || d->stride == 1) && d->kh * d->kw <= MAX_TAPS &&
+  // narrow outputs: stride 1 streams well through the TMA im2col path; stride 2 with cin >= 8 (the 11-channel image + label
+  // concat of --concat_y) runs as one merged parity launch; 1..4 channels go through the GEMM + col2im path (nnops.ScatterDgrad)
+  return d->dtype == RCGAN_BF16 && d->ldy % 8 == 0 && d->cout >= 32 && (d->cin >= 8 || d->stride == 1) && d->kh * d->kw <= MAX_TAPS &&
          (d->stride == 1 || d->stride == 2);
 }
 

@@ -25,10 +25,12 @@ def gp(t):
 
 
 def make_patch(prog, desc, rows, ld_out):
-    """(patch tensor, GEMM desc) for a bf16 conv with cin <= 4 and kh*kw*cin <= 64, else (None, None).
+    """(patch tensor, GEMM desc) for a bf16 conv with few input channels, else (None, None).
     The GEMM desc is the 1x1 conv over the [rows, 1, 1, K'] patch matrix with the same weights viewed as [K', cout]."""
     kp = desc.kh * desc.kw * desc.cin
-    if desc.dtype != _C.BF16 or desc.cin > 4 or kp > 64 or desc.cout < 32 or desc.ldy % 8 != 0:
+    # cin <= 4 (1- / 3-channel images), or the 11-channel image + label concat of --concat_y (run_rcgany.sh: 5x5x11 = 275
+    # columns) -- below the 32 channels the implicit-GEMM kernel needs per K block
+    if desc.dtype != _C.BF16 or desc.cin > 16 or kp > 512 or (desc.cin > 4 and kp <= 64) or desc.cout < 32 or desc.ldy % 8 != 0:
         return None, None
     ldp = round_up(kp, 8)
     patch = prog.new((rows, kp), _C.BF16, ld=ldp)
@@ -117,6 +119,11 @@ class ConvOp(Op):
         # ... and their input gradient (a 1..3-channel result from a wide dL/dy: d_h0_conv / D.Block.1 in the G step) as one
         # dense GEMM + col2im
         self.scatter = ScatterDgrad(prog, self.desc, self.y.ld) if self.patch is not None else None
+        # 5..16 input channels: too wide for the scatter GEMM's tap matrix; the implicit-GEMM dgrad needs its own pack of the
+        # TRUE conv geometry (self.pack belongs to the patch GEMM)
+        self.dpack = None
+        if self.patch is not None and not self.scatter.ok and _C.load().rcgan_conv_uses_tensor_cores(self.desc, 1):
+            self.dpack = torch.zeros(_C.load().rcgan_conv_wpack_bytes(self.desc), dtype=torch.uint8, device=prog.device)
         # few-channel OUTPUTS (G.Output: 256 -> 3): the backward is the transposed conv of dL/dy (cin' = cout <= 4) with the
         # flipped filter, so it runs as GEMMs on the patch matrix of dL/dy (rcgan_wflip in the header)
         self.tpatch = None
@@ -213,6 +220,10 @@ class ConvOp(Op):
         if nx:
             if self.scatter is not None and self.scatter.ok:
                 self.scatter.run(dp(self.w), dy, gp(self.x), self.x.grad_dtype, None, _C.ACT_NONE, 0.0, self.acc_x, st)
+            elif self.dpack is not None:
+                call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.dpack), st)
+                call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), pp(self.dpack), None, gp(self.x), self.x.grad_dtype,
+                     _C.ACT_NONE, 0.0, self.acc_x, st)
             else:
                 call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
                      gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
