@@ -950,6 +950,28 @@ __global__ void __launch_bounds__(256) wpack_kernel(const float* __restrict__ w,
   }
 }
 
+// element-per-thread variant (kept for A/B: RCGAN_WPACK_FLAT=1)
+__global__ void wpack_flat_kernel(const float* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ packF,
+                             bf16* __restrict__ packD, int taps, int cin, int cout, int kpadF, int kpadD) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
+  const float sc = scale ? *scale : 1.f;
+  long nF = (long)taps * cout * kpadF, nD = (long)taps * cin * kpadD;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nF + nD; i += (long)gridDim.x * blockDim.x) {
+    if (i < nF) {
+      int k = (int)(i % kpadF);
+      long r = i / kpadF;
+      int co = (int)(r % cout), tap = (int)(r / cout);
+      packF[i] = __float2bfloat16_rn(k < cin ? w[((size_t)tap * cin + k) * cout + co] * sc : 0.f);
+    } else {
+      long j = i - nF;
+      int k = (int)(j % kpadD);
+      long r = j / kpadD;
+      int ci = (int)(r % cin), tap = (int)(r / cin);
+      packD[j] = __float2bfloat16_rn(k < cout ? w[((size_t)tap * cin + ci) * cout + k] * sc : 0.f);
+    }
+  }
+}
+
 // UpsampleConv (gan_resnet.py:259-272) = 3x3 SAME conv of the 2x nearest-neighbour upsampled input.  For output pixel
 // (2a+py, 2b+px) the three filter rows read source rows {a-1: ky 0; a: ky 1,2} (py = 0) or {a: ky 0,1; a+1: ky 2} (py = 1), and
 // likewise for columns: each output parity class is a 2x2-tap conv of the SMALL input with pre-summed filter taps
@@ -1184,9 +1206,19 @@ extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const 
   RCGAN_CHECK_ARG(d && w && pack, "conv_wpack: null argument");
   if (!(fprop_ok(d) || dgrad_ok(d))) { rcgan_set_error("conv_wpack: shape has no tensor-core pack"); return RCGAN_EUNSUPPORTED; }
   PackGeo g = pack_geo(d);
+  bf16* pk = reinterpret_cast<bf16*>(pack);
+  static int flat = -1;
+  if (flat < 0) { const char* e = getenv("RCGAN_WPACK_FLAT"); flat = (e && e[0] == '1') ? 1 : 0; }
+  if (flat) {
+    long n = (long)(g.bytes / sizeof(bf16));
+    int fg = (int)((n + 255) / 256);
+    if (fg > RCGAN_NUM_SMS * 8) fg = RCGAN_NUM_SMS * 8;
+    launch_pdl(wpack_flat_kernel, fg, 256, 0, as_stream(stream), w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
+    RCGAN_LAUNCH_CHECK("conv_wpack");
+    return 0;
+  }
   const long items = (long)g.taps * ((d->cout + 31) / 32) * (g.kpadF / 32) + ((long)g.taps * d->cin * g.kpadD + 1023) / 1024;
   int grid = (int)(items < RCGAN_NUM_SMS * 8 ? items : RCGAN_NUM_SMS * 8);
-  bf16* pk = reinterpret_cast<bf16*>(pack);
   launch_pdl(wpack_kernel, grid, 256, 0, as_stream(stream), w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
   RCGAN_LAUNCH_CHECK("conv_wpack");
   return 0;
