@@ -72,7 +72,7 @@ Geo make_geo(int samples, int hw, int c, bool per_sample, int vmax = 4) {
   while (lc < 32 && lc * 2 <= g.cg) lc *= 2;
   g.LC = lc; g.LR = 256 / lc;
   g.gx = (g.cg + lc - 1) / lc;
-  // blocks per SM wanted: 2, or 4 for large unconditional norms (measured, tests/debug_bn_bench.py: [1024*196, 128] bf16
+  // blocks per SM wanted: 2, or 4 for large unconditional norms (measured, tools/bn_bench.py: [1024*196, 128] bf16
   // fwd 72 -> 53 us, bwd 117 -> 96 us; the conditional per-sample chunking and small tensors are better off with 2)
   int waves = (!per_sample && (long)g.rows * c * 2 >= (32L << 20)) ? 4 : 2;
   { const char* e = getenv("RCGAN_BN_WAVES"); if (e && atoi(e) > 0) waves = atoi(e); }

@@ -1,5 +1,5 @@
 """Micro-benchmark of single conv launches through the C ABI (debug helper, not a test).
-usage: python tests/debug_conv_bench.py  [variant ...]"""
+usage: python tools/conv_bench.py  [variant ...]"""
 import os, sys, ctypes
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,4 @@
+"""Label-noise sampler timings: full load_mnist_labels path and the individual launches (run from the repo root on a B200)."""
 import sys, json, time
 sys.path.insert(0, ".")
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Weight-pack kernel timings on the layers that matter (run from the repo root on a B200; RCGAN_WPACK_FLAT=1 = old kernel)."""
 import sys, ctypes, torch
 sys.path.insert(0, '.')
 from robust_conditional_gan_b200 import _C
