@@ -159,6 +159,17 @@ int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int sam
                  const float* scale, const int* labels, int n_labels, const float* save, int act, float leak,
                  float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws, size_t ws_bytes,
                  void* stream);
+/* Batch norm with the label concat that follows it in the MNIST generator fused in (mnist/model.py:714-728: h = relu(bn(.)),
+ * then concat([h, y]) / conv_cond_concat(h, yb)): y has row stride ldy >= c + c2 (a multiple of 8), its channels [c, c + c2)
+ * receive yb[sample, :] (fp32 [samples, c2]), the rest of the padding is left untouched; the backward reads dy / y with the
+ * same stride and ignores the label channels.  One pass less over the activation in each direction. */
+int rcgan_bn_fwd_cat(const void* x, void* y, int ldy, const float* yb, int c2, int samples, int hw, int c, int xdtype, int ydtype,
+                     const float* scale, const float* offset, const int* labels, float eps, int act, float leak, int train,
+                     float decay, float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream);
+int rcgan_bn_bwd_cat(const void* dy, const void* x, const void* y, int ldy, void* dx, int samples, int hw, int c, int xdtype,
+                     int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act, float leak,
+                     float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* ---------------------------------------------------------------- spectral norm
  * spectral_normed_weight (mnist/sn.py:17-75 == cifar10/common/ops/sn.py), one power iteration.
@@ -225,14 +236,14 @@ int rcgan_adam_tf(float* p, const float* g, float* m, float* v, long numel, floa
  *
  * rcgan_bn_infer_bwd: backward of y = act(scale*(x - moving_mean)*rsqrt(moving_var + eps) + offset) with respect to x only
  *   (model.py:733-757 runs the norms with train=False): dx (=|+=) dy * act'(y) * scale[label] * save[c + ch].
- *   `save` is what rcgan_bn_fwd(train = 0) wrote; ws: 2*c floats.
+ *   `save` is what rcgan_bn_fwd(train = 0) wrote; ws: 2*c floats; ldy: row stride of dy / y (c, or a fused concat's width).
  * rcgan_recover_mse (model.py:538-541): sq[r,j] = mean_p (actual[r,p] - sample[r*k + j, p])^2,
  *   loss_acc[0] += (1/R) sum_r sum_j sq[r,j] * y_rec[r,j];   dsample (=) (2/npix) (sample - actual) y_rec[r,j] / R;
  *   dyrec[r,j] (=) sq[r,j] / R.   fp32; any output may be NULL.
  * rcgan_sgd: tf.train.GradientDescentOptimizer (model.py:612-617): p -= lr * grad_scale * g. */
-int rcgan_bn_infer_bwd(const void* dy, const void* y, void* dx, int samples, int hw, int c, int dtype, const float* scale,
-                       const int* labels, const float* save, int act, float leak, int accumulate_dx, void* ws, size_t ws_bytes,
-                       void* stream);
+int rcgan_bn_infer_bwd(const void* dy, const void* y, int ldy, void* dx, int samples, int hw, int c, int dtype,
+                       const float* scale, const int* labels, const float* save, int act, float leak, int accumulate_dx, void* ws,
+                       size_t ws_bytes, void* stream);
 int rcgan_recover_mse(const float* sample, const float* actual, const float* y_rec, int R, int k, int npix, float* loss_acc,
                       float* sq, float* dsample, float* dyrec, void* stream);
 int rcgan_sgd(float* p, const float* g, long numel, float lr, float grad_scale, void* stream);

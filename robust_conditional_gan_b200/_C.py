@@ -67,7 +67,11 @@ _SIGS = {
                              P, P, c_size_t, P]),
     'rcgan_bn_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_int,
                              c_int, P, c_size_t, P]),
-    'rcgan_bn_infer_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
+    'rcgan_bn_infer_bwd': (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
+    'rcgan_bn_fwd_cat': (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_float, c_int, c_float, c_int, c_float,
+                                 P, P, P, P, c_size_t, P]),
+    'rcgan_bn_bwd_cat': (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_int,
+                                 c_int, P, c_size_t, P]),
     'rcgan_recover_mse': (c_int, [P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
     'rcgan_sgd': (c_int, [P, P, c_long, c_float, c_float, P]),
     'rcgan_sn_save_floats': (c_size_t, [c_int, c_int]),

@@ -56,6 +56,7 @@ template <typename T, int V> __device__ __forceinline__ void store_vec(T* p, con
 
 struct Geo {
   int rows, c, hw;
+  int ldy;         // row stride of y / dy (the normalised side): c, or the padded width of a fused label concat
   int V;           // channels per thread-vector (4 or 1)
   int cg;          // channel vectors = c / V
   int LC, LR;      // thread layout: LC channel lanes x LR row lanes = 256
@@ -65,7 +66,7 @@ struct Geo {
 
 Geo make_geo(int samples, int hw, int c, bool per_sample, int vmax = 4) {
   Geo g;
-  g.rows = samples * hw; g.c = c; g.hw = hw;
+  g.rows = samples * hw; g.c = c; g.hw = hw; g.ldy = c;
   g.V = (vmax == 8 && c % 8 == 0) ? 8 : ((c % 4 == 0) ? 4 : 1);   // 16-byte vectors when both x and y are bf16
   g.cg = c / g.V;
   int lc = 1;
@@ -191,12 +192,20 @@ template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, Geo g,
                                                        const float* __restrict__ scale, const float* __restrict__ offset,
                                                        const int* __restrict__ labels, const float* __restrict__ save,
-                                                       int act, float leak) {
+                                                       int act, float leak, const float* __restrict__ yb, int c2) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
-  if (cv >= g.cg) return;
   const int r0 = blockIdx.y * g.chunk_rows, r1 = min(g.rows, r0 + g.chunk_rows);
+  if (yb && blockIdx.x == 0) {
+    // fused conv_cond_concat (mnist/ops.py:46-51): channels [c, c + c2) of every output row carry the sample's label vector
+    // (the padding up to ldy stays zero from allocation)
+    for (int i = threadIdx.x; i < (r1 - r0) * c2; i += 256) {
+      const int r = r0 + i / c2, j = i - (i / c2) * c2;
+      y[(size_t)r * g.ldy + g.c + j] = from_f<TY>(yb[(size_t)(r / g.hw) * c2 + j]);
+    }
+  }
+  if (cv >= g.cg) return;
   const int ch = cv * V;
   const size_t tab = (size_t)(labels ? labels[r0 / g.hw] : 0) * g.c + ch;
   float a[V], b[V];
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
       load_vec<TX, V>(xp + (size_t)r * g.c, v);
 #pragma unroll
       for (int k = 0; k < V; k++) v[k] = fmaxf(fmaf(v[k], a[k], b[k]), 0.f);
-      store_vec<TY, V>(yp + (size_t)r * g.c, v);
+      store_vec<TY, V>(yp + (size_t)r * g.ldy, v);
     }
   } else {
 #pragma unroll 4
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
       load_vec<TX, V>(xp + (size_t)r * g.c, v);
 #pragma unroll
       for (int k = 0; k < V; k++) v[k] = act_fwd(fmaf(v[k], a[k], b[k]), act, leak);
-      store_vec<TY, V>(yp + (size_t)r * g.c, v);
+      store_vec<TY, V>(yp + (size_t)r * g.ldy, v);
     }
   }
 }
@@ -247,10 +256,10 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restric
 #pragma unroll 4
     for (int r = r0 + lr; r < r1; r += g.LR) {
       float vd[V], vx[V], vy[V];
-      size_t o = (size_t)r * g.c + (size_t)cv * V;
-      load_vec<TY, V>(dy + o, vd);
+      const size_t o = (size_t)r * g.c + (size_t)cv * V, oy = (size_t)r * g.ldy + (size_t)cv * V;
+      load_vec<TY, V>(dy + oy, vd);
       load_vec<TX, V>(x + o, vx);
-      if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + o, vy);
+      if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + oy, vy);
 #pragma unroll
       for (int i = 0; i < V; i++) {
         float gg = vd[i];
@@ -366,11 +375,11 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
   }
 #pragma unroll 2
   for (int r = r0 + lr; r < r1; r += g.LR) {
-    const size_t off = (size_t)r * g.c + ch;
+    const size_t off = (size_t)r * g.c + ch, offy = (size_t)r * g.ldy + ch;
     float vd[V], vx[V], vy[V], o[V];
-    load_vec<TY, V>(dy + off, vd);
+    load_vec<TY, V>(dy + offy, vd);
     load_vec<TX, V>(x + off, vx);
-    if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + off, vy);
+    if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + offy, vy);
     if (accumulate) load_vec<TY, V>(dx + off, o);
 #pragma unroll
     for (int k = 0; k < V; k++) {
@@ -429,11 +438,12 @@ extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
     if ((V) == 4) { constexpr int VV = 4; __VA_ARGS__; } else { constexpr int VV = 1; __VA_ARGS__; }     \
   }
 
-extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
-                            const float* offset, const int* labels, float eps, int act, float leak, int train,
-                            float decay, float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes,
-                            void* stream) {
+static int bn_fwd_impl(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
+                       const float* offset, const int* labels, float eps, int act, float leak, int train, float decay,
+                       float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream, int ldy,
+                       const float* yb, int c2) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "bn_fwd: bad shape");
+  RCGAN_CHECK_ARG(ldy >= c + c2 && (ldy == c || ldy % 8 == 0) && c2 >= 0 && (c2 == 0 || yb), "bn_fwd: bad concat geometry");
   if (int e = check_types(xdtype, ydtype, "bn_fwd")) return e;
   RCGAN_CHECK_ARG(x && y && scale && offset && save, "bn_fwd: null pointer");
   RCGAN_CHECK_ARG((long)samples * hw * c < 2147483647L, "bn_fwd: too large");
@@ -453,22 +463,41 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
     RCGAN_LAUNCH_CHECK("bn_infer_stats");
   }
   // streaming geometry: 16-byte vectors when x and y are both bf16
-  const Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
-  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_apply_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TX*)x, (TY*)y, ga, scale, offset, labels, save, act, leak));
+  Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
+  ga.ldy = ldy;
+  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_apply_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TX*)x, (TY*)y, ga, scale, offset, labels, save, act, leak, c2 > 0 ? yb : (const float*)nullptr, c2));
   RCGAN_LAUNCH_CHECK("bn_apply");
   return 0;
 }
 
-extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
-                            int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
-                            float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
-                            size_t ws_bytes, void* stream) {
+extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
+                            const float* offset, const int* labels, float eps, int act, float leak, int train,
+                            float decay, float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes,
+                            void* stream) {
+  return bn_fwd_impl(x, y, samples, hw, c, xdtype, ydtype, scale, offset, labels, eps, act, leak, train, decay, moving_mean,
+                     moving_var, save, ws, ws_bytes, stream, c, nullptr, 0);
+}
+
+extern "C" int rcgan_bn_fwd_cat(const void* x, void* y, int ldy, const float* yb, int c2, int samples, int hw, int c, int xdtype,
+                                int ydtype, const float* scale, const float* offset, const int* labels, float eps, int act,
+                                float leak, int train, float decay, float* moving_mean, float* moving_var, float* save,
+                                void* ws, size_t ws_bytes, void* stream) {
+  return bn_fwd_impl(x, y, samples, hw, c, xdtype, ydtype, scale, offset, labels, eps, act, leak, train, decay, moving_mean,
+                     moving_var, save, ws, ws_bytes, stream, ldy, yb, c2);
+}
+
+static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
+                       int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
+                       float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
+                       size_t ws_bytes, void* stream, int ldy) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0 && n_labels > 0, "bn_bwd: bad shape");
+  RCGAN_CHECK_ARG(ldy >= c && (ldy == c || ldy % 8 == 0), "bn_bwd: bad dy/y row stride");
   if (int e = check_types(xdtype, ydtype, "bn_bwd")) return e;
   RCGAN_CHECK_ARG(dy && x && dx && scale && save && dscale && doffset, "bn_bwd: null pointer");
   RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y, "bn_bwd: activation needs y");
   cudaStream_t st = as_stream(stream);
   Geo g = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? stats_vmax() : 4);
+  g.ldy = ldy;
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
@@ -478,17 +507,34 @@ extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* 
                                                             accumulate_param);
   RCGAN_LAUNCH_CHECK("bn_bwd_finalize");
   const float* AB = (const float*)ws + (size_t)2 * g.nchunk * c;
-  const Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
+  Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
+  ga.ldy = ldy;
   BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
                                         leak, accumulate_dx));
   RCGAN_LAUNCH_CHECK("bn_bwd_dx");
   return 0;
 }
 
-extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, void* dx, int samples, int hw, int c, int dtype, const float* scale,
-                                  const int* labels, const float* save, int act, float leak, int accumulate_dx, void* ws,
-                                  size_t ws_bytes, void* stream) {
-  RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "bn_infer_bwd: bad shape");
+extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
+                            int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
+                            float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
+                            size_t ws_bytes, void* stream) {
+  return bn_bwd_impl(dy, x, y, dx, samples, hw, c, xdtype, ydtype, scale, labels, n_labels, save, act, leak, dscale, doffset,
+                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, c);
+}
+
+extern "C" int rcgan_bn_bwd_cat(const void* dy, const void* x, const void* y, int ldy, void* dx, int samples, int hw, int c,
+                                int xdtype, int ydtype, const float* scale, const int* labels, int n_labels, const float* save,
+                                int act, float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param,
+                                void* ws, size_t ws_bytes, void* stream) {
+  return bn_bwd_impl(dy, x, y, dx, samples, hw, c, xdtype, ydtype, scale, labels, n_labels, save, act, leak, dscale, doffset,
+                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, ldy);
+}
+
+extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, int ldy, void* dx, int samples, int hw, int c, int dtype,
+                                  const float* scale, const int* labels, const float* save, int act, float leak,
+                                  int accumulate_dx, void* ws, size_t ws_bytes, void* stream) {
+  RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0 && ldy >= c && (ldy == c || ldy % 8 == 0), "bn_infer_bwd: bad shape");
   RCGAN_CHECK_ARG(dtype == RCGAN_F32 || dtype == RCGAN_BF16, "bn_infer_bwd: bad dtype");
   RCGAN_CHECK_ARG(dy && dx && scale && save && (act == RCGAN_ACT_NONE || y), "bn_infer_bwd: null pointer");
   RCGAN_CHECK_ARG(ws && ws_bytes >= (size_t)2 * c * sizeof(float), "bn_infer_bwd: workspace too small");
@@ -497,7 +543,8 @@ extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, void* dx, int s
   // (c2 = c3 = 0; its x operand is only multiplied by 0 -- dy stands in for it)
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)2 * c * sizeof(float), st);
   if (e != cudaSuccess) { rcgan_set_error("bn_infer_bwd: memset failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
-  const Geo ga = make_geo(samples, hw, c, labels != nullptr, dtype == RCGAN_BF16 ? 8 : 4);
+  Geo ga = make_geo(samples, hw, c, labels != nullptr, dtype == RCGAN_BF16 ? 8 : 4);
+  ga.ldy = ldy;
   BN_DISPATCH(dtype, dtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy,
                                              (const TX*)dy, (const TY*)y, (TY*)dx, ga, scale, labels, save, (const float*)ws, act,
                                              leak, accumulate_dx));

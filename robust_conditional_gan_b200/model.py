@@ -133,15 +133,15 @@ class DCGAN(object):
             s_w2, s_w4 = int(s_w / 2), int(s_w / 4)
             B = self.batch_size
             z = ops.concat_label(z, y)
-            h0 = self.g_bn0(ops.linear(z, self.gfc_dim, 'g_h0_lin', pre_norm=self.pre_norm_fp32), train=train, fuse_act='relu')
-            h0 = ops.concat_label(h0, y)
+            # (the concat([h, y]) / conv_cond_concat after g_bn0 and g_bn2 is written by the norm's apply pass itself)
+            h0 = self.g_bn0(ops.linear(z, self.gfc_dim, 'g_h0_lin', pre_norm=self.pre_norm_fp32), train=train, fuse_act='relu',
+                            concat_y=y)
             h1 = self.g_bn1(ops.linear(h0, self.gf_dim * 2 * s_h4 * s_w4, 'g_h1_lin', pre_norm=self.pre_norm_fp32), train=train,
                             fuse_act='relu')
             h1 = h1.view([B, s_h4, s_w4, self.gf_dim * 2])
             h1 = ops.conv_cond_concat(h1, y)
             h2 = self.g_bn2(ops.deconv2d(h1, [B, s_h2, s_w2, self.gf_dim * 2], name='g_h2', pre_norm=self.pre_norm_fp32), train=train,
-                            fuse_act='relu')
-            h2 = ops.conv_cond_concat(h2, y)
+                            fuse_act='relu', concat_y=y)
             return ops.deconv2d(h2, [B, s_h, s_w, self.c_dim], name='g_h3', fuse_act='sigmoid')
 
     def gen_sampler(self, z, y=None):

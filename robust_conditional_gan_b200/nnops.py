@@ -307,8 +307,11 @@ class BatchNormOp(Op):
     """y = act(BN(x)).  labels None: tf.contrib.layers.batch_norm (mnist/ops.py:30-44), scale/offset [c];
     labels int32 [n]: cond_batchnorm (cifar10/common/ops/normalization.py:27-59), tables [n_labels,c]."""
 
-    def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2, groups=1):
-        """groups > 1: the batch is `groups` equal sample ranges with INDEPENDENT batch statistics (the reference's separate
+    def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2, groups=1,
+                 concat_y=None):
+        """concat_y (fp32 [n, c2]): the output is concat([act(BN(x)), y broadcast over H, W]) -- the generator's
+        conv_cond_concat / concat right after each norm (mnist/model.py:714-728) -- written in the same pass.
+        groups > 1: the batch is `groups` equal sample ranges with INDEPENDENT batch statistics (the reference's separate
         discriminator calls on the real and on the generated batch, mnist/model.py:150-207, run here as one pass)."""
         prog = cur()
         n, h, w = spatial(x)
@@ -320,7 +323,14 @@ class BatchNormOp(Op):
         self.moving, self.train, self.eps, self.decay = moving, train, eps, decay
         self.act, self.leak = ACT[act], leak
         assert x.grad_dtype == prog.act_dtype or x.dtype == x.grad_dtype
-        self.y = prog.new(x.shape, x.grad_dtype)
+        self.cat = concat_y
+        if concat_y is None:
+            self.y = prog.new(x.shape, x.grad_dtype)
+            self.c2 = 0
+        else:
+            assert groups == 1 and concat_y.dtype == _C.F32 and concat_y.shape[0] == n and concat_y.ld == concat_y.c
+            self.c2 = concat_y.c
+            self.y = prog.new(tuple(x.shape[:-1]) + (x.c + self.c2,), x.grad_dtype, ld=round_up(x.c + self.c2, 8))
         self.save = [torch.zeros(2 * x.c, dtype=torch.float32, device=prog.device) for _ in range(groups)]
         self.inputs, self.outputs = (x, scale, offset), (self.y,)
         self.ws_bytes = _C.load().rcgan_bn_workspace(self.samples, self.hw, self.c)
@@ -335,6 +345,10 @@ class BatchNormOp(Op):
             self.claim(self.scale), self.claim(self.offset)
         elif needs(self.y):
             self.dummy = torch.zeros(2 * self.n_labels * self.c, dtype=torch.float32, device=prog.device)
+        self.dx_dummy = None
+        if self.cat is not None and needs(self.y) and not nx:
+            # parameter gradients only: with a concat output dx cannot alias y.grad (different row stride)
+            self.dx_dummy = torch.zeros(self.x.data.numel(), dtype=self.y.data.dtype, device=prog.device)
 
     def _off(self, ptr, g, esz):
         """pointer to sample range g of a [groups*samples*hw, c] buffer"""
@@ -344,6 +358,11 @@ class BatchNormOp(Op):
         mm = mv = None
         if self.moving is not None:
             mm, mv = dp(self.moving[0]), dp(self.moving[1])
+        if self.cat is not None:
+            call('rcgan_bn_fwd_cat', dp(self.x), dp(self.y), self.y.ld, dp(self.cat), self.c2, self.samples, self.hw, self.c,
+                 self.x.dtype, self.y.dtype, dp(self.scale), dp(self.offset), dp(self.labels), self.eps, self.act, self.leak,
+                 1 if self.train else 0, self.decay, mm, mv, self.save[0].data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+            return
         xs, ys = self.x.data.element_size(), self.y.data.element_size()
         for g in range(self.groups):
             call('rcgan_bn_fwd', self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), self.samples, self.hw, self.c,
@@ -360,7 +379,7 @@ class BatchNormOp(Op):
             if nx:
                 ys, gs = self.y.data.element_size(), self.y.grad.element_size()
                 for g in range(self.groups):
-                    call('rcgan_bn_infer_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.y), g, ys),
+                    call('rcgan_bn_infer_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.y), g, ys), self.y.ld,
                          self._off(gp(self.x), g, self.x.grad.element_size()), self.samples, self.hw, self.c, self.y.dtype,
                          dp(self.scale), dp(self.labels), self.save[g].data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
                          prog.ws.bytes, stream_ptr())
@@ -370,6 +389,12 @@ class BatchNormOp(Op):
             accp = 0
         else:
             dsc, dof, accp = gp(self.scale), gp(self.offset), 1
+        if self.cat is not None:
+            dxp, accx = (gp(self.x), self.acc_x) if nx else (self.dx_dummy.data_ptr(), 0)
+            call('rcgan_bn_bwd_cat', gp(self.y), dp(self.x), dp(self.y), self.y.ld, dxp, self.samples, self.hw, self.c, self.x.dtype,
+                 self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels, self.save[0].data_ptr(), self.act, self.leak, dsc, dof,
+                 accx, accp, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+            return
         xs, ys, gs = self.x.data.element_size(), self.y.data.element_size(), self.y.grad.element_size()
         for g in range(self.groups):
             if not nx:

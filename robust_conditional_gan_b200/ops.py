@@ -35,7 +35,7 @@ class batch_norm(object):
         self.momentum = momentum
         self.name = name
 
-    def __call__(self, x, train=True, fuse_act=None, track_moving=True, groups=1):
+    def __call__(self, x, train=True, fuse_act=None, track_moving=True, groups=1, concat_y=None):
         c = x.shape[-1]
         with S.variable_scope(self.name):
             beta = S.get_variable('beta', [c], _const(0.0))
@@ -44,7 +44,9 @@ class batch_norm(object):
             mv = S.get_variable('moving_variance', [c], _const(1.0), trainable=False)
         moving = (mm, mv) if (track_moving or not train) else None
         # groups: equal sample ranges normalised with their own batch statistics (one pass over [real; fake])
-        return BatchNormOp(x, gamma, beta, None, moving, train, self.epsilon, self.momentum, fuse_act, groups=groups).y
+        # concat_y: the conv_cond_concat / concat([h, y]) that follows the norm in the generator, written in the same pass
+        return BatchNormOp(x, gamma, beta, None, moving, train, self.epsilon, self.momentum, fuse_act, groups=groups,
+                           concat_y=concat_y).y
 
 
 def conv_cond_concat(x, y):

@@ -68,6 +68,44 @@ def test_bn_fwd_bwd(lib, samples, hw, c, act, xdt, dtype):
 
 
 @pytest.mark.parametrize('xdt,dtype', PAIRS)
+@pytest.mark.parametrize('samples,hw,c,c2', [(8, 196, 128, 10), (16, 1, 1024, 10), (5, 49, 64, 3)])
+def test_bn_with_fused_label_concat(lib, samples, hw, c, c2, xdt, dtype):
+    """rcgan_bn_fwd_cat / rcgan_bn_bwd_cat: concat([relu(BN(x)), y broadcast]) written by the norm itself (generator,
+    mnist/model.py:714-728), padding untouched, backward ignoring the label channels' gradient."""
+    g = torch.Generator().manual_seed(2)
+    td = TD[dtype]
+    ld = (c + c2 + 7) // 8 * 8
+    x = (torch.randn(samples, hw, c, generator=g) + 1).to(TD[xdt]).float()
+    yb = torch.randn(samples, c2, generator=g)
+    dyfull = torch.randn(samples, hw, ld, generator=g).to(td).float()
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g)
+    xr = x.double().requires_grad_(True); gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+    y0, mean, var = O.batch_norm_train(xr, gr, br)
+    yr = torch.relu(y0)
+    yr.backward(dyfull[..., :c].double())
+    xd, dyd = dev(x, TD[xdt]), dev(dyfull, td)
+    y = torch.full((samples, hw, ld), 7.0, device='cuda', dtype=td)
+    save = torch.zeros(2 * c, device='cuda')
+    nb = lib.rcgan_bn_workspace(samples, hw, c)
+    ws = ws_buf(nb)
+    call('rcgan_bn_fwd_cat', xd.data_ptr(), y.data_ptr(), ld, keep(dev(yb)), c2, samples, hw, c, xdt, dtype, keep(dev(gamma)),
+         keep(dev(beta)), None, 1e-5, _C.ACT_RELU, 0.0, 1, 0.9, None, None, save.data_ptr(), ws.data_ptr(), nb, st())
+    assert relerr(y[..., :c].float(), yr) < TOL[dtype]
+    lab = yb.to(td).float()[:, None, :].expand(samples, hw, c2)
+    assert float((y[..., c:c + c2].float().cpu() - lab).abs().max()) == 0.0
+    if ld > c + c2:
+        assert float((y[..., c + c2:].float() - 7.0).abs().max()) == 0.0        # padding untouched
+    dx = torch.zeros(samples, hw, c, device='cuda', dtype=td)
+    dg, db = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    call('rcgan_bn_bwd_cat', dyd.data_ptr(), xd.data_ptr(), y.data_ptr(), ld, dx.data_ptr(), samples, hw, c, xdt, dtype,
+         keep(dev(gamma)), None, 1, save.data_ptr(), _C.ACT_RELU, 0.0, dg.data_ptr(), db.data_ptr(), 0, 0, ws.data_ptr(), nb, st())
+    tol = TOL[dtype] * (3 if dtype == _C.BF16 else 1)
+    assert relerr(dx.float(), xr.grad) < tol
+    assert relerr(dg, gr.grad) < tol and relerr(db, br.grad) < tol
+
+
+@pytest.mark.parametrize('xdt,dtype', PAIRS)
 @pytest.mark.parametrize('n,hh,c', [(6, 4, 1024), (6, 8, 256), (4, 32, 256), (64, 4, 64)])
 def test_cond_batchnorm(lib, n, hh, c, xdt, dtype):
     g = torch.Generator().manual_seed(2)

@@ -75,7 +75,7 @@ def test_kernels_recover_mse_sgd_and_bn_infer_bwd(lib):
         call('rcgan_bn_fwd', xd.data_ptr(), yd2.data_ptr(), n, hw, c, dtype, dtype, keep(dev(scale)), keep(dev(offset)), None, 1e-5,
              _C.ACT_RELU, 0.0, 0, 0.9, keep(dev(mm)), keep(dev(mv)), save.data_ptr(), ws.data_ptr(), wsb, st())
         assert relerr(yd2.float(), y64.detach()) < tol
-        call('rcgan_bn_infer_bwd', dyd.data_ptr(), yd2.data_ptr(), dxd.data_ptr(), n, hw, c, dtype, keep(dev(scale)), None,
+        call('rcgan_bn_infer_bwd', dyd.data_ptr(), yd2.data_ptr(), c, dxd.data_ptr(), n, hw, c, dtype, keep(dev(scale)), None,
              save.data_ptr(), _C.ACT_RELU, 0.0, 1, ws.data_ptr(), wsb, st())
         assert relerr(dxd.float() - 1.0, x64.grad) < 2 * tol
 
