@@ -34,9 +34,10 @@ def main():
         agg[short(n)][1] += t
     tot = sum(v[1] for v in agg.values())
     print('# %s rows [%d, %d) of %s: %d launches, %.1f us of kernel time (cold-cache, serialised by ncu)' % (label, a, b, sys.argv[1], b - a, tot / 1e3))
-    print('kernel,launches,total_us,share_pct')
+    w = csv.writer(sys.stdout)
+    w.writerow(['kernel', 'launches', 'total_us', 'share_pct'])
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print('%s,%d,%.1f,%.2f' % (k, v[0], v[1] / 1e3, 100 * v[1] / tot))
+        w.writerow([k, v[0], '%.1f' % (v[1] / 1e3), '%.2f' % (100 * v[1] / tot)])
 
 
 if __name__ == '__main__':
