@@ -109,8 +109,13 @@ class Net:
             else:
                 shortcut = conv_shortcut(inputs, output_dim=output_dim, filter_size=1, name=name + '.Shortcut', he_init=False, **kw)
         output = self.Normalize(name + '.N1', inputs, labels=labels, fuse_act='relu')
-        output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, **kw)
-        output = self.Normalize(name + '.N2', output, labels=labels, fuse_act='relu')
+        if 'G.' in name and labels is not None:
+            output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, **kw)
+            output = self.Normalize(name + '.N2', output, labels=labels, fuse_act='relu')
+        else:
+            # D: Normalize is the identity (NORMALIZATION_D = False), so N2 + nonlinearity is a bare relu on Conv1's output:
+            # it rides in Conv1's epilogue instead of a separate pass
+            output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, fuse_act='relu', **kw)
         if resample == 'down' or not FUSE_RESIDUAL:
             output = conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, **kw)
             return AddOp(shortcut, output).y
