@@ -297,6 +297,13 @@ class Program:
                     seen_vars[id(t.base)] = t.base
             op.plan(self)
             op.need = [needs(t) for t in op.inputs]     # frozen: variables are shared across programs
+        # how many ops read each activation (lets a sole reader alias gradient buffers instead of copying, see AddOp)
+        for t in self.tensors:
+            t.n_readers = 0
+        for op in self.ops:
+            for t in op.inputs:
+                if t is not None and not t.is_variable:
+                    t.base.n_readers = getattr(t.base, 'n_readers', 0) + 1
         for t in self.tensors:
             if t.needs_grad and t._grad is None:
                 t._grad = torch.zeros(t._data.numel(), dtype=TORCH_DTYPE[t.grad_dtype], device=self.device)

@@ -890,7 +890,18 @@ class AddOp(Op):
 
     def plan_bwd(self, prog):
         self.acc_a = self.claim(self.a) if self.need[0] else 0
-        self.acc_b = self.claim(self.b) if self.need[1] else 0
+        # d(a + b)/db = identity: when this op is b's ONLY reader, b's gradient IS y's gradient -- alias the buffer instead of
+        # copying it (b's producer runs its backward after this op and only reads it; y's gradient is complete by then)
+        b, y = self.b.base, self.y.base
+        self.alias_b = bool(self.need[1] and needs(self.y) and b is self.b and y is self.y and getattr(b, 'n_readers', 0) == 1
+                            and not b.grad_written and b._grad is not None and y._grad is not None
+                            and b._grad.numel() == y._grad.numel() and b._grad.dtype == y._grad.dtype)
+        if self.alias_b:
+            b._grad = y._grad
+            b.grad_written = True
+            self.acc_b = 0
+        else:
+            self.acc_b = self.claim(self.b) if self.need[1] else 0
 
     def forward(self, prog):
         call('rcgan_add', dp(self.a), dp(self.b), dp(self.y), self.a.numel(), self.a.dtype, stream_ptr())
@@ -901,7 +912,7 @@ class AddOp(Op):
         st = stream_ptr()
         if self.need[0]:
             call('rcgan_copy_acc', gp(self.y), gp(self.a), self.a.numel(), self.a.dtype, self.acc_a, st)
-        if self.need[1]:
+        if self.need[1] and not self.alias_b:
             call('rcgan_copy_acc', gp(self.y), gp(self.b), self.b.numel(), self.b.dtype, self.acc_b, st)
 
 
