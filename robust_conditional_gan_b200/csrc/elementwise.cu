@@ -470,6 +470,48 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ T
   }
 }
 
+// tiled variant: a block owns RB output rows of one sample and first stages the T rows they gather from (one contiguous,
+// coalesced read) in shared memory -- every T row feeds up to kh*kw/s^2 output pixels; the per-pixel version re-fetched them
+// with scattered 4-byte loads (28 us for g_h3's 1024 x 28 x 28 image, ~0.9 TB/s).
+template <typename TO>
+__global__ void __launch_bounds__(256) col2im_tiled_kernel(const float* __restrict__ T, int ldt, const float* __restrict__ bias,
+                                                           TO* __restrict__ x, int h, int w, int cin, int ho, int wo, int kh, int kw,
+                                                           int stride, int pad_t, int pad_l, int ldx, int act, float leak,
+                                                           int accumulate, int RB) {
+  pdl_sync();
+  extern __shared__ float4 tsm4[];
+  float* tsm = reinterpret_cast<float*>(tsm4);
+  const long nb = blockIdx.y;
+  const int iy0 = blockIdx.x * RB, iy1 = min(h, iy0 + RB);
+  int lo = iy0 + pad_t - (kh - 1);
+  const int oy_lo = lo <= 0 ? 0 : lo / stride;
+  const int oy_hi = min(ho - 1, (iy1 - 1 + pad_t) / stride);
+  const int rows = oy_hi - oy_lo + 1;
+  if (rows > 0) {
+    const float4* src = reinterpret_cast<const float4*>(T + ((nb * ho + oy_lo) * wo) * (long)ldt);
+    const int n4 = rows * wo * ldt / 4;                 // ldt % 4 == 0 (checked by the host)
+    for (int i = threadIdx.x; i < n4; i += 256) tsm4[i] = src[i];
+  }
+  __syncthreads();
+  const int per_row = w * cin, total = (iy1 - iy0) * per_row;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int iy = iy0 + i / per_row, rem = i % per_row, ix = rem / cin, ci = rem - ix * cin;
+    float acc = bias ? bias[ci] : 0.f;
+    for (int ky = (iy + pad_t) % stride; ky < kh; ky += stride) {
+      const int oy = (iy + pad_t - ky) / stride;
+      if (iy + pad_t - ky < 0 || oy >= ho) continue;
+      for (int kx = (ix + pad_l) % stride; kx < kw; kx += stride) {
+        const int ox = (ix + pad_l - kx) / stride;
+        if (ix + pad_l - kx < 0 || ox >= wo) continue;
+        acc += tsm[((oy - oy_lo) * wo + ox) * ldt + (ky * kw + kx) * cin + ci];
+      }
+    }
+    acc = act_fwd(acc, act, leak);
+    TO* o = x + ((nb * h + iy) * w + ix) * (long)ldx + ci;
+    *o = from_f<TO>(accumulate ? to_f(*o) + acc : acc);
+  }
+}
+
 __global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ out, int kh, int kw, int cin, int cout,
                              int accumulate) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
@@ -701,15 +743,36 @@ extern "C" int rcgan_col2im(const rcgan_conv_desc* d, const float* T, int ldt, c
   RCGAN_CHECK_ARG(d && T && x && ldt >= d->kh * d->kw * d->cin && d->stride >= 1, "col2im: bad args");
   const long total = (long)d->n * d->h * d->w * d->cin;
   RCGAN_CHECK_ARG(total > 0, "col2im: empty");
+  RCGAN_CHECK_ARG(out_dtype == RCGAN_F32 || out_dtype == RCGAN_BF16, "col2im: bad dtype");
+  // rows per block: the staged T rows (RB/s + (kh-1)/s + 2 of them, wo*ldt floats each) must fit 44 KB of shared memory
+  const size_t row_bytes = (size_t)d->wo * ldt * sizeof(float);
+  int RB = 0;
+  if (ldt % 4 == 0 && (reinterpret_cast<uintptr_t>(T) & 15) == 0 && d->n <= 65535) {
+    for (int rb = 32; rb >= 1; rb /= 2) {
+      const size_t need = (size_t)(rb / d->stride + (d->kh - 1) / d->stride + 2) * row_bytes;
+      if (need <= 44 * 1024) { RB = rb; break; }
+    }
+  }
+  if (RB > 0) {
+    const size_t shb = (size_t)(RB / d->stride + (d->kh - 1) / d->stride + 2) * row_bytes;
+    dim3 grid((d->h + RB - 1) / RB, d->n);
+    if (out_dtype == RCGAN_F32)
+      launch_pdl(col2im_tiled_kernel<float>, grid, 256, shb, as_stream(stream), T, ldt, bias, (float*)x, d->h, d->w, d->cin, d->ho, d->wo,
+                 d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak, accumulate, RB);
+    else
+      launch_pdl(col2im_tiled_kernel<bf16>, grid, 256, shb, as_stream(stream), T, ldt, bias, (bf16*)x, d->h, d->w, d->cin, d->ho, d->wo,
+                 d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak, accumulate, RB);
+    RCGAN_LAUNCH_CHECK("col2im");
+    return 0;
+  }
   if (out_dtype == RCGAN_F32)
     launch_pdl(col2im_kernel<float>, grid_for(total, 256), 256, 0, as_stream(stream), T, ldt, bias, (float*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
                                                                             d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
                                                                             accumulate);
-  else if (out_dtype == RCGAN_BF16)
+  else
     launch_pdl(col2im_kernel<bf16>, grid_for(total, 256), 256, 0, as_stream(stream), T, ldt, bias, (bf16*)x, d->n, d->h, d->w, d->cin, d->ho, d->wo,
                                                                            d->kh, d->kw, d->stride, d->pad_t, d->pad_l, d->ldx, act, leak,
                                                                            accumulate);
-  else { rcgan_set_error("col2im: bad dtype %d", out_dtype); return RCGAN_EBADSHAPE; }
   RCGAN_LAUNCH_CHECK("col2im");
   return 0;
 }
