@@ -1,0 +1,123 @@
+"""Host-side planning logic of the static-program runtime (graph.py / nnops.py) on a CPU-only box: programs are BUILT
+and PLANNED here (buffers on the CPU, library loaded for its host-only shape queries); nothing is launched."""
+import torch
+
+from robust_conditional_gan_b200 import _C, scope as S
+from robust_conditional_gan_b200.graph import Program, VariableStore
+from robust_conditional_gan_b200.nnops import (ActOp, AddOp, BatchNormOp, CastOp, ChannelLossOp, ConvOp, DeconvOp, MeanHWOp,
+                                               SpectralNormOp, Upsample2Op)
+
+DEV = torch.device('cpu')
+
+
+def store_with(**shapes):
+    st = VariableStore(DEV, lambda n: 'g')
+    S.set_store(st, 0)
+    vs = {k: st.get(k, s, lambda sh: torch.randn(sh) * 0.1) for k, s in shapes.items()}
+    return st, vs
+
+
+def test_residual_add_aliases_sole_reader_gradient_and_orders_writers():
+    st, v = store_with(w1=(3, 3, 64, 64), w2=(3, 3, 64, 64), w3=(3, 3, 64, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x = p.input('x', [2, 8, 8, 64], _C.BF16)
+        h = ConvOp(x, v['w1'], None).y
+        r = ActOp(h, 'relu')
+        c = ConvOp(r.y, v['w2'], None).y
+        z = AddOp(h, c)                      # c has one reader (the add); h has two (relu, add)
+        c2 = ConvOp(z.y, v['w3'], None)
+        z2 = AddOp(c2.y, z.y)                # here the SECOND operand (z.y) has two readers -> must not be aliased
+    st.finalize()
+    p.finalize([v['w1'], v['w2'], v['w3']])
+    assert z.alias_b and c.grad.data_ptr() == z.y.grad.data_ptr()
+    assert not z2.alias_b and z2.y.grad.data_ptr() != z.y.grad.data_ptr()
+    # reverse sweep: the add writes h's gradient first (overwrite), the relu's backward then accumulates into it
+    assert z.acc_a == 0 and r.acc_x == 1
+    # parameter gradients always accumulate into the zeroed arena
+    assert c2.acc_w == 1 and c2.acc_x == 1 and z2.acc_b == 0
+
+
+def test_gradients_are_only_planned_for_the_requested_variables():
+    st, v = store_with(wg=(3, 3, 64, 64), wd=(3, 3, 64, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x = p.input('x', [2, 8, 8, 64], _C.BF16)
+        g = ConvOp(x, v['wg'], None)         # "generator"
+        d = ConvOp(g.y, v['wd'], None)       # "discriminator"
+        MeanHWOp(d.y)
+    st.finalize()
+    p.finalize([v['wd']])                    # D step: var_list = discriminator variables only
+    assert d.need[:3] == [False, True, False] and g.need[:3] == [False, False, False]
+    assert g.y.grad is None                  # no buffer is allocated for a gradient nobody needs
+    p2 = Program('t2', DEV, _C.BF16)
+    with p2:
+        x = p2.input('x', [2, 8, 8, 64], _C.BF16)
+        g = ConvOp(x, v['wg'], None)
+        d = ConvOp(g.y, v['wd'], None)
+        m = MeanHWOp(d.y)
+        h32 = CastOp(m.y, _C.F32).y
+        eye = p2.input('eye', [2, 64])
+        wgt = p2.input('w', [2, 2])
+        ChannelLossOp(h32, None, eye, wgt, _C.HINGE_G, 'g_loss')
+    p2.finalize([v['wg']])                   # G step: D is differentiated w.r.t. its INPUT only
+    assert d.need[:3] == [True, False, False] and g.need[:3] == [False, True, False]
+
+
+def test_conv_path_selection_by_shape():
+    st, v = store_with(w_img=(5, 5, 1, 64), w_cat=(5, 5, 11, 64), w_out=(3, 3, 256, 3), w_big=(3, 3, 256, 256), w_up=(3, 3, 256, 256))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        img = p.input('img', [4, 28, 28, 1], _C.BF16)
+        cat = p.new((4, 28, 28, 11), _C.BF16, ld=16)
+        feat = p.input('feat', [4, 16, 16, 256], _C.BF16)
+        a = ConvOp(img, v['w_img'], None, stride=2)      # d_h0_conv: patch-matrix GEMM + scatter dgrad
+        b = ConvOp(cat, v['w_cat'], None, stride=2)      # --concat_y first layer: patch GEMM + implicit-GEMM dgrad pack
+        c = ConvOp(feat, v['w_out'], None)               # G.Output: transposed patch path for the backward
+        d = ConvOp(feat, v['w_big'], None)               # ordinary tensor-core layer
+        up = Upsample2Op(feat)
+        e = ConvOp(up.y, v['w_up'], None, up_op=up)      # UpsampleConv pair
+    st.finalize()
+    p.finalize([])                                       # nothing differentiated: the pair folds onto the small input
+    assert a.patch is not None and a.scatter.ok and a.dpack is None
+    assert b.patch is not None and not b.scatter.ok and b.dpack is not None
+    assert c.patch is None and c.tpatch is not None
+    assert d.patch is None and d.tpatch is None and d.pack is not None
+    assert e.up_op is up and e.folds_upsample()
+    p2 = Program('t2', DEV, _C.BF16)
+    with p2:
+        feat = p2.input('feat', [4, 16, 16, 256], _C.BF16)
+        up = Upsample2Op(feat)
+        e = ConvOp(up.y, v['w_up'], None, up_op=up)
+    p2.finalize([v['w_up']])                             # differentiated: upsample + ordinary conv
+    assert not e.folds_upsample()
+
+
+def test_sliced_channel_loss_zeroes_once_and_grouped_bn_keeps_two_statistics():
+    st, v = store_with(w=(3, 3, 64, 64), gamma=(64,), beta=(64,))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x = p.input('x', [8, 4, 4, 64], _C.BF16)                  # [real; fake], 4 + 4 samples
+        c = ConvOp(x, v['w'], None)
+        bn = BatchNormOp(c.y, v['gamma'], v['beta'], act='lrelu', groups=2)
+        h = CastOp(MeanHWOp(bn.y).y, _C.F32).y
+        V = p.input('V', [10, 64])
+        wr, wf = p.input('wr', [4, 10]), p.input('wf', [4, 10])
+        lr = ChannelLossOp(h, None, V, wr, _C.HINGE_D_REAL, 'real', rows=(0, 4))
+        lf = ChannelLossOp(h, None, V, wf, _C.HINGE_D_FAKE, 'fake', rows=(4, 4))
+    st.finalize()
+    p.finalize([v['w'], v['gamma'], v['beta']])
+    assert bn.groups == 2 and bn.samples == 4 and len(bn.save) == 2
+    # reverse order: the fake term runs first and clears the whole gradient once, both then accumulate their rows
+    assert lf.zero_h and not lr.zero_h and lf.acc_h == 1 and lr.acc_h == 1
+    assert p.loss_names == ['real', 'fake']
+
+
+def test_spectral_norm_ops_batch_only_parameters():
+    st, v = store_with(W=(3, 3, 64, 64), u=(1, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        a = SpectralNormOp(v['W'], v['u'])
+        w2 = CastOp(a.wbar, _C.F32).y                              # a W produced by another op is not available up front
+        b = SpectralNormOp(w2, v['u'], update=False)
+    assert a.batched and not b.batched
