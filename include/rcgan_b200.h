@@ -36,8 +36,14 @@ enum rcgan_loss_mode {
   RCGAN_CE_D_REAL = 3, /* sCE(l,1) */ RCGAN_CE_D_FAKE = 4, /* sCE(l,0) */ RCGAN_CE_G = 5 /* sCE(l,1) */
 };
 
+/* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
+#define RCGAN_ABI_VERSION 2
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
+/* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
+ * e.g. "conv_tc_persist<256,1,3,bf16,multi=0>", "conv_tc<128,3,im2col=1>", "wgrad_tc<128,im2col=1>", "conv_simt".
+ * Test hook: the parity tests assert which instantiation a shape dispatches to. */
+const char* rcgan_last_conv_variant(void);
 /* number of kernels this library has launched in this process (captured graph replays are not re-counted) */
 long rcgan_launch_count(void);
 /* 1 when the library was built for sm_100a and the current device is compute capability 10.x */

@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
+ABI_VERSION = 2        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -32,6 +33,7 @@ DP = POINTER(ConvDesc)
 _SIGS = {
     'rcgan_last_error': (c_char_p, []),
     'rcgan_abi_version': (c_int, []),
+    'rcgan_last_conv_variant': (c_char_p, []),
     'rcgan_launch_count': (c_long, []),
     'rcgan_device_ok': (c_int, []),
     'rcgan_conv_wpack_bytes': (c_size_t, [DP]),
@@ -112,7 +114,18 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RcganError('%s is missing: build it with `python -m robust_conditional_gan_b200.build` or '
                              '__graft_entry__.build(); there is no CPU or PyTorch fallback' % LIB_PATH)
+        from . import build
+        if build.sources_present() and build.needs_build() and os.path.exists(build.NVCC):
+            build.build_library()             # sources changed since the library was built: rebuild, never call a stale ABI
+        if build.sources_present() and build.needs_build():
+            raise RcganError('%s is older than its sources under csrc/ or include/rcgan_b200.h: rebuild it with '
+                             '`python -m robust_conditional_gan_b200.build` (a stale library would be called with the '
+                             'wrong argument layout)' % LIB_PATH)
         lib = ctypes.CDLL(LIB_PATH)
+        lib.rcgan_abi_version.restype = c_int
+        got = lib.rcgan_abi_version()
+        if got != ABI_VERSION:
+            raise RcganError('%s has ABI version %d, this binding needs %d: rebuild the library' % (LIB_PATH, got, ABI_VERSION))
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)       # AttributeError if the symbol is not exported
             fn.restype = res
@@ -123,6 +136,11 @@ def load():
 
 def last_error():
     return load().rcgan_last_error().decode()
+
+
+def last_conv_variant():
+    """kernel variant the last conv entry point launched on this thread (test hook)"""
+    return load().rcgan_last_conv_variant().decode()
 
 
 def call(name, *args):

@@ -17,13 +17,31 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def needs_build():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+def sources_present():
+    return os.path.isdir(CSRC) and any(f.endswith('.cu') for f in os.listdir(CSRC))
+
+
+def source_hash():
+    """sha256 over every source the library is built from (content, not mtime: the snapshot that travels to the GPU box
+    does not have to preserve timestamps)"""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h')))
     deps.append(os.path.join(HERE, '..', 'include', 'rcgan_b200.h'))
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode() + b'\0')
+        h.update(open(d, 'rb').read())
+    h.update(' '.join(FLAGS).encode())
+    return h.hexdigest()
+
+
+STAMP = OUT + '.stamp'
+
+
+def needs_build():
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
+        return True
+    return open(STAMP).read().strip() != source_hash()
 
 
 def build_library(force=False, verbose=False):
@@ -46,6 +64,8 @@ def build_library(force=False, verbose=False):
     r = subprocess.run([NVCC, '-shared', '-o', OUT] + objs + ['-lcudart'], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
+    with open(STAMP, 'w') as f:
+        f.write(source_hash() + '\n')
     with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
         for src, out in log:
             f.write('==== %s\n%s\n' % (src, out))

@@ -29,7 +29,18 @@ bool rcgan_pdl_enabled() {
 extern "C" long rcgan_launch_count(void) { return g_launches.load(); }
 
 extern "C" const char* rcgan_last_error(void) { return g_err; }
-extern "C" int rcgan_abi_version(void) { return 1; }
+extern "C" int rcgan_abi_version(void) { return RCGAN_ABI_VERSION; }
+
+// name of the conv kernel variant the last conv entry point launched on this thread (tests assert which instantiation
+// a shape dispatches to: the persistent tcgen05 variants only engage above tile-count thresholds)
+static thread_local char g_variant[96] = "";
+void rcgan_set_conv_variant(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_variant, sizeof(g_variant), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* rcgan_last_conv_variant(void) { return g_variant; }
 
 extern "C" int rcgan_device_ok(void) {
   int dev = 0;

@@ -10,6 +10,7 @@
 #define RCGAN_NUM_SMS 148
 
 void rcgan_set_error(const char* fmt, ...);
+void rcgan_set_conv_variant(const char* fmt, ...);
 void rcgan_count_launch();  // every kernel launch of this library bumps rcgan_launch_count()
 
 #define RCGAN_CHECK_ARG(cond, ...)            \

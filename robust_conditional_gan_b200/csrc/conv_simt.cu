@@ -616,6 +616,7 @@ static int conv2d_fprop_impl(const rcgan_conv_desc* d, const void* x, const floa
   p.bias = bias; p.act = act; p.leak = leak; p.klen = ((p.K + BK - 1) / BK) * BK;
   if (int e = launch_io<MODE_FPROP>(p, d->dtype, out_dtype, x, w, y, as_stream(stream))) return e;
   RCGAN_LAUNCH_CHECK("conv2d_fprop");
+  rcgan_set_conv_variant("conv_simt");
   if (res) {
     // CUDA-core path (fp32 parity mode, odd shapes): the residual is a separate in-place add over the dense output
     RCGAN_CHECK_ARG(d->ldy == d->cout, "conv2d_fprop_res: the CUDA-core path needs a dense output (ldy == cout)");
@@ -651,6 +652,7 @@ extern "C" int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, cons
   p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate; p.klen = ((p.K + BK - 1) / BK) * BK;
   if (int e = launch_io<MODE_DGRAD>(p, d->dtype, out_dtype, dy, w, dx, as_stream(stream))) return e;
   RCGAN_LAUNCH_CHECK("conv2d_dgrad");
+  rcgan_set_conv_variant("conv_simt");
   return 0;
 }
 
@@ -674,6 +676,7 @@ extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const
   if (d->dtype == RCGAN_F32 ? launch_wgrad_narrow<float>(p, x, dy, dw, accumulate, as_stream(stream))
                             : launch_wgrad_narrow<bf16>(p, x, dy, dw, accumulate, as_stream(stream))) {
     RCGAN_LAUNCH_CHECK("conv2d_wgrad_narrow");
+    rcgan_set_conv_variant("conv_wgrad_narrow");
     return 0;
   }
   int ns = wgrad_splits(p);
@@ -688,5 +691,6 @@ extern "C" int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const
   long mn = (long)p.M * p.N;
   launch_pdl(splitk_reduce_kernel, ceil_div(mn, 256), 256, 0, as_stream(stream), (const float*)ws, dw, mn, ns, accumulate);
   RCGAN_LAUNCH_CHECK("conv2d_wgrad_reduce");
+  rcgan_set_conv_variant("conv_simt");
   return 0;
 }

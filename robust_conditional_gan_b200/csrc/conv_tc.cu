@@ -1093,6 +1093,7 @@ int launch_tc(const TcParams& p, const CUtensorMap& map, const CUtensorMap& amap
   dim3 grid(((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN));
   launch_pdl(conv_tc_kernel<BN, ST, IM2COL>, grid, 192, Cfg<BN, ST>::SMEM, st, p, map, amap);
   RCGAN_LAUNCH_CHECK("conv_tc");
+  rcgan_set_conv_variant("conv_tc<%d,%d,im2col=%d>", BN, ST, (int)IM2COL);
   return 0;
 }
 
@@ -1139,6 +1140,7 @@ int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, 
   if (mp.nprob > 1) launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, true>, grid, 192, C::SMEM, st, mp, map, amaps);
   else launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, false>, grid, 192, C::SMEM, st, mp, map, amaps);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
+  rcgan_set_conv_variant("conv_tc_persist<%d,%d,%d,%s,multi=%d>", BN, MT, ST, sizeof(TO) == 4 ? "f32" : "bf16", mp.nprob > 1 ? 1 : 0);
   return 0;
 }
 
@@ -1377,6 +1379,7 @@ static int launch_wgrad_tc(const WgParams& p, const CUtensorMap& map, const CUte
   }
   launch_pdl(wgrad_tc_kernel<BN, IM2COL>, grid, 192, WgCfg<BN>::SMEM, st, p, map, xmap);
   RCGAN_LAUNCH_CHECK("wgrad_tc");
+  rcgan_set_conv_variant("wgrad_tc<%d,im2col=%d>", BN, (int)IM2COL);
   return 0;
 }
 

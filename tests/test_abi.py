@@ -22,7 +22,9 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for s in syms:
         assert hasattr(lib, s), 'declared but not exported: ' + s
     assert sorted(_C.EXPORTS) == syms, set(_C.EXPORTS) ^ set(syms)
-    assert lib.rcgan_abi_version() == 1
+    assert lib.rcgan_abi_version() == _C.ABI_VERSION
+    hdr = open(os.path.join(ROOT, 'include', 'rcgan_b200.h')).read()
+    assert int(re.search(r'#define RCGAN_ABI_VERSION (\d+)', hdr).group(1)) == _C.ABI_VERSION
 
 
 def test_argument_validation_without_gpu(lib):

@@ -372,7 +372,8 @@ def test_few_output_channel_forward_as_gemm_plus_col2im(lib, shape):
 @pytest.mark.parametrize('shape', [SHAPES[7], (2, 32, 32, 256, 256, 3, 1, 0, 0), (600, 8, 8, 128, 128, 3, 1, 0, 0)])
 def test_fprop_with_fused_residual(lib, shape, dtype):
     """rcgan_conv2d_fprop_res == conv + bias + residual (ResidualBlock's shortcut add, gan_resnet.py:328), bit-identical
-    to the unfused fprop + add sequence; the last shape takes the persistent kernel."""
+    to the unfused fprop + add sequence.  (All three shapes are below the persistent kernel's tile threshold and run the
+    one-tile kernel; the persistent variants are covered by tests/test_gpu_conv_persist.py.)"""
     d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape, dtype)
     n, cout = shape[0], shape[4]
     res = torch.randn(n, ho, wo, cout, generator=torch.Generator().manual_seed(9)).to(TD[dtype])
