@@ -236,10 +236,11 @@ def test_wgrad_at_benchmark_sizes(lib, shape, variant):
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
     torch.cuda.synchronize()
     assert _C.last_conv_variant() == variant
-    assert relerr(dw.cpu(), wr.grad) < 5e-5               # fp32 reference over K ~ 1e5 pixels carries its own ~1e-5
+    assert relerr(dw.cpu(), wr.grad) < 8e-5               # fp32 reference over K ~ 1e5 pixels carries its own ~2e-5
     # fp64 on a slice of the output channels (wgrad cost is linear in cout)
     w64 = wt[..., :16].double().requires_grad_(True)
     O.conv2d(x.double(), w64, s).backward(dy[..., :16].double())
-    assert relerr(dw[..., :16].cpu(), w64.grad) < 2e-5
+    # fp32 accumulation over K = n*ho*wo up to 131072 pixels: sqrt(K) * 2^-24 ~ 2e-5 is the arithmetic's own floor
+    assert relerr(dw[..., :16].cpu(), w64.grad) < 6e-5
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
-    assert relerr(dw[..., :16].cpu(), 2 * w64.grad) < 2e-5
+    assert relerr(dw[..., :16].cpu(), 2 * w64.grad) < 6e-5
