@@ -3,10 +3,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W     # the reference-equivalent CPU path (oracle)
 
-A "step" is one full training iteration of the reference hot loop (mnist/model.py:335-372): 1 discriminator
-step + 2 generator(+confusion) steps; images/sec = real images consumed per second = B / t_iter.
-Workload at N=1 (and per GPU for N>1, weak scaling): BASELINE configs[1], MNIST DCGAN RCGAN-U (learned confusion
-matrix + permutation regulariser), batch 1024, bf16, synthetic 28x28x1.
+A "step" is one full training iteration of the reference hot loop.  Default workload at N=1 (and per GPU for N>1,
+weak scaling): BASELINE configs[3], the CIFAR-10 SN-ResNet RCGAN with projection discriminator, bf16, batch 256 per
+GPU, synthetic 32x32x3 -- the largest single-GPU configuration of BASELINE.json; at N=8 the global batch is 2048
+(configs[4]).  One iteration = gan_resnet.py:919-947 = 1 G step (batch 2B) + 5 D steps (B real + B fake each);
+images/sec = real images consumed per second = 5B / t_iter.  The other configs (`--workload ...`: RCGAN-U
+with learned confusion matrix + permutation classifier, the MNIST DCGAN configs, label recovery) are timed briefly as
+`secondary` records of the same JSON line at N=1.
 """
 import argparse
 import json
@@ -118,25 +121,6 @@ def oracle_iteration_timer(B, flags, threads):
     return step
 
 
-def oracle_iteration_timer_cifar(n, flags, threads):
-    """CIFAR arm of the CPU port: oracle/cifar.py's Trainer, one iteration = 1 G step (batch 2n) + 5 D steps (gan_resnet.py:919-947)."""
-    import torch
-    from oracle import cifar as OC
-    torch.set_num_threads(threads)
-    cfg = OC.default_config(alpha=0.5, **flags)
-    P = OC.init_params(cfg, seed=0, dtype=torch.float32)
-    b = OC.synthetic_batch(n, seed=0, dtype=torch.float32)
-    tr = OC.Trainer(P, cfg)
-
-    def step():
-        t = time.perf_counter()
-        tr.g_step(b, it=1)
-        for _ in range(5):
-            tr.d_step(b, it=1)
-        return time.perf_counter() - t
-    return step
-
-
 def oracle_recover_timer(R, flags, threads):
     """CPU port of one recover_labels step (oracle/mnist.py recover_step)."""
     import torch
@@ -157,35 +141,76 @@ def oracle_recover_timer(R, flags, threads):
     return step
 
 
+STEP_DESC = {'cifar': '1 G step (batch 2B) + 5 D steps (B real + B fake)',
+             'recover': '1 recover_labels step: gen_sampler on 10 B images, mse, SGD on z_recover / y_logit_recover'}
+
+
+def config_of(name, wl, world):
+    """the workload description both arms print (same keys and values: the driver compares them)"""
+    B = wl['batch']
+    return {'workload': name, 'batch_per_gpu': B, 'global_batch': world * B,
+            'step': STEP_DESC.get(wl.get('kind'), '1 D step + 2 G(+C) steps'), 'parallelism': 'dp%d' % world,
+            'l2': 'no explicit flush: one iteration touches > 1 GB of activations/gradients, >> 126 MB L2'}
+
+
+def cpu_sample(wl, cores, timed, warm, budget_s):
+    """The reference-equivalent CPU path (oracle port; TensorFlow 1.5 cannot run here) on a BOUNDED sample of the workload
+    at the workload's own batch.  Returns (images/s, seconds per iteration, description, units timed).
+    CIFAR: one iteration = 1 G step (batch 2B) + 5 D steps; the sample is ONE G step plus `timed` D steps (after `warm`),
+    iteration time = t_G + 5 * mean(t_D).  MNIST / recover: `timed` whole iterations / steps.  Stops early at budget_s."""
+    B = wl['batch']
+    t_start = time.perf_counter()
+    kind = wl.get('kind')
+    if kind == 'cifar':
+        import torch
+        from oracle import cifar as OC
+        torch.set_num_threads(cores)
+        cfg = OC.default_config(alpha=0.5, **wl['flags'])
+        P = OC.init_params(cfg, seed=0, dtype=torch.float32)
+        b = OC.synthetic_batch(B, seed=0, dtype=torch.float32)
+        tr = OC.Trainer(P, cfg)
+        for _ in range(warm):
+            tr.d_step(b, it=1)
+        t = time.perf_counter(); tr.g_step(b, it=1); t_g = time.perf_counter() - t
+        ts = []
+        for _ in range(timed):
+            t = time.perf_counter(); tr.d_step(b, it=1); ts.append(time.perf_counter() - t)
+            if time.perf_counter() - t_start > budget_s:
+                break
+        t_it = t_g + 5 * sum(ts) / len(ts)
+        return 5 * B / t_it, t_it, ('oracle port, fp32, %d threads, tower batch %d (the workload\'s): 1 G step (batch %d) timed once '
+                                    '(%.2f s) + %d timed D steps after %d warm-up (mean %.2f s); iteration = t_G + 5 t_D'
+                                    % (cores, B, 2 * B, t_g, len(ts), warm, sum(ts) / len(ts))), len(ts)
+    if kind == 'recover':
+        R = min(B, 50)
+        step = oracle_recover_timer(R, wl['flags'], cores)
+        per, what = R, 'oracle recover_step at recover_batch_size %d (%d generated images)' % (R, 10 * R)
+    else:
+        step = oracle_iteration_timer(B, wl['flags'], cores)
+        per, what = B, 'oracle iteration (1 D + 2 G steps, literal reference graph incl. its 10 label-wise D calls) at batch %d' % B
+    for _ in range(warm):
+        step()
+    ts = []
+    for _ in range(timed):
+        ts.append(step())
+        if time.perf_counter() - t_start > budget_s:
+            break
+    t_it = sum(ts) / len(ts)
+    return per / t_it, t_it, '%s, fp32, %d threads: %d timed after %d warm-up' % (what, cores, len(ts), warm), len(ts)
+
+
 def run_reference(args, wl):
+    """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference is TF-1.5
+    Python, not installable here), all host threads, same config as our arm; every step is a bounded sample (see cpu_sample)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count()
-    if wl.get('kind') == 'recover':
-        B = 50
-        step = oracle_recover_timer(B, wl['flags'], cores)
-        per_step = B
-        sample = 'oracle recover_step at recover_batch_size %d (%d generated images), fp32, %d threads' % (B, 10 * B, cores)
-    elif wl.get('kind') == 'cifar':
-        B = 8                                # bounded sample: tower batch 8 (the workload's 256 would take minutes per step)
-        step = oracle_iteration_timer_cifar(B, wl['flags'], cores)
-        per_step = 5 * B
-        sample = 'oracle iteration (1 G step at 2n + 5 D steps, SN-ResNet dim 128) at tower batch %d, fp32, %d threads' % (B, cores)
-    else:
-        B = 128                              # bounded sample: one iteration at 1/8 of the workload batch
-        step = oracle_iteration_timer(B, wl['flags'], cores)
-        per_step = B
-        sample = 'oracle iteration (1 D + 2 G steps, literal reference graph) at batch %d, fp32, %d threads' % (B, cores)
-    for _ in range(min(args.warmup, 2)):
-        step()
-    ts = [step() for _ in range(args.steps)]
-    t = sum(ts) / len(ts)
-    v = per_step / t
+    v, t_it, sample, n = cpu_sample(wl, cores, args.steps, min(args.warmup, 2), budget_s=240.0)
     print(json.dumps({
         'impl': 'reference', 'metric': metric_of(wl), 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_step': B},
+        'warmup': args.warmup, 'ms_per_step': t_it * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': config_of(args.workload, wl, max(args.gpus, 1)), 'units_timed': n,
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -398,84 +423,98 @@ class MnistBench:
         return self.m.train_iteration(fetch_losses=False)
 
 
-def run_ours(args, wl):
+def make_bench(wl, precision, world, rank):
+    return {'cifar': CifarBench, 'recover': RecoverBench}.get(wl.get('kind'), MnistBench)(wl['batch'], wl['flags'], precision, world, rank)
+
+
+def time_workload(bench, steps, warmup, world, local, sample_clocks):
+    """W warm-up iterations, then (1) `steps` iterations with inputs resident in HBM, device-timed with CUDA events, and
+    (2) `steps` iterations end to end through the public API (pinned-host inputs copied every step, losses read back).
+    Barrier + synchronize on both sides of each leg, max over ranks."""
     import torch
     import torch.distributed as dist
     from robust_conditional_gan_b200 import _C
-    from robust_conditional_gan_b200.model import DCGAN, default_flags
-    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    B = wl['batch']
     lib = _C.load()
-    bench = {'cifar': CifarBench, 'recover': RecoverBench}.get(wl.get('kind'), MnistBench)(B, wl['flags'], args.precision, world, rank)
-    model = bench
-    # launches per iteration: count once with eager (uncaptured) launches
-    bench.set_graph(False)
-    n0 = lib.rcgan_launch_count()
-    bench.step(True)
-    launches_per_iter = lib.rcgan_launch_count() - n0
-    bench.set_graph(True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    bench.set_graph(False)                   # launches per iteration: count once with eager (uncaptured) launches
+    n0 = lib.rcgan_launch_count()
+    bench.step(True)
+    launches_per_iter = lib.rcgan_launch_count() - n0
+    bench.set_graph(True)
+    for _ in range(max(warmup, 3)):
         bench.step(True)
-    # ---- leg 1: inputs resident in HBM, device-timed
     bench.resident()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local) if sample_clocks else None
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         bench.step(False)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # ---- leg 2: end to end through the public API: pinned-host inputs copied every step, losses read back
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = bench.step(True)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     if world > 1:
         t = torch.tensor([ms, e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+    ms_step = ms / steps
+    return dict(ms_per_step=ms_step, value=world * bench.images_per_step / (ms_step / 1e3),
+                e2e=world * bench.images_per_step * steps / e2e_s, launches_per_iter=launches_per_iter, clocks=clk, losses=out)
+
+
+SECONDARY = ('cifar_rcganu_b256', 'mnist_rcganu_b1024', 'mnist_rcgany_b1024', 'mnist_rcgan_b64')
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    B = wl['batch']
+    bench = make_bench(wl, args.precision, world, rank)
+    r = time_workload(bench, args.steps, args.warmup, world, local, True)
     h2d, d2h = bench.h2d, bench.d2h
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    ms_step = ms / args.steps
-    value = world * bench.images_per_step / (ms_step / 1e3)
     result = {
-        'metric': metric_of(wl), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'metric': metric_of(wl), 'value': r['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'batch_per_gpu': B, 'global_batch': world * B,
-                   'step': {'cifar': '1 G step (batch 2B) + 5 D steps (B real + B fake)',
-                            'recover': '1 recover_labels step: gen_sampler on 10 B images, mse, SGD on z_recover / y_logit_recover'
-                            }.get(wl.get('kind'), '1 D step + 2 G(+C) steps'),
-                   'parallelism': 'dp%d' % world,
-                   'l2': 'no explicit flush: one iteration touches ~1.5 GB of activations/gradients, >> 126 MB L2'},
-        'clocks': clk,
-        'e2e': {'value': world * bench.images_per_step * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': launches_per_iter * args.steps,
-        'losses': {k: round(v, 5) for k, v in out.items()},
+        'config': config_of(args.workload, wl, world),
+        'clocks': r['clocks'],
+        'e2e': {'value': r['e2e'], 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': r['launches_per_iter'] * args.steps,
+        'losses': {k: round(v, 5) for k, v in r['losses'].items()},
     }
+    if wl.get('kind') == 'cifar':
+        # step-level utilisation on the REFERENCE formulation's flops (SURVEY 8d: 15.56 TFLOP per iteration at B=256, incl. the
+        # generator forward of every D step; the folded pool / upsample convs issue fewer) against the sustained bf16 rate
+        tf_iter = 15.56e12 * B / 256
+        result['step_tflops'] = {'algorithmic_tflop_per_iteration': tf_iter / 1e12, 'achieved': tf_iter / (r['ms_per_step'] * 1e-3) / 1e12,
+                                 'peak_sustained': pk['tf_sust'], 'frac': tf_iter / (r['ms_per_step'] * 1e-3) / 1e12 / pk['tf_sust']}
     if world == 1 and not args.no_op_profile:
-        # roofline of the dominant op (timed live, CUDA events, L2 flushed) ...
-        rows = op_profile(model)
-        rf = kernel_roofline(model, rows, pk)
+        # roofline of the dominant kernel (timed live, CUDA events, L2 flushed) ...
+        rows = op_profile(bench)
+        rf = kernel_roofline(bench, rows, pk)
         if rf is not None:
             result['roofline'] = rf
         else:
@@ -486,30 +525,28 @@ def run_ours(args, wl):
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         with open(os.path.join(ROOT, 'gpurun_out', 'op_profile.json'), 'w') as f:
             json.dump(rows, f, indent=1)
-        if wl.get('kind') is None and not args.no_cpu_baseline:
-            result['sampler'] = sampler_bench()
-        # ... and the CPU baseline (oracle port) on a bounded sample of the same workload
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count()
-            if wl.get('kind') == 'recover':
-                step = oracle_recover_timer(50, wl['flags'], cores)
-                step()
-                t = step()
-                result['cpu_baseline'] = {'value': 50 / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                          'sample': '1 warm-up + 1 timed oracle recover_step at recover_batch_size 50 (500 generated images), fp32'}
-            elif wl.get('kind') == 'cifar':
-                nb = 8
-                step = oracle_iteration_timer_cifar(nb, wl['flags'], cores)
-                step()
-                t = step()
-                result['cpu_baseline'] = {'value': 5 * nb / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                          'sample': '1 warm-up + 1 timed oracle iteration (1 G + 5 D steps) at tower batch %d, fp32' % nb}
-            else:
-                step = oracle_iteration_timer(B, wl['flags'], cores)
-                step()
-                t = step()
-                result['cpu_baseline'] = {'value': B / t, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                          'sample': '1 warm-up + 1 timed oracle iteration (1 D + 2 G steps) at batch %d, fp32' % B}
+    del bench
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_secondary:
+        # the other BASELINE configs, timed briefly (same legs, fewer steps); parity of each is in tests/
+        sec = {}
+        for name in SECONDARY:
+            if name == args.workload:
+                continue
+            w2 = WORKLOADS[name]
+            b2 = make_bench(w2, args.precision, 1, 0)
+            r2 = time_workload(b2, 10, 3, 1, local, False)
+            sec[name] = {'value': r2['value'], 'unit': 'images/s', 'ms_per_step': r2['ms_per_step'], 'e2e': r2['e2e'],
+                         'gpu_launches_per_step': r2['launches_per_iter'], 'batch_per_gpu': w2['batch']}
+            del b2
+            torch.cuda.empty_cache()
+        result['secondary'] = sec
+        result['sampler'] = sampler_bench()
+    if world == 1 and not args.no_cpu_baseline:
+        # the CPU baseline (oracle port) on a bounded sample of the same workload at the same batch
+        cores = os.cpu_count()
+        v, t_it, sample, n = cpu_sample(wl, cores, 3, 1, budget_s=45.0)
+        result['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
@@ -521,7 +558,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='mnist_rcganu_b1024', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='cifar_rcgan_b256', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary workload records')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-op-profile', action='store_true', help='skip the per-op roofline pass (clean ncu launch lists)')

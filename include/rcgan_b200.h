@@ -37,13 +37,16 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 2
+#define RCGAN_ABI_VERSION 3
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
  * e.g. "conv_tc_persist<256,1,3,bf16,multi=0>", "conv_tc<128,3,im2col=1>", "wgrad_tc<128,im2col=1>", "conv_simt".
  * Test hook: the parity tests assert which instantiation a shape dispatches to. */
 const char* rcgan_last_conv_variant(void);
+/* every distinct variant launched by any thread since the last reset, ';'-separated (valid until the calling thread's next
+ * call); reset != 0 clears the log afterwards.  Lets a test of a whole training step assert which kernels it ran. */
+const char* rcgan_conv_variant_log(int reset);
 /* number of kernels this library has launched in this process (captured graph replays are not re-counted) */
 long rcgan_launch_count(void);
 /* 1 when the library was built for sm_100a and the current device is compute capability 10.x */

@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 2        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 3        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -34,6 +34,7 @@ _SIGS = {
     'rcgan_last_error': (c_char_p, []),
     'rcgan_abi_version': (c_int, []),
     'rcgan_last_conv_variant': (c_char_p, []),
+    'rcgan_conv_variant_log': (c_char_p, [c_int]),
     'rcgan_launch_count': (c_long, []),
     'rcgan_device_ok': (c_int, []),
     'rcgan_conv_wpack_bytes': (c_size_t, [DP]),
@@ -141,6 +142,11 @@ def last_error():
 def last_conv_variant():
     """kernel variant the last conv entry point launched on this thread (test hook)"""
     return load().rcgan_last_conv_variant().decode()
+
+
+def conv_variant_log(reset=True):
+    """set of conv kernel variants launched since the last reset (test hook)"""
+    return set(v for v in load().rcgan_conv_variant_log(1 if reset else 0).decode().split(';') if v)
 
 
 def call(name, *args):
