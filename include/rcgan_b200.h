@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 3
+#define RCGAN_ABI_VERSION 4
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -113,6 +113,14 @@ int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp
  * this filter, so its backward runs as patch-matrix GEMMs like the few-input-channel convs above; applied to the GEMM's
  * filter gradient (cin/cout swapped) the same call maps it back. */
 int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream);
+/* 3x3 filter folded with a 2x resampling into a 4x4 stride-2 filter (both maps linear; SURVEY section 7: "ConvMeanPool == 4x4-s2
+ * conv and Upsample+3x3 == four 2x2 sub-pixel convs are algorithmic flop reductions, legal for results parity").
+ *   mode 0: ConvMeanPool (cifar10/gan_resnet.py:231-241): meanpool2(conv3x3_SAME(x, w)) == conv4x4_stride2_SAME(x, w4), w4 HWIO
+ *   mode 1: UpsampleConv (cifar10/gan_resnet.py:259-272): conv3x3_SAME(upsample2(x), w) == conv2d_transpose_4x4_stride2(x, w4),
+ *           w4 in conv2d_transpose layout [4,4,cout,cin]
+ * w, dw: [3,3,cin,cout] fp32; w4, dw4: 16*cin*cout fp32.  rcgan_wfold4_bwd is the adjoint: dw (=|+=) fold^T(dw4). */
+int rcgan_wfold4(const float* w, float* w4, int cin, int cout, int mode, void* stream);
+int rcgan_wfold4_bwd(const float* dw4, float* dw, int cin, int cout, int mode, int accumulate, void* stream);
 /* Adjoint of rcgan_im2col: x[n, iy, ix, ci] (=|+=) act(bias[ci] + sum over taps (ky,kx) with (iy + pad_t - ky) % s == 0 ... of
  * T[(n, oy, ox), (ky*kw + kx)*cin + ci]), T fp32 with row stride ldt.  With T = dy[M, cout] * W^T[cout, kh*kw*cin] (one dense
  * GEMM that reads dy once) this is the input gradient of a conv with cin <= 4 -- i.e. the FORWARD of g_h3's

@@ -183,3 +183,22 @@ class TFAdam:
             if n in self.clip:
                 new = new.clamp(-1.0, 1.0)
             P[n] = new
+
+
+# --------------------------------------------------------------------------- 2x resampling folded into the filter
+_FOLD_SETS = {0: [[0], [0, 1], [1, 2], [2]],          # ConvMeanPool: taps k with a - k in {0, 1}
+              1: [[2], [1, 2], [0, 1], [0]]}          # UpsampleConv, conv2d_transpose tap order
+
+
+def fold4(w, mode):
+    """Checker for rcgan_wfold4.  w [3,3,cin,cout] ->
+    mode 0: w4 [4,4,cin,cout] with meanpool2(conv2d(x, w)) == conv2d(x, w4, stride 2)   (cifar10/gan_resnet.py:231-241)
+    mode 1: w4 [4,4,cout,cin] with conv2d(upsample2(x), w) == conv2d_transpose(x, w4, 2h x 2w, stride 2)   (:259-272)."""
+    S = _FOLD_SETS[mode]
+    cin, cout = w.shape[2], w.shape[3]
+    w4 = w.new_zeros((4, 4, cin, cout) if mode == 0 else (4, 4, cout, cin))
+    for a in range(4):
+        for b in range(4):
+            acc = sum(w[k, l] for k in S[a] for l in S[b])
+            w4[a, b] = 0.25 * acc if mode == 0 else acc.t()
+    return w4

@@ -19,6 +19,8 @@ from . import ops as lib_ops
 
 NO_OPS = 'NO_OPS'
 FUSE_RESIDUAL = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL', '0') == '1'
+# 3x3 ConvMeanPool / UpsampleConv as ONE 4x4 stride-2 conv / conv2d_transpose with the folded filter; 0 = A/B switch
+FOLD_RESAMPLE = __import__('os').environ.get('RCGAN_FOLD', '1') == '1'
 Z_DIM, VOCAB_SIZE, EMBEDDING_DIM, IMG_SIZE, IMG_DIM, OUTPUT_DIM = 128, 10, 300, 32, 3, 3072
 N_CRITIC, GEN_BS_MULTIPLE = 5, 2
 
@@ -56,6 +58,9 @@ class Net:
     def ConvMeanPool(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
                      inputs_norm=False, he_init=True, biases=True):
         """:231-241"""
+        if FOLD_RESAMPLE and filter_size == 3 and inputs.shape[1] % 2 == 0 and inputs.shape[2] % 2 == 0:
+            return lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
+                                  update_collection=update_collection, he_init=he_init, biases=biases, fold='pool')
         out = lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
                              update_collection=update_collection, he_init=he_init, biases=biases)
         return Pool2Op(out).y
@@ -72,6 +77,9 @@ class Net:
     def UpsampleConv(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
                      inputs_norm=False, he_init=True, biases=True, pre_norm=False):
         """:259-272"""
+        if FOLD_RESAMPLE and filter_size == 3:
+            return lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
+                                  update_collection=update_collection, he_init=he_init, biases=biases, pre_norm=pre_norm, fold='up')
         up = Upsample2Op(inputs)
         out = up.y
         return lib_ops.Conv2D(out, out.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,

@@ -526,6 +526,60 @@ __global__ void wflip_kernel(const float* __restrict__ w, float* __restrict__ ou
   }
 }
 
+// ---- 3x3 filters folded with a 2x resampling into 4x4 stride-2 filters (hard part 5: algorithmic flop
+// reductions that keep the results -- both maps are linear, so their adjoints give the 3x3 filter gradient back).
+//   mode 0, ConvMeanPool (gan_resnet.py:231-241): meanpool2(conv3x3(x)) == conv4x4_stride2(x, w4), SAME pad_before 1,
+//           w4[a][b][ci][co] = 1/4 * sum over (k, l) with a-k, b-l in {0,1} of w[k][l][ci][co]
+//   mode 1, UpsampleConv (gan_resnet.py:259-272): conv3x3(upsample2(x)) == conv2d_transpose4x4_stride2(x, w4),
+//           w4[a][b][co][ci] (conv2d_transpose filter layout) = sum over k in S[a], l in S[b] of w[k][l][ci][co],
+//           S = {2}, {1,2}, {0,1}, {0}
+__device__ __forceinline__ void fold4_range(int mode, int a, int& lo, int& hi) {
+  if (mode == 0) { lo = a - 1 < 0 ? 0 : a - 1; hi = a > 2 ? 2 : a; }
+  else { lo = a == 0 ? 2 : (a == 1 ? 1 : 0); hi = a <= 1 ? 2 : (a == 2 ? 1 : 0); }
+}
+__global__ void wfold4_kernel(const float* __restrict__ w, float* __restrict__ w4, int cin, int cout, int mode) {
+  pdl_sync();
+  long total = 16L * cin * cout;
+  GRID_STRIDE(i, total) {
+    int a, b, ci, co;
+    long r = i;
+    if (mode == 0) { co = (int)(r % cout); r /= cout; ci = (int)(r % cin); r /= cin; }
+    else { ci = (int)(r % cin); r /= cin; co = (int)(r % cout); r /= cout; }
+    b = (int)(r % 4); a = (int)(r / 4);
+    int klo, khi, llo, lhi;
+    fold4_range(mode, a, klo, khi);
+    fold4_range(mode, b, llo, lhi);
+    float acc = 0.f;
+    for (int k = klo; k <= khi; k++)
+      for (int l = llo; l <= lhi; l++) acc += w[((size_t)(k * 3 + l) * cin + ci) * cout + co];
+    w4[i] = mode == 0 ? 0.25f * acc : acc;
+  }
+}
+__global__ void wfold4_bwd_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int cin, int cout, int mode, int accumulate) {
+  pdl_sync();
+  long total = 9L * cin * cout;
+  GRID_STRIDE(i, total) {      // i indexes dw: [k][l][ci][co]
+    int co = (int)(i % cout);
+    long r = i / cout;
+    int ci = (int)(r % cin); r /= cin;
+    int l = (int)(r % 3), k = (int)(r / 3);
+    float acc = 0.f;
+    for (int a = 0; a < 4; a++) {
+      int klo, khi;
+      fold4_range(mode, a, klo, khi);
+      if (k < klo || k > khi) continue;
+      for (int b = 0; b < 4; b++) {
+        int llo, lhi;
+        fold4_range(mode, b, llo, lhi);
+        if (l < llo || l > lhi) continue;
+        acc += mode == 0 ? dw4[((size_t)(a * 4 + b) * cin + ci) * cout + co] : dw4[((size_t)(a * 4 + b) * cout + co) * cin + ci];
+      }
+    }
+    if (mode == 0) acc *= 0.25f;
+    dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+
 __global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
@@ -781,6 +835,20 @@ extern "C" int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, 
   RCGAN_CHECK_ARG(w && out && kh > 0 && kw > 0 && cin > 0 && cout > 0, "wflip: bad args");
   launch_pdl(wflip_kernel, grid_for((long)kh * kw * cin * cout, 256), 256, 0, as_stream(stream), w, out, kh, kw, cin, cout, accumulate);
   RCGAN_LAUNCH_CHECK("wflip");
+  return 0;
+}
+
+extern "C" int rcgan_wfold4(const float* w, float* w4, int cin, int cout, int mode, void* stream) {
+  RCGAN_CHECK_ARG(w && w4 && cin > 0 && cout > 0 && (mode == 0 || mode == 1), "wfold4: bad args");
+  launch_pdl(wfold4_kernel, grid_for(16L * cin * cout, 256), 256, 0, as_stream(stream), w, w4, cin, cout, mode);
+  RCGAN_LAUNCH_CHECK("wfold4");
+  return 0;
+}
+
+extern "C" int rcgan_wfold4_bwd(const float* dw4, float* dw, int cin, int cout, int mode, int accumulate, void* stream) {
+  RCGAN_CHECK_ARG(dw4 && dw && cin > 0 && cout > 0 && (mode == 0 || mode == 1), "wfold4_bwd: bad args");
+  launch_pdl(wfold4_bwd_kernel, grid_for(9L * cin * cout, 256), 256, 0, as_stream(stream), dw4, dw, cin, cout, mode, accumulate);
+  RCGAN_LAUNCH_CHECK("wfold4_bwd");
   return 0;
 }
 

@@ -950,6 +950,33 @@ class ConcatRowsOp(Op):
                  self.acc_b, st)
 
 
+class FoldWeightOp(Op):
+    """3x3 filter -> the 4x4 stride-2 filter that absorbs a 2x resampling next to the conv (rcgan_wfold4):
+    mode 'pool': ConvMeanPool (cifar10/gan_resnet.py:231-241) = one stride-2 conv, 4/9 of the flops, no full-resolution output;
+    mode 'up':   UpsampleConv (:259-272) = one stride-2 conv2d_transpose on the small input, no upsampled tensor.
+    Both folds are linear; backward is the adjoint on the filter gradient."""
+
+    def __init__(self, w, mode):
+        prog = cur()
+        kh, kw, cin, cout = w.shape
+        assert kh == 3 and kw == 3
+        self.w, self.mode, self.cin, self.cout = w, {'pool': 0, 'up': 1}[mode], cin, cout
+        self.w4 = prog.new((4, 4, cin, cout) if self.mode == 0 else (4, 4, cout, cin), _C.F32)
+        self.inputs, self.outputs = (w,), (self.w4,)
+        prog.add(self)
+
+    def plan_bwd(self, prog):
+        self.acc_w = self.claim(self.w) if self.need[0] else 0
+
+    def forward(self, prog):
+        call('rcgan_wfold4', dp(self.w), dp(self.w4), self.cin, self.cout, self.mode, stream_ptr())
+
+    def backward(self, prog):
+        if not needs(self.w4) or not self.need[0]:
+            return
+        call('rcgan_wfold4_bwd', gp(self.w4), gp(self.w), self.cin, self.cout, self.mode, self.acc_w, stream_ptr())
+
+
 class PreprocessCifarOp(Op):
     """int32 CHW [n,3072] -> 2*(v/256 - .5) (+ dequantisation noise) -> NHWC (cifar10/gan_resnet.py:548-552)."""
 

@@ -18,6 +18,11 @@ import test_gpu_mnist as TM
 pytestmark = pytest.mark.gpu
 
 
+# biases in front of a batch norm: their true gradient is exactly 0 (the norm subtracts the batch mean); in fp32 both sides hold
+# rounding noise of arbitrary direction (the fp64 oracle of the small-batch tests returns < 1e-9 and they are skipped there too)
+ZERO_GRAD = ('d_h1_conv/biases', 'd_h2_conv/biases', 'd_h3_conv/biases', 'g_h0_lin/bias', 'g_h1_lin/bias', 'g_h2/biases')
+
+
 def cosine(a, b):
     a = a.detach().double().cpu().reshape(-1); b = b.detach().double().cpu().reshape(-1)
     return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
@@ -45,6 +50,9 @@ def test_mnist_rcganu_b1024_step_matches_oracle(lib):
         ref = tr.last['d_grads'][v.name]
         if float(ref.norm()) < 1e-9:
             continue
+        if v.name.endswith(ZERO_GRAD):
+            assert float(ref.norm()) < 1e-4 and float(v.grad.norm()) < 1e-2, (v.name, float(ref.norm()), float(v.grad.norm()))
+            continue
         e, c = relerr(v.grad.reshape(ref.shape), ref), cosine(v.grad, ref)
         worst.append((e, c, v.name))
         head = any(t in v.name for t in ('d_h4_lin', 'd_h5_y_lin', 'classifier', 'bn3/gamma'))
@@ -58,6 +66,9 @@ def test_mnist_rcganu_b1024_step_matches_oracle(lib):
     for v in model.g_vars + model.c_vars:
         ref = tr.last['g_grads'][v.name]
         if float(ref.norm()) < 1e-9:
+            continue
+        if v.name.endswith(ZERO_GRAD):
+            assert float(ref.norm()) < 1e-4 and float(v.grad.norm()) < 1e-2, (v.name, float(ref.norm()), float(v.grad.norm()))
             continue
         e, c = relerr(v.grad.reshape(ref.shape), ref), cosine(v.grad, ref)
         worst.append((e, c, v.name))

@@ -353,3 +353,26 @@ def test_preprocess_cifar(lib):
     out = torch.zeros(n, 32, 32, 3, device='cuda')
     call('rcgan_preprocess_cifar', keep(raw.cuda()), keep(dev(noise)), out.data_ptr(), n, _C.F32, st())
     assert maxabs(out, ref) < 1e-6
+
+
+# ----------------------------------------------------------------------------- resampling folded into the filter
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('cin,cout', [(128, 128), (256, 256), (24, 40)])
+def test_wfold4_and_adjoint(lib, mode, cin, cout):
+    """rcgan_wfold4 == oracle fold4 (ConvMeanPool -> 4x4 s2 conv, UpsampleConv -> 4x4 s2 conv2d_transpose; the conv identities
+    themselves are in tests/test_oracle_nn.py), rcgan_wfold4_bwd == its autograd adjoint, overwrite and accumulate"""
+    g = torch.Generator().manual_seed(cin + mode)
+    w = torch.randn(3, 3, cin, cout, generator=g)
+    gw4 = torch.randn((4, 4, cin, cout) if mode == 0 else (4, 4, cout, cin), generator=g)
+    wr = w.double().requires_grad_(True)
+    ref = O.fold4(wr, mode)
+    (ref * gw4.double()).sum().backward()
+    wd, gd = dev(w), dev(gw4)
+    w4 = torch.zeros(16 * cin * cout, device='cuda')
+    call('rcgan_wfold4', wd.data_ptr(), w4.data_ptr(), cin, cout, mode, st())
+    assert relerr(w4.reshape(ref.shape), ref) < 1e-6
+    dw = torch.full((9 * cin * cout,), 2.0, device='cuda')
+    call('rcgan_wfold4_bwd', gd.data_ptr(), dw.data_ptr(), cin, cout, mode, 0, st())
+    assert relerr(dw.reshape(w.shape), wr.grad) < 1e-6
+    call('rcgan_wfold4_bwd', gd.data_ptr(), dw.data_ptr(), cin, cout, mode, 1, st())
+    assert relerr(dw.reshape(w.shape), 2 * wr.grad) < 1e-6

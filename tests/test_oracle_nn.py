@@ -172,3 +172,26 @@ def test_recover_loss_restates_the_reference_formula():
     ya = torch.eye(k, dtype=torch.float64)[torch.tensor([1, 2, 3])]
     acc = float((y_rec.argmax(-1) == torch.tensor([1, 2, 3])).double().mean())
     assert abs(float(OM.zero_one_loss(ya, y_rec)) - (1 - acc)) < 1e-12
+
+
+def test_resampling_folds_into_a_4x4_stride2_filter():
+    """SURVEY section 7 (hard part 5): meanpool2(conv3x3(x)) == conv4x4_s2(x, fold4(w, 0)) and conv3x3(upsample2(x)) ==
+    conv2d_transpose4x4_s2(x, fold4(w, 1)) -- the algebra behind the product's ConvMeanPool / UpsampleConv (gan_resnet.py:231-272),
+    including the filter gradient through the fold."""
+    from oracle.cifar import mean_pool, upsample
+    g = torch.Generator().manual_seed(3)
+    for h, w_ in ((8, 8), (6, 10), (32, 32)):
+        x = torch.randn(2, h, w_, 5, generator=g, dtype=torch.float64)
+        w = torch.randn(3, 3, 5, 7, generator=g, dtype=torch.float64, requires_grad=True)
+        a = mean_pool(O.conv2d(x, w, 1))
+        b = O.conv2d(x, O.fold4(w, 0), 2)
+        assert float((a - b).abs().max()) < 1e-12
+        ga, = torch.autograd.grad(a.square().sum(), w)
+        gb, = torch.autograd.grad(b.square().sum(), w)
+        assert float((ga - gb).abs().max()) < 1e-9
+        a = O.conv2d(upsample(x), w, 1)
+        b = O.conv2d_transpose(x, O.fold4(w, 1), (2 * h, 2 * w_), 2)
+        assert float((a - b).abs().max()) < 1e-12
+        ga, = torch.autograd.grad(a.square().sum(), w)
+        gb, = torch.autograd.grad(b.square().sum(), w)
+        assert float((ga - gb).abs().max()) < 1e-9
