@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 4
+#define RCGAN_ABI_VERSION 5
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -73,6 +73,8 @@ size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d);
 int rcgan_conv_uses_tensor_cores(const rcgan_conv_desc* d, int direction);
 /* w_f32 (optionally scaled by *scale_dev, e.g. 1/sigma) -> bf16 pack (both GEMM layouts) */
 int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const float* scale_dev, void* pack, void* stream);
+/* the same for `count` weights in one launch (all packs of a training step are refreshed at its start) */
+int rcgan_conv_wpack_batched(int count, const rcgan_conv_desc* const* descs, const float* const* w, void* const* packs, void* stream);
 
 /* y = act(conv(x, w) + bias)        bias may be NULL.  out_dtype: storage type of y -- d->dtype, or RCGAN_F32
  * for a bf16 conv whose output feeds a batch norm (kept fp32: the norm's backward cancels catastrophically on

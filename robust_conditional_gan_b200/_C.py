@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 4        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 5        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -40,6 +40,7 @@ _SIGS = {
     'rcgan_conv_wpack_bytes': (c_size_t, [DP]),
     'rcgan_conv_uses_tensor_cores': (c_int, [DP, c_int]),
     'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
+    'rcgan_conv_wpack_batched': (c_int, [c_int, P, P, P, P]),
     'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_upconv2d_pack_bytes': (c_size_t, [DP]),
     'rcgan_upconv2d_fold': (c_int, [DP, P, P, P, P]),

@@ -907,17 +907,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 // F is a transpose of the (cin, cout) plane: 32x32 tiles through shared memory so that both the fp32 reads (cout fastest)
 // and the bf16 writes (cin fastest) are coalesced (the element-per-thread version read with stride cout: 0.95 TB/s on
 // g_h1_lin's 6.4 M weights).  D keeps cout fastest on both sides.  Work items: F tiles first, then 1024-element D chunks.
-__global__ void __launch_bounds__(256) wpack_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                                    bf16* __restrict__ packF, bf16* __restrict__ packD, int taps, int cin, int cout,
-                                                    int kpadF, int kpadD) {
-  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
-  __shared__ float sm[32][33];
+__device__ __forceinline__ void wpack_body(const float* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ packF,
+                                           bf16* __restrict__ packD, int taps, int cin, int cout, int kpadF, int kpadD, int bid,
+                                           int nblocks, float (*sm)[33]) {
   const float sc = scale ? *scale : 1.f;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int cot = (cout + 31) / 32, kt = kpadF / 32;
   const long nFt = (long)taps * cot * kt;
   const long nD = (long)taps * cin * kpadD, nDt = (nD + 1023) / 1024;
-  for (long t = blockIdx.x; t < nFt + nDt; t += gridDim.x) {
+  for (long t = bid; t < nFt + nDt; t += nblocks) {
     if (t < nFt) {
       const int k0 = (int)(t % kt) * 32;
       const long r = t / kt;
@@ -948,6 +946,24 @@ __global__ void __launch_bounds__(256) wpack_kernel(const float* __restrict__ w,
       }
     }
   }
+}
+__global__ void __launch_bounds__(256) wpack_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                                    bf16* __restrict__ packF, bf16* __restrict__ packD, int taps, int cin, int cout,
+                                                    int kpadF, int kpadD) {
+  pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
+  __shared__ float sm[32][33];
+  wpack_body(w, scale, packF, packD, taps, cin, cout, kpadF, kpadD, blockIdx.x, gridDim.x, sm);
+}
+// every weight pack of a program in ONE launch (blockIdx.y = weight): the CIFAR iteration refreshed 153 packs in 153 launches of
+// ~7 us (3.7 % of the iteration); the weights of a step are all known at its start (parameters, spectral-norm outputs, folds)
+constexpr int WPACK_MAX_BATCH = 32;
+struct WpackItem { const float* w; bf16* packF; bf16* packD; int taps, cin, cout, kpadF, kpadD, nblk; };
+struct WpackBatch { WpackItem it[WPACK_MAX_BATCH]; };
+__global__ void __launch_bounds__(256) wpack_batched_kernel(const __grid_constant__ WpackBatch b) {
+  pdl_sync();
+  __shared__ float sm[32][33];
+  const WpackItem& t = b.it[blockIdx.y];
+  if ((int)blockIdx.x < t.nblk) wpack_body(t.w, nullptr, t.packF, t.packD, t.taps, t.cin, t.cout, t.kpadF, t.kpadD, blockIdx.x, t.nblk, sm);
 }
 
 // element-per-thread variant (kept for A/B: RCGAN_WPACK_FLAT=1)
@@ -1223,6 +1239,32 @@ extern "C" int rcgan_conv_wpack(const rcgan_conv_desc* d, const float* w, const 
   int grid = (int)(items < RCGAN_NUM_SMS * 8 ? items : RCGAN_NUM_SMS * 8);
   launch_pdl(wpack_kernel, grid, 256, 0, as_stream(stream), w, scale_dev, pk, pk + g.offD, g.taps, d->cin, d->cout, g.kpadF, g.kpadD);
   RCGAN_LAUNCH_CHECK("conv_wpack");
+  return 0;
+}
+
+extern "C" int rcgan_conv_wpack_batched(int count, const rcgan_conv_desc* const* descs, const float* const* w, void* const* packs,
+                                       void* stream) {
+  RCGAN_CHECK_ARG(count > 0 && descs && w && packs, "conv_wpack_batched: bad args");
+  for (int i0 = 0; i0 < count; i0 += WPACK_MAX_BATCH) {
+    const int n = count - i0 < WPACK_MAX_BATCH ? count - i0 : WPACK_MAX_BATCH;
+    WpackBatch b;
+    int max_blk = 1;
+    for (int k = 0; k < n; k++) {
+      const rcgan_conv_desc* d = descs[i0 + k];
+      RCGAN_CHECK_ARG(d && w[i0 + k] && packs[i0 + k], "conv_wpack_batched: null item %d", i0 + k);
+      if (!(fprop_ok(d) || dgrad_ok(d))) { rcgan_set_error("conv_wpack_batched: item %d has no tensor-core pack", i0 + k); return RCGAN_EUNSUPPORTED; }
+      PackGeo g = pack_geo(d);
+      bf16* pk = reinterpret_cast<bf16*>(packs[i0 + k]);
+      const long items = (long)g.taps * ((d->cout + 31) / 32) * (g.kpadF / 32) + ((long)g.taps * d->cin * g.kpadD + 1023) / 1024;
+      WpackItem& t = b.it[k];
+      t.w = w[i0 + k]; t.packF = pk; t.packD = pk + g.offD; t.taps = g.taps; t.cin = d->cin; t.cout = d->cout;
+      t.kpadF = g.kpadF; t.kpadD = g.kpadD;
+      t.nblk = (int)(items < 2 * RCGAN_NUM_SMS ? items : 2 * RCGAN_NUM_SMS);
+      if (t.nblk > max_blk) max_blk = t.nblk;
+    }
+    launch_pdl(wpack_batched_kernel, dim3(max_blk, n), 256, 0, as_stream(stream), b);
+    RCGAN_LAUNCH_CHECK("conv_wpack_batched");
+  }
   return 0;
 }
 

@@ -92,6 +92,11 @@ def needs(t):
     return t is not None and t.base.needs_grad
 
 
+def is_static_weight(t):
+    """known at program start: a parameter, or computed from parameters only by weight_only ops"""
+    return t.is_variable or getattr(t.base, 'static_weight', False)
+
+
 class Variable(Tensor):
     """A named parameter / state tensor (fp32).  After VariableStore.finalize() `data`, `grad`,
     `m`, `v` are views into the flat per-group arenas."""
@@ -195,6 +200,9 @@ class Op:
     gradient buffer, whether this op is the first writer (overwrite) or a later one (accumulate)."""
     inputs = ()
     outputs = ()
+    # an op whose inputs are parameters only (spectral norm, filter folds): Program.run_forward runs these first, followed by ONE
+    # batched refresh of every tensor-core weight pack, and run_backward runs their backward last
+    weight_only = False
 
     def plan(self, prog):
         ng = any(needs(t) for t in self.inputs)
@@ -235,6 +243,8 @@ class Program:
         self.losses = None          # fp32 [n_losses] device
         self.updates = []           # (dst tensor, src tensor) state assignments applied after backward
         self.packs = {}             # id(weight base) -> bf16 tensor-core weight pack (torch uint8 buffer)
+        self.pack_jobs = []         # (desc, weight tensor, pack buffer) refreshed in one launch at the start of every run
+        self._pack_args = None
         self.finalized = False
 
     def __enter__(self):
@@ -273,6 +283,26 @@ class Program:
             return self.packs[key], False
         self.packs[key] = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         return self.packs[key], True
+
+    def hoist_pack(self, w, desc, buf):
+        """Register the pack of a weight that is known at program start (a parameter or the output of a weight_only op) for the
+        batched refresh (rcgan_conv_wpack_batched); False if the weight is computed mid-program and its user must pack it."""
+        if not is_static_weight(w):
+            return False
+        self.pack_jobs.append((desc, w, buf))
+        return True
+
+    def _refresh_packs(self):
+        if not self.pack_jobs:
+            return
+        if self._pack_args is None:
+            import ctypes
+            n = len(self.pack_jobs)
+            PA = ctypes.c_void_p * n
+            self._pack_args = (n, PA(*[ctypes.addressof(d) for d, _, _ in self.pack_jobs]),
+                               PA(*[w.data.data_ptr() for _, w, _ in self.pack_jobs]), PA(*[b.data_ptr() for _, _, b in self.pack_jobs]))
+        n, descs, ws, packs = self._pack_args
+        call('rcgan_conv_wpack_batched', n, descs, ws, packs, stream_ptr())
 
     def loss_slot(self, name):
         self.loss_names.append(name)
@@ -317,11 +347,20 @@ class Program:
     def run_forward(self):
         call('rcgan_zero', self.losses.data_ptr(), self.losses.numel() * 4, stream_ptr())
         for op in self.ops:
-            op.forward(self)
+            if op.weight_only:
+                op.forward(self)
+        self._refresh_packs()
+        for op in self.ops:
+            if not op.weight_only:
+                op.forward(self)
 
     def run_backward(self):
         for op in reversed(self.ops):
-            op.backward(self)
+            if not op.weight_only:
+                op.backward(self)
+        for op in reversed(self.ops):
+            if op.weight_only:
+                op.backward(self)
 
     def run_updates(self):
         for dst, src in self.updates:

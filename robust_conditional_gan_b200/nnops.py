@@ -4,7 +4,7 @@ import torch
 
 from . import _C
 from ._C import ConvDesc, call, stream_ptr
-from .graph import Op, Tensor, cur, needs, round_up, same_pad
+from .graph import Op, Tensor, cur, is_static_weight, needs, round_up, same_pad
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -116,6 +116,8 @@ class ConvOp(Op):
         # few-channel inputs (cin <= 4): materialise the patch matrix once and run fprop / wgrad as dense GEMMs on it
         self.patch, self.gdesc = make_patch(prog, self.desc, n * ho * wo, self.y.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
+        if self.pack_owner and prog.hoist_pack(w, self.gdesc if self.patch is not None else self.desc, self.pack):
+            self.pack_owner = False          # refreshed with every other pack of the program at its start
         # ... and their input gradient (a 1..3-channel result from a wide dL/dy: d_h0_conv / D.Block.1 in the G step) as one
         # dense GEMM + col2im
         self.scatter = ScatterDgrad(prog, self.desc, self.y.ld) if self.patch is not None else None
@@ -261,6 +263,8 @@ class DeconvOp(Op):
         # run as GEMMs on the patch matrix of dL/dy
         self.patch, self.gdesc = make_patch(prog, self.desc, n * h * wd, x.ld)
         self.pack, self.pack_owner = prog.weight_pack(w, self.gdesc if self.patch is not None else self.desc)
+        if self.pack_owner and prog.hoist_pack(w, self.gdesc if self.patch is not None else self.desc, self.pack):
+            self.pack_owner = False
         self.scatter = ScatterDgrad(prog, self.desc, x.ld) if self.patch is not None else None
         prog.add(self)
 
@@ -547,6 +551,8 @@ class SpectralNormOp(Op):
             prog.add_update(u, self.u_new)
         # parameters only: a W computed by another op of the program is not available at program start
         self.batched = bool(W.is_variable and u.is_variable)
+        self.weight_only = self.batched
+        self.wbar.static_weight = self.batched
 
     def plan_bwd(self, prog):
         self.acc_w = self.claim(self.W) if self.need[0] else 0
@@ -963,6 +969,8 @@ class FoldWeightOp(Op):
         self.w, self.mode, self.cin, self.cout = w, {'pool': 0, 'up': 1}[mode], cin, cout
         self.w4 = prog.new((4, 4, cin, cout) if self.mode == 0 else (4, 4, cout, cin), _C.F32)
         self.inputs, self.outputs = (w,), (self.w4,)
+        self.weight_only = is_static_weight(w)
+        self.w4.static_weight = self.weight_only
         prog.add(self)
 
     def plan_bwd(self, prog):

@@ -100,7 +100,15 @@ def test_cifar_rcgan_b256_steps_match_oracle(lib):
     torch.cuda.synchronize()
     got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
     assert abs(got['gen_wgan'] - float(tr.last['g']['gen_wgan'])) < 2e-2
-    TC.check_grads(model.gen_params + model.c_params, tr.last['g_grads'], 2e-1, 'rcgan G bf16 n=256')
+    # every generator conv bias but G.Output's shifts a channel by a constant that the following conditional batch norms remove
+    # (a 1x1 shortcut / upsampling keeps it constant): the true gradient is exactly 0, the fp32 oracle holds rounding noise there
+    # (the fp64 oracle of tests/test_gpu_cifar.py returns < 1e-10 and check_grads skips them)
+    zero = [v for v in model.gen_params if v.name.endswith('/Biases') and 'G.Output' not in v.name]
+    for v in zero:
+        wg = tr.last['g_grads'][v.name.replace('/Biases', '/Filters')]
+        assert float(tr.last['g_grads'][v.name].norm()) < 1e-3 * float(wg.norm()), v.name
+        assert float(v.grad.norm()) < 2e-2 * float(wg.norm()), (v.name, float(v.grad.norm()), float(wg.norm()))
+    TC.check_grads([v for v in model.gen_params + model.c_params if v not in zero], tr.last['g_grads'], 2e-1, 'rcgan G bf16 n=256')
     glog = _C.conv_variant_log()
     print('D step variants', sorted(dlog)); print('G step variants', sorted(glog))
     for log in (dlog, glog):
