@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 5
+#define RCGAN_ABI_VERSION 6
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -100,6 +100,26 @@ int rcgan_conv2d_fprop_res(const rcgan_conv_desc* d, const void* x, const float*
  * forward of deconv2d (mnist/ops.py:69-92).  bias may be NULL. */
 int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, const float* w, const void* wpack,
                        const float* bias, void* dx, int out_dtype, int act, float leak, int accumulate, void* stream);
+/* Epilogue fusions of the tensor-core conv kernels: element-wise passes of the reference graph that touch exactly the tile
+ * the conv is writing, applied in this order to the bf16 value act(conv + bias) (every pointer may be NULL):
+ *   mask:  value *= act'(mask) -- the backward of a relu / lrelu whose forward OUTPUT is `mask` (laid out like the output):
+ *          the `nonlinearity` in front of a conv (cifar10/gan_resnet.py:199-205, 318-325) differentiated inside the dgrad that
+ *          produces its input gradient, instead of a separate pass over the gradient;
+ *   res:   value += res -- ResidualBlock's `shortcut + output` (:328); res_up = 1 reads res [n, OH/2, OW/2, N] (channel stride
+ *          ld_res) through a nearest-neighbour 2x upsampling, i.e. UpsampleConv_1x1's shortcut (:259-272, 305-309) is added
+ *          without materialising the upsampled tensor.  Not combinable with accumulate;
+ *   out2:  a second output relu(value) with the output's layout (the next block's `nonlinearity(inputs)`, :318).
+ * Each step rounds to bf16 exactly where the separate kernels did, so results are bit-identical to the unfused sequence.
+ * bf16 outputs on the tensor-core path only; the calls fail with RCGAN_EUNSUPPORTED otherwise (no fallback). */
+typedef struct {
+  const void* mask; int mask_act; float mask_leak;
+  const void* res; int res_up; int ld_res;
+  void* out2; int out2_act;
+} rcgan_conv_epilogue;
+int rcgan_conv2d_fprop_ex(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
+                          int act, float leak, const rcgan_conv_epilogue* ep, void* stream);
+int rcgan_conv2d_dgrad_ex(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
+                          int act, float leak, int accumulate, const rcgan_conv_epilogue* ep, void* stream);
 /* dw (=|+=) x^T * dy ;  ws: caller workspace of rcgan_conv2d_wgrad_workspace() bytes */
 size_t rcgan_conv2d_wgrad_workspace(const rcgan_conv_desc* d);
 int rcgan_conv2d_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate,

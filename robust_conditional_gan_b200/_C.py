@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 5        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 6        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -30,6 +30,15 @@ class ConvDesc(ctypes.Structure):
 
 P = c_void_p
 DP = POINTER(ConvDesc)
+
+
+class ConvEpilogue(ctypes.Structure):
+    """mirror of rcgan_conv_epilogue (include/rcgan_b200.h)"""
+    _fields_ = [('mask', c_void_p), ('mask_act', c_int), ('mask_leak', c_float), ('res', c_void_p), ('res_up', c_int),
+                ('ld_res', c_int), ('out2', c_void_p), ('out2_act', c_int)]
+
+
+EP = POINTER(ConvEpilogue)
 _SIGS = {
     'rcgan_last_error': (c_char_p, []),
     'rcgan_abi_version': (c_int, []),
@@ -41,6 +50,8 @@ _SIGS = {
     'rcgan_conv_uses_tensor_cores': (c_int, [DP, c_int]),
     'rcgan_conv_wpack': (c_int, [DP, P, P, P, P]),
     'rcgan_conv_wpack_batched': (c_int, [c_int, P, P, P, P]),
+    'rcgan_conv2d_fprop_ex': (c_int, [DP, P, P, P, P, c_int, c_int, c_float, EP, P]),
+    'rcgan_conv2d_dgrad_ex': (c_int, [DP, P, P, P, P, c_int, c_int, c_float, c_int, EP, P]),
     'rcgan_conv2d_fprop': (c_int, [DP, P, P, P, P, P, c_int, c_int, c_float, P]),
     'rcgan_upconv2d_pack_bytes': (c_size_t, [DP]),
     'rcgan_upconv2d_fold': (c_int, [DP, P, P, P, P]),

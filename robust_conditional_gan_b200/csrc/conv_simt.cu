@@ -595,9 +595,9 @@ int launch_io(const ConvP& p, int dtype, int out_dtype, const void* a, const flo
 
 // Implemented in conv_tc.cu (tcgen05 path); return 1 when they handled the call.
 int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, const void* res, void* y,
-                   int out_dtype, int act, float leak, cudaStream_t st, int* handled);
+                   int out_dtype, int act, float leak, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep);
 int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
-                   int act, float leak, int accumulate, cudaStream_t st, int* handled);
+                   int act, float leak, int accumulate, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep);
 
 int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st,
                    int* handled);
@@ -607,7 +607,7 @@ static int conv2d_fprop_impl(const rcgan_conv_desc* d, const void* x, const floa
   if (int e = check_desc(d, "conv2d_fprop")) return e;
   if (wpack) {
     int handled = 0;
-    int e = rcgan_tc_fprop(d, x, wpack, bias, res, y, out_dtype, act, leak, as_stream(stream), &handled);
+    int e = rcgan_tc_fprop(d, x, wpack, bias, res, y, out_dtype, act, leak, as_stream(stream), &handled, nullptr);
     if (e || handled) return e;
   }
   RCGAN_CHECK_ARG(w, "conv2d_fprop: null fp32 weights");
@@ -643,7 +643,7 @@ extern "C" int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, cons
   if (int e = check_desc(d, "conv2d_dgrad")) return e;
   if (wpack) {
     int handled = 0;
-    int e = rcgan_tc_dgrad(d, dy, wpack, bias, dx, out_dtype, act, leak, accumulate, as_stream(stream), &handled);
+    int e = rcgan_tc_dgrad(d, dy, wpack, bias, dx, out_dtype, act, leak, accumulate, as_stream(stream), &handled, nullptr);
     if (e || handled) return e;
   }
   RCGAN_CHECK_ARG(w, "conv2d_dgrad: null fp32 weights");
@@ -653,6 +653,29 @@ extern "C" int rcgan_conv2d_dgrad(const rcgan_conv_desc* d, const void* dy, cons
   if (int e = launch_io<MODE_DGRAD>(p, d->dtype, out_dtype, dy, w, dx, as_stream(stream))) return e;
   RCGAN_LAUNCH_CHECK("conv2d_dgrad");
   rcgan_set_conv_variant("conv_simt");
+  return 0;
+}
+
+// tensor-core only: the fused epilogues exist in the tcgen05 kernels (rcgan_conv_epilogue_supported tells the caller beforehand)
+extern "C" int rcgan_conv2d_fprop_ex(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y,
+                                     int out_dtype, int act, float leak, const rcgan_conv_epilogue* ep, void* stream) {
+  if (int e = check_desc(d, "conv2d_fprop_ex")) return e;
+  RCGAN_CHECK_ARG(wpack && x && y, "conv2d_fprop_ex: null argument");
+  int handled = 0;
+  int e = rcgan_tc_fprop(d, x, wpack, bias, nullptr, y, out_dtype, act, leak, as_stream(stream), &handled, ep);
+  if (e) return e;
+  if (!handled) { rcgan_set_error("conv2d_fprop_ex: shape has no tensor-core path"); return RCGAN_EUNSUPPORTED; }
+  return 0;
+}
+extern "C" int rcgan_conv2d_dgrad_ex(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx,
+                                     int out_dtype, int act, float leak, int accumulate, const rcgan_conv_epilogue* ep,
+                                     void* stream) {
+  if (int e = check_desc(d, "conv2d_dgrad_ex")) return e;
+  RCGAN_CHECK_ARG(wpack && dy && dx, "conv2d_dgrad_ex: null argument");
+  int handled = 0;
+  int e = rcgan_tc_dgrad(d, dy, wpack, bias, dx, out_dtype, act, leak, accumulate, as_stream(stream), &handled, ep);
+  if (e) return e;
+  if (!handled) { rcgan_set_error("conv2d_dgrad_ex: shape has no tensor-core path"); return RCGAN_EUNSUPPORTED; }
   return 0;
 }
 

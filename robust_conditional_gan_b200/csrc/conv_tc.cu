@@ -39,6 +39,13 @@ struct TcParams {
   float leak;
   int accumulate;
   const void* res;            // fused residual: out = act(conv + bias) + res, res laid out exactly like out (NULL = none)
+  // further epilogue fusions (rcgan_conv_epilogue in the header; bf16 outputs only)
+  int res_up, ld_res;         // res is [n, OH/2, OW/2, N] with channel stride ld_res, read through a nearest-neighbour 2x upsampling
+  const void* mask;           // out = value * act'(mask): the backward of the activation whose OUTPUT is mask (laid out like out)
+  int mask_act;
+  float mask_leak;
+  void* out2;                 // second output act2(final value), laid out like out
+  int out2_act;
   // TMA im2col A loader (one cp.async.bulk.tensor.im2col per K block instead of 1024 cp.async):
   // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
   int im_w_lo, im_h_lo, im_sw, im_sh;
@@ -174,16 +181,20 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
                                             int n0, uint32_t tempty_bar = 0, int bn_lim = BN) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   constexpr int PITCH = BN * (int)sizeof(TO) + 16;
-  static_assert(4 * 32 * PITCH + 1024 <= AVAIL, "staging must fit the drained pipeline buffers");
+  static_assert(4 * 32 * PITCH + 2048 <= AVAIL, "staging must fit the drained pipeline buffers");
   uint8_t* slab = smem + warp * (32 * PITCH);
   unsigned long long* rowoff = reinterpret_cast<unsigned long long*>(smem + 4 * 32 * PITCH) + warp * 32;
+  unsigned long long* rowoff_res = rowoff + 4 * 32;      // offsets into an upsampled-on-the-fly residual (res_up)
   const int m = m0 + warp * 32 + lane;
-  unsigned long long ob = ~0ull;
+  unsigned long long ob = ~0ull, orr = 0;
   if (m < p.M) {
     int b = m % p.MW, r = m / p.MW, a = r % p.MH, n = r / p.MH;
-    ob = ((unsigned long long)(n * p.OH + a * p.oy_mul + p.oy_add) * p.OW + (b * p.ox_mul + p.ox_add)) * p.ld_out;
+    const int oy = a * p.oy_mul + p.oy_add, ox = b * p.ox_mul + p.ox_add;
+    ob = ((unsigned long long)(n * p.OH + oy) * p.OW + ox) * p.ld_out;
+    if (p.res_up) orr = ((unsigned long long)(n * (p.OH >> 1) + (oy >> 1)) * (p.OW >> 1) + (ox >> 1)) * p.ld_res;
   }
   rowoff[lane] = ob;
+  if (p.res_up) rowoff_res[lane] = orr;
   const int ncols = min(bn_lim, p.N - n0);
 #pragma unroll 1
   for (int c0 = 0; c0 < bn_lim; c0 += 32) {
@@ -256,8 +267,70 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
   // the tile is added onto `addsrc` (same layout as out): out itself when accumulating, the residual input when fusing the
   // ResidualBlock's shortcut add (gan_resnet.py:328); both round like the separate add kernel did (bf16 + bf16 in fp32 -> bf16)
   const TO* addsrc = p.accumulate ? out : reinterpret_cast<const TO*>(p.res);
+  const bool up = !p.accumulate && p.res && p.res_up;       // residual read through a 2x nearest-neighbour upsampling
+  const TO* mask = reinterpret_cast<const TO*>(p.mask);
+  TO* out2 = reinterpret_cast<TO*>(p.out2);
   const bool fast = p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0 && ncols >= VEC &&
-                    (reinterpret_cast<uintptr_t>(addsrc) & 15) == 0;
+                    (reinterpret_cast<uintptr_t>(addsrc) & 15) == 0 && (!up || p.ld_res % VEC == 0) &&
+                    (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0;
+  if (sizeof(TO) == 2 && (mask || out2 || up)) {
+    // fused variant of the store loop (bf16 only): mask -> residual / accumulate -> store -> second output
+    const float mleak = p.mask_act == RCGAN_ACT_LRELU ? p.mask_leak : 0.f;
+    if (fast) {
+      const int lpr = ncols / VEC;
+      const int drow = 32 / lpr, dpiece = 32 - drow * lpr;
+      int row = lane / lpr, piece = lane - row * lpr;
+#pragma unroll 2
+      for (int idx = lane; idx < 32 * lpr; idx += 32, row += drow, piece += dpiece) {
+        if (piece >= lpr) { piece -= lpr; row++; }
+        const unsigned long long o = rowoff[row];
+        if (o == ~0ull) continue;
+        uint4 q = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
+        __nv_bfloat162* c = reinterpret_cast<__nv_bfloat162*>(&q);
+        const size_t col = (size_t)n0 + piece * VEC;
+        if (mask) {
+          const uint4 mq = *reinterpret_cast<const uint4*>(mask + o + col);
+          const __nv_bfloat162* mm = reinterpret_cast<const __nv_bfloat162*>(&mq);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float2 fm = __bfloat1622float2(mm[e]), fc = __bfloat1622float2(c[e]);
+            c[e] = __floats2bfloat162_rn(fm.x > 0.f ? fc.x : mleak * fc.x, fm.y > 0.f ? fc.y : mleak * fc.y);
+          }
+        }
+        if (addsrc) {
+          const uint4 old = *reinterpret_cast<const uint4*>(addsrc + (up ? rowoff_res[row] : o) + col);
+          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float2 fa = __bfloat1622float2(a[e]), fc = __bfloat1622float2(c[e]);
+            c[e] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+          }
+        }
+        *reinterpret_cast<uint4*>(out + o + col) = q;
+        if (out2) {
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; e++) c[e] = __hmax2(c[e], z);
+          *reinterpret_cast<uint4*>(out2 + o + col) = q;
+        }
+      }
+    }
+    const int tail0 = fast ? (ncols / VEC) * VEC : 0, ntail = ncols - tail0;
+    if (ntail > 0) {
+      for (int idx = lane; idx < 32 * ntail; idx += 32) {
+        const int row = idx / ntail, cc = tail0 + idx - row * ntail;
+        const unsigned long long o = rowoff[row];
+        if (o == ~0ull) continue;
+        float x = to_f(reinterpret_cast<const TO*>(slab + row * PITCH)[cc]);
+        if (mask) x = to_f(from_f<TO>(to_f(mask[o + n0 + cc]) > 0.f ? x : mleak * x));
+        if (addsrc) x += to_f(addsrc[(up ? rowoff_res[row] : o) + n0 + cc]);
+        const TO v = from_f<TO>(x);
+        out[o + n0 + cc] = v;
+        if (out2) out2[o + n0 + cc] = from_f<TO>(fmaxf(to_f(v), 0.f));
+      }
+    }
+    return;
+  }
   if (fast) {
     // whole 16-byte pieces of every row, consecutive lanes on consecutive pieces; a ragged tail (ncols % VEC columns,
     // e.g. 138 = 17 pieces + 2) is finished element-wise below
@@ -487,7 +560,7 @@ struct PCfg {
   static constexpr int A_BYTES = MT * BM * BK * 2;     // MT stacked 128-row sub-tiles share one B tile
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int PITCH = BN * (int)sizeof(TO) + 16;
-  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 1024;
+  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 2048;
   static constexpr int SMEM = ST * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "persistent conv tile does not fit shared memory");
   static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
@@ -1268,10 +1341,29 @@ extern "C" int rcgan_conv_wpack_batched(int count, const rcgan_conv_desc* const*
   return 0;
 }
 
+// optional epilogue fusions -> kernel parameters (bf16 outputs only; the caller has validated the combination)
+static void set_epilogue(TcParams& p, const rcgan_conv_epilogue* ep) {
+  p.res_up = 0; p.ld_res = 0; p.mask = nullptr; p.mask_act = 0; p.mask_leak = 0.f; p.out2 = nullptr; p.out2_act = 0;
+  if (!ep) return;
+  if (ep->res) { p.res = ep->res; p.res_up = ep->res_up; p.ld_res = ep->ld_res; }
+  p.mask = ep->mask; p.mask_act = ep->mask_act; p.mask_leak = ep->mask_leak;
+  p.out2 = ep->out2; p.out2_act = ep->out2_act;
+}
+static bool epilogue_ok(const rcgan_conv_epilogue* ep, int out_dtype, int accumulate, int oh, int ow) {
+  if (!ep) return true;
+  if (out_dtype != RCGAN_BF16) return false;
+  if (ep->res && accumulate) return false;
+  if (ep->res && ep->res_up && (oh % 2 || ow % 2 || ep->ld_res <= 0)) return false;
+  if (ep->mask && ep->mask_act != RCGAN_ACT_RELU && ep->mask_act != RCGAN_ACT_LRELU) return false;
+  if (ep->out2 && ep->out2_act != RCGAN_ACT_RELU) return false;
+  return true;
+}
+
 int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, const void* res, void* y,
-                   int out_dtype, int act, float leak, cudaStream_t st, int* handled) {
+                   int out_dtype, int act, float leak, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep) {
   *handled = 0;
   if (!fprop_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
+  if (!epilogue_ok(ep, out_dtype, 0, d->ho, d->wo)) { rcgan_set_error("conv2d_fprop_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED; }
   PackGeo g = pack_geo(d);
   TcParams p;
   p.src = reinterpret_cast<const bf16*>(x);
@@ -1283,6 +1375,7 @@ int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, c
   p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->ho; p.OW = d->wo;
   p.oy_mul = 1; p.oy_add = 0; p.ox_mul = 1; p.ox_add = 0; p.N = d->cout;
   p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0; p.res = res;
+  set_epilogue(p, ep);
   p.im_w_lo = -d->pad_l; p.im_h_lo = -d->pad_t; p.im_sw = d->stride; p.im_sh = d->stride;
   for (int t = 0; t < g.taps; t++) { p.toffh[t] = (unsigned short)(t / d->kw); p.toffw[t] = (unsigned short)(t % d->kw); }
   if (int e = run_tc(p, reinterpret_cast<const bf16*>(wpack), g.kpadF, d->cout, g.taps, d->cin, d->n, st)) return e;
@@ -1291,9 +1384,10 @@ int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, c
 }
 
 int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
-                   int act, float leak, int accumulate, cudaStream_t st, int* handled) {
+                   int act, float leak, int accumulate, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep) {
   *handled = 0;
   if (!dgrad_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
+  if (!epilogue_ok(ep, out_dtype, accumulate, d->h, d->w)) { rcgan_set_error("conv2d_dgrad_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED; }
   PackGeo g = pack_geo(d);
   const bf16* wD = reinterpret_cast<const bf16*>(wpack) + g.offD;
   const int s = d->stride;
@@ -1326,6 +1420,7 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
       p.out = dx; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldx; p.OH = d->h; p.OW = d->w;
       p.oy_mul = s; p.oy_add = py; p.ox_mul = s; p.ox_add = px; p.N = d->cin;
       p.bias = bias; p.act = act; p.leak = leak; p.accumulate = accumulate; p.res = nullptr;
+      set_epilogue(p, ep);
       if (nt == 0) { rcgan_set_error("conv_tc dgrad: parity class without taps"); return RCGAN_EUNSUPPORTED; }
       if (s == 2) {
         { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -1401,6 +1496,7 @@ extern "C" int rcgan_upconv2d_fprop(const rcgan_conv_desc* d, const void* x_smal
       p.out = y; p.out_f32 = out_dtype == RCGAN_F32; p.ld_out = d->ldy; p.OH = d->h; p.OW = d->w;
       p.oy_mul = 2; p.oy_add = py; p.ox_mul = 2; p.ox_add = px; p.N = d->cout;
       p.bias = bias; p.act = act; p.leak = leak; p.accumulate = 0; p.res = nullptr;
+      set_epilogue(p, nullptr);
       { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
       if (!make_amap(&amaps.a[mp.nprob], p, d->cin, d->n)) {
         rcgan_set_error("upconv2d_fprop: im2col tensor map not encodable for this shape");

@@ -268,6 +268,9 @@ class Program:
         return t
 
     def add(self, op):
+        op.index = len(self.ops)          # program order: backward planning reasons about who runs before whom
+        for o in op.outputs:
+            o.base.producer = op
         self.ops.append(op)
         return op
 
@@ -330,10 +333,14 @@ class Program:
         # how many ops read each activation (lets a sole reader alias gradient buffers instead of copying, see AddOp)
         for t in self.tensors:
             t.n_readers = 0
+            t.readers = []
         for op in self.ops:
             for t in op.inputs:
                 if t is not None and not t.is_variable:
                     t.base.n_readers = getattr(t.base, 'n_readers', 0) + 1
+                    if not hasattr(t.base, 'readers'):
+                        t.base.readers = []
+                    t.base.readers.append(op)
         for t in self.tensors:
             if t.needs_grad and t._grad is None:
                 t._grad = torch.zeros(t._data.numel(), dtype=TORCH_DTYPE[t.grad_dtype], device=self.device)

@@ -1,10 +1,17 @@
 """Op classes of the static program: each maps one reference op (cited per class) onto
 forward/backward launches of librcgan_b200.so.  See graph.py for the planning protocol."""
+import ctypes
+import os
+
 import torch
 
 from . import _C
 from ._C import ConvDesc, call, stream_ptr
 from .graph import Op, Tensor, cur, is_static_weight, needs, round_up, same_pad
+
+# A/B switches of the fused-epilogue planning (default on)
+FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '1') == '1'
+ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -99,6 +106,7 @@ class ConvOp(Op):
         wo, pl = same_pad(wd, kw, stride)
         self.x, self.w, self.b, self.res = x, w, b, residual
         self.act, self.leak = ACT[act], leak
+        self.act_bwd_fused = False       # set by the consumer whose dgrad applies act'(y) while writing y's gradient
         oshape = (n, cout) if len(x.shape) == 2 else (n, ho, wo, cout)
         assert not (pre_norm and self.act != _C.ACT_NONE)
         assert residual is None or (self.act == _C.ACT_NONE and not pre_norm and tuple(residual.shape) == tuple(oshape)
@@ -149,11 +157,33 @@ class ConvOp(Op):
             prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.tgdesc))
         prog.add(self)
 
+    def _plain_tc_dgrad(self):
+        """the input gradient is ONE tensor-core dgrad launch with a bf16 result (no patch / scatter / transposed special path)"""
+        return (self.x.dtype == _C.BF16 and self.x.grad_dtype == _C.BF16 and self.pack is not None and self.patch is None
+                and self.tpatch is None and bool(_C.load().rcgan_conv_uses_tensor_cores(self.desc, 1)))
+
     def plan_bwd(self, prog):
         nx, nw, nb, nr = self.need
         # (reverse program order: the residual's gradient is claimed first, as the separate AddOp used to do)
         self.acc_r = self.claim(self.res) if (nr and self.res is not None) else 0
-        self.acc_x = self.claim(self.x) if nx else 0
+        # The activation IN FRONT of this conv differentiated inside the dgrad that produces its gradient (rcgan_conv_epilogue.mask):
+        # x = act(raw) was written by an ActOp, or by the fused epilogue activation of the producing conv, and this conv is its only
+        # reader -> the dgrad multiplies by act'(x) as it stores; for an ActOp it stores straight into raw's gradient and the ActOp
+        # has no backward pass left.  Results are bit-identical to the separate act_bwd kernel (same roundings).
+        self.dx_target, self.dx_mask = self.x, None
+        if nx and FUSE_ACT_BWD and self._plain_tc_dgrad() and getattr(self.x.base, 'n_readers', 0) == 1:
+            prod = getattr(self.x.base, 'producer', None)
+            if (isinstance(prod, ActOp) and prod.act in (_C.ACT_RELU, _C.ACT_LRELU) and prod.need[0] and prod.x.ld == self.x.ld
+                    and prod.x.grad_dtype == _C.BF16 and not prod.x.is_variable):
+                self.dx_target, self.dx_mask = prod.x, (prod.act, prod.leak)
+                prod.bwd_fused = True
+            elif (isinstance(prod, (ConvOp, DeconvOp)) and prod.act in (_C.ACT_RELU, _C.ACT_LRELU) and prod.y.base is self.x.base
+                  and prod.y.dtype == _C.BF16):
+                self.dx_mask = (prod.act, prod.leak)
+                prod.act_bwd_fused = True
+        self.acc_x = self.claim(self.dx_target) if nx else 0
+        if self.dx_mask is not None:
+            self.dx_ep = _C.ConvEpilogue(mask=dp(self.x), mask_act=self.dx_mask[0], mask_leak=self.dx_mask[1])
         self.acc_w = self.claim(self.w) if nw else 0
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
@@ -214,13 +244,16 @@ class ConvOp(Op):
         y, dy = self.y, gp(self.y)
         if nr and self.res is not None:
             call('rcgan_copy_acc', dy, gp(self.res), self.res.numel(), self.res.grad_dtype, self.acc_r, st)
-        if self.act != _C.ACT_NONE:
+        if self.act != _C.ACT_NONE and not self.act_bwd_fused:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
         if nx:
-            if self.scatter is not None and self.scatter.ok:
+            if self.dx_mask is not None:
+                call('rcgan_conv2d_dgrad_ex', self.desc, dy, pp(self.pack), None, gp(self.dx_target), self.x.grad_dtype, _C.ACT_NONE,
+                     0.0, self.acc_x, ctypes.byref(self.dx_ep), st)
+            elif self.scatter is not None and self.scatter.ok:
                 self.scatter.run(dp(self.w), dy, gp(self.x), self.x.grad_dtype, None, _C.ACT_NONE, 0.0, self.acc_x, st)
             elif self.dpack is not None:
                 call('rcgan_conv_wpack', self.desc, dp(self.w), None, pp(self.dpack), st)
@@ -253,6 +286,7 @@ class DeconvOp(Op):
         assert (ho, wo) == (h, wd), 'deconv2d: output_shape inconsistent with SAME/stride'
         self.x, self.w, self.b = x, w, b
         self.act, self.leak = ACT[act], leak
+        self.act_bwd_fused = False
         assert not (pre_norm and self.act != _C.ACT_NONE)
         self.y = prog.new((n, oh, ow, cout), _C.F32 if pre_norm else x.dtype, grad_dtype=x.dtype)
         # the conv being transposed: input = y [n,oh,ow,cout], output = x [n,h,w,cin]
@@ -292,7 +326,7 @@ class DeconvOp(Op):
         nx, nw, nb = self.need
         st = stream_ptr()
         y, dy = self.y, gp(self.y)
-        if self.act != _C.ACT_NONE:
+        if self.act != _C.ACT_NONE and not self.act_bwd_fused:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         d, dyin = self.desc, dy
         if self.patch is not None and (nx or nw):
@@ -420,17 +454,18 @@ class ActOp(Op):
         self.x, self.act, self.leak = x, ACT[act], leak
         self.y = prog.new(x.shape, x.dtype)
         self.inputs, self.outputs = (x,), (self.y,)
+        self.bwd_fused = False           # the consuming conv's dgrad writes act'(y) * gradient straight into x's gradient
         prog.add(self)
 
     def plan_bwd(self, prog):
-        self.acc_x = self.claim(self.x) if self.need[0] else 0
+        self.acc_x = self.claim(self.x) if (self.need[0] and not self.bwd_fused) else 0
 
     def forward(self, prog):
         x, y = self.x, self.y
         call('rcgan_bias_act_fwd', dp(x), None, dp(y), x.rows, x.c, x.ld, y.ld, x.dtype, self.act, self.leak, stream_ptr())
 
     def backward(self, prog):
-        if not needs(self.y) or not self.need[0]:
+        if not needs(self.y) or not self.need[0] or self.bwd_fused:
             return
         x, y = self.x, self.y
         call('rcgan_act_bwd', gp(y), dp(y), gp(x), y.rows, y.c, y.ld, y.ld, x.ld, y.dtype, self.act, self.leak, self.acc_x,
@@ -895,13 +930,28 @@ class AddOp(Op):
         prog.add(self)
 
     def plan_bwd(self, prog):
-        self.acc_a = self.claim(self.a) if self.need[0] else 0
         # d(a + b)/db = identity: when this op is b's ONLY reader, b's gradient IS y's gradient -- alias the buffer instead of
         # copying it (b's producer runs its backward after this op and only reads it; y's gradient is complete by then)
-        b, y = self.b.base, self.y.base
-        self.alias_b = bool(self.need[1] and needs(self.y) and b is self.b and y is self.y and getattr(b, 'n_readers', 0) == 1
-                            and not b.grad_written and b._grad is not None and y._grad is not None
-                            and b._grad.numel() == y._grad.numel() and b._grad.dtype == y._grad.dtype)
+        a, b, y = self.a.base, self.b.base, self.y.base
+        ok = lambda t, me: bool(needs(self.y) and t is me and y is self.y and not t.is_variable and not t.grad_written
+                                and t._grad is not None and y._grad is not None and t._grad.numel() == y._grad.numel()
+                                and t._grad.dtype == y._grad.dtype)
+        self.alias_b = bool(self.need[1] and ok(b, self.b) and getattr(b, 'n_readers', 0) == 1)
+        # ... and a's gradient STARTS as y's gradient: the same buffer can be a's too, accumulated into in place by a's other
+        # readers (the residual trunk keeps ONE gradient buffer through the blocks) -- provided those all run their backward after
+        # everything that still reads the buffer as dL/dy, i.e. they precede b's producer in program order, and that producer does
+        # not modify its output gradient in place
+        pb = getattr(b, 'producer', None)
+        others = [o for o in getattr(a, 'readers', []) if o is not self]
+        self.alias_a = bool(ALIAS_RESIDUAL and self.need[0] and ok(a, self.a) and a is not b
+                            and (not self.alias_b or (pb is not None and getattr(pb, 'act', None) == _C.ACT_NONE
+                                                      and all(o.index < pb.index for o in others))))
+        if self.alias_a:
+            a._grad = y._grad
+            a.grad_written = True
+            self.acc_a = 0
+        else:
+            self.acc_a = self.claim(self.a) if self.need[0] else 0
         if self.alias_b:
             b._grad = y._grad
             b.grad_written = True
@@ -916,7 +966,7 @@ class AddOp(Op):
         if not needs(self.y):
             return
         st = stream_ptr()
-        if self.need[0]:
+        if self.need[0] and not self.alias_a:
             call('rcgan_copy_acc', gp(self.y), gp(self.a), self.a.numel(), self.a.dtype, self.acc_a, st)
         if self.need[1] and not self.alias_b:
             call('rcgan_copy_acc', gp(self.y), gp(self.b), self.b.numel(), self.b.dtype, self.acc_b, st)

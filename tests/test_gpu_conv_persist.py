@@ -244,3 +244,77 @@ def test_wgrad_at_benchmark_sizes(lib, shape, variant):
     assert relerr(dw[..., :16].cpu(), w64.grad) < 6e-5
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 1, ws.data_ptr(), nb, st())
     assert relerr(dw[..., :16].cpu(), 2 * w64.grad) < 6e-5
+
+
+# ------------------------------------------------------------------------------------------------ fused epilogues
+EX_SHAPES = [((600, 8, 8, 128, 128, 3, 1, 0, 0), 'conv_tc<128,3,im2col=1>'),
+             ((1800, 8, 8, 128, 128, 3, 1, 0, 0), 'conv_tc_persist<128,2,3,bf16,multi=0>'),
+             ((64, 32, 32, 256, 256, 3, 1, 0, 0), 'conv_tc_persist<256,1,3,bf16,multi=0>'),
+             ((512, 32, 32, 128, 128, 4, 2, 0, 0), 'conv_tc_persist<128,2,3,bf16,multi=1>'),     # the folded ConvMeanPool's dgrad
+             ((37, 16, 16, 64, 72, 3, 1, 0, 0), 'conv_tc<128,3,im2col=1>')]                      # N = 64 / 72: ragged pieces
+
+
+@pytest.mark.parametrize('shape,variant', EX_SHAPES)
+@pytest.mark.parametrize('act', [_C.ACT_RELU, _C.ACT_LRELU])
+def test_dgrad_with_fused_activation_backward(lib, shape, variant, act):
+    """rcgan_conv2d_dgrad_ex(mask): dx (=|+=) act'(mask) * dgrad -- bit-identical to rcgan_conv2d_dgrad followed by rcgan_act_bwd
+    (the `nonlinearity` in front of a conv, gan_resnet.py:318-325, differentiated in the producing dgrad's epilogue)"""
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
+    n, h, w, cin = shape[:4]
+    pack, wd = pack_for(lib, d, wt)
+    g = torch.Generator().manual_seed(11)
+    mask = torch.randn(n, h, w, ldx, generator=g).bfloat16().cuda()          # the activation's forward output (sign matters only)
+    old = torch.randn(n, h, w, ldx, generator=g).bfloat16().cuda()
+    tmp = torch.zeros(n, h, w, ldx, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, tmp.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, 0, st())
+    rows = n * h * w
+    for acc in (0, 1):
+        ref = old.clone()
+        call('rcgan_act_bwd', tmp.data_ptr(), mask.data_ptr(), ref.data_ptr(), rows, cin, ldx, ldx, ldx, _C.BF16, act, 0.2, acc, st())
+        got = old.clone()
+        ep = _C.ConvEpilogue(mask=mask.data_ptr(), mask_act=act, mask_leak=0.2)
+        import ctypes
+        call('rcgan_conv2d_dgrad_ex', d, dyd.data_ptr(), pack.data_ptr(), None, got.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, acc,
+             ctypes.byref(ep), st())
+        torch.cuda.synchronize()
+        assert _C.last_conv_variant() == variant
+        assert torch.equal(got[..., :cin], ref[..., :cin])
+    # and against the oracle: relu'(mask) * conv2d gradient
+    xr = x.clone().requires_grad_(True)
+    O.conv2d(xr, wt, shape[6]).backward(dy)
+    m = mask[..., :cin].float().cpu()
+    slope = torch.where(m > 0, torch.ones_like(m), torch.full_like(m, 0.0 if act == _C.ACT_RELU else 0.2))
+    call('rcgan_conv2d_dgrad_ex', d, dyd.data_ptr(), pack.data_ptr(), None, got.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, 0, ctypes.byref(ep), st())
+    assert relerr(got[..., :cin].float().cpu(), slope * xr.grad) < 6e-3
+
+
+@pytest.mark.parametrize('shape,variant', [s for s in EX_SHAPES if s[0][6] == 1])
+@pytest.mark.parametrize('res_up', [0, 1])
+def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, variant, res_up):
+    """rcgan_conv2d_fprop_ex(res, res_up, out2): y = conv + bias + [upsample2](res), out2 = relu(y) -- ResidualBlock's
+    `shortcut + output` with UpsampleConv_1x1's shortcut still at the small resolution (gan_resnet.py:259-272, 305-328) and the
+    next block's `nonlinearity(inputs)`; bit-identical to fprop, upsample, add, relu as separate kernels"""
+    import ctypes
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
+    n, cout = shape[0], shape[4]
+    if res_up and (ho % 2 or wo % 2):
+        pytest.skip('odd output size')
+    pack, wd = pack_for(lib, d, wt)
+    bd = dev(b)
+    g = torch.Generator().manual_seed(13)
+    rs = (n, ho // 2, wo // 2, ldy) if res_up else (n, ho, wo, ldy)
+    res = torch.randn(*rs, generator=g).bfloat16().cuda()
+    y0 = torch.zeros(n, ho, wo, ldy, device='cuda', dtype=torch.bfloat16)
+    call('rcgan_conv2d_fprop', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y0.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, st())
+    full = res.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) if res_up else res
+    ref = (y0.float() + full.float()).bfloat16()
+    y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=torch.bfloat16)
+    y2 = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=torch.bfloat16)
+    ep = _C.ConvEpilogue(res=res.data_ptr(), res_up=res_up, ld_res=ldy, out2=y2.data_ptr(), out2_act=_C.ACT_RELU)
+    call('rcgan_conv2d_fprop_ex', d, xd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, ctypes.byref(ep), st())
+    torch.cuda.synchronize()
+    assert _C.last_conv_variant() == variant
+    assert torch.equal(y[..., :cout], ref[..., :cout])
+    assert torch.equal(y2[..., :cout], torch.relu(ref[..., :cout]))
+    if ldy > cout:
+        assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0 and float((y2[..., cout:].float() - 7.0).abs().max()) == 0.0

@@ -24,7 +24,8 @@ def test_residual_add_aliases_sole_reader_gradient_and_orders_writers():
         x = p.input('x', [2, 8, 8, 64], _C.BF16)
         h = ConvOp(x, v['w1'], None).y
         r = ActOp(h, 'relu')
-        c = ConvOp(r.y, v['w2'], None).y
+        cop = ConvOp(r.y, v['w2'], None)
+        c = cop.y
         z = AddOp(h, c)                      # c has one reader (the add); h has two (relu, add)
         c2 = ConvOp(z.y, v['w3'], None)
         z2 = AddOp(c2.y, z.y)                # here the SECOND operand (z.y) has two readers -> must not be aliased
@@ -32,8 +33,11 @@ def test_residual_add_aliases_sole_reader_gradient_and_orders_writers():
     p.finalize([v['w1'], v['w2'], v['w3']])
     assert z.alias_b and c.grad.data_ptr() == z.y.grad.data_ptr()
     assert not z2.alias_b and z2.y.grad.data_ptr() != z.y.grad.data_ptr()
-    # reverse sweep: the add writes h's gradient first (overwrite), the relu's backward then accumulates into it
-    assert z.acc_a == 0 and r.acc_x == 1
+    # reverse sweep: h's gradient STARTS as the sum's gradient (same buffer, no copy: h's other reader, the relu, precedes c's
+    # producer in program order); the relu's backward is fused into the dgrad of the conv that reads it, which accumulates
+    # act'(relu output) * gradient straight into h's gradient
+    assert z.alias_a and h.grad.data_ptr() == z.y.grad.data_ptr() and z.acc_a == 0
+    assert r.bwd_fused and cop.dx_target is h and cop.dx_mask == (_C.ACT_RELU, 0.2) and cop.acc_x == 1
     # parameter gradients always accumulate into the zeroed arena
     assert c2.acc_w == 1 and c2.acc_x == 1 and z2.acc_b == 0
 
