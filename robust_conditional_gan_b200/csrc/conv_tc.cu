@@ -277,41 +277,62 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
     // fused variant of the store loop (bf16 only): mask -> residual / accumulate -> store -> second output
     const float mleak = p.mask_act == RCGAN_ACT_LRELU ? p.mask_leak : 0.f;
     if (fast) {
+      // The extra operands (mask, residual / old value) are global loads in the store loop: U pieces per lane are put in flight
+      // before the first one is consumed (a dependent load-use chain per piece made this epilogue slower than the tile's main
+      // loop: 25.8 vs 24.2 ms per iteration with the separate passes)
+      constexpr int U = 4;
       const int lpr = ncols / VEC;
       const int drow = 32 / lpr, dpiece = 32 - drow * lpr;
       int row = lane / lpr, piece = lane - row * lpr;
-#pragma unroll 2
-      for (int idx = lane; idx < 32 * lpr; idx += 32, row += drow, piece += dpiece) {
-        if (piece >= lpr) { piece -= lpr; row++; }
-        const unsigned long long o = rowoff[row];
-        if (o == ~0ull) continue;
-        uint4 q = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
-        __nv_bfloat162* c = reinterpret_cast<__nv_bfloat162*>(&q);
-        const size_t col = (size_t)n0 + piece * VEC;
-        if (mask) {
-          const uint4 mq = *reinterpret_cast<const uint4*>(mask + o + col);
-          const __nv_bfloat162* mm = reinterpret_cast<const __nv_bfloat162*>(&mq);
+      const int niter = lpr;                       // idx = lane + 32 * it < 32 * lpr
+      for (int it0 = 0; it0 < niter; it0 += U) {
+        uint4 q[U], mq[U], aq[U];
+        unsigned long long off[U];
+        bool live[U];
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float2 fm = __bfloat1622float2(mm[e]), fc = __bfloat1622float2(c[e]);
-            c[e] = __floats2bfloat162_rn(fm.x > 0.f ? fc.x : mleak * fc.x, fm.y > 0.f ? fc.y : mleak * fc.y);
+        for (int u = 0; u < U; u++) {
+          live[u] = false;
+          if (it0 + u < niter) {
+            if (piece >= lpr) { piece -= lpr; row++; }
+            const unsigned long long o = rowoff[row];
+            if (o != ~0ull) {
+              live[u] = true;
+              const size_t col = (size_t)n0 + piece * VEC;
+              off[u] = o + col;
+              if (mask) mq[u] = __ldg(reinterpret_cast<const uint4*>(mask + o + col));
+              if (addsrc) aq[u] = *reinterpret_cast<const uint4*>(addsrc + (up ? rowoff_res[row] : o) + col);
+              q[u] = *reinterpret_cast<const uint4*>(slab + row * PITCH + piece * 16);
+            }
+            row += drow; piece += dpiece;
           }
         }
-        if (addsrc) {
-          const uint4 old = *reinterpret_cast<const uint4*>(addsrc + (up ? rowoff_res[row] : o) + col);
-          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float2 fa = __bfloat1622float2(a[e]), fc = __bfloat1622float2(c[e]);
-            c[e] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+        for (int u = 0; u < U; u++) {
+          if (!live[u]) continue;
+          __nv_bfloat162* c = reinterpret_cast<__nv_bfloat162*>(&q[u]);
+          if (mask) {
+            const __nv_bfloat162* mm = reinterpret_cast<const __nv_bfloat162*>(&mq[u]);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float2 fm = __bfloat1622float2(mm[e]), fc = __bfloat1622float2(c[e]);
+              c[e] = __floats2bfloat162_rn(fm.x > 0.f ? fc.x : mleak * fc.x, fm.y > 0.f ? fc.y : mleak * fc.y);
+            }
           }
-        }
-        *reinterpret_cast<uint4*>(out + o + col) = q;
-        if (out2) {
-          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+          if (addsrc) {
+            const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&aq[u]);
 #pragma unroll
-          for (int e = 0; e < 4; e++) c[e] = __hmax2(c[e], z);
-          *reinterpret_cast<uint4*>(out2 + o + col) = q;
+            for (int e = 0; e < 4; e++) {
+              const float2 fa = __bfloat1622float2(a[e]), fc = __bfloat1622float2(c[e]);
+              c[e] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(out + off[u]) = q[u];
+          if (out2) {
+            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 4; e++) c[e] = __hmax2(c[e], z);
+            *reinterpret_cast<uint4*>(out2 + off[u]) = q[u];
+          }
         }
       }
     }

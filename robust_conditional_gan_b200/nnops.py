@@ -12,6 +12,7 @@ from .graph import Op, Tensor, cur, is_static_weight, needs, round_up, same_pad
 # A/B switches of the fused-epilogue planning (default on)
 FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '1') == '1'
 ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
+FUSE_RELU_OUT = os.environ.get('RCGAN_FUSE_RELU_OUT', '1') == '1'
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -84,14 +85,31 @@ def spatial(t):
     return t.shape[0], t.shape[1], t.shape[2]
 
 
+def derive(raw, out):
+    """`out` = act(raw): whoever reads `out` may end up writing raw's gradient directly (fused activation backward)"""
+    if not hasattr(raw.base, 'derived'):
+        raw.base.derived = []
+    raw.base.derived.append(out.base)
+
+
+def grad_writer_ops(t):
+    """every op whose backward can write t's gradient: t's readers and the readers of the activations derived from t"""
+    ops = list(getattr(t.base, 'readers', []))
+    for u in getattr(t.base, 'derived', []):
+        ops += list(getattr(u, 'readers', []))
+    return ops
+
+
 class ConvOp(Op):
     """y = act(conv2d_SAME(x, w, stride) + b).  tf.nn.conv2d + bias_add (mnist/ops.py:53-67;
     cifar10/common/ops/conv2d.py:181-216); with a 2-D x it is tf.matmul + bias
     (mnist/ops.py:97-116; cifar10/common/ops/linear.py:161-180).  w: [kh,kw,cin,cout] or [cin,cout]."""
 
-    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False, residual=None, up_op=None):
+    def __init__(self, x, w, b, stride=1, act=None, leak=0.2, pre_norm=False, residual=None, up_op=None, residual_up=False):
         """pre_norm: the output feeds a batch norm -> stored in fp32 even in bf16 mode (gradient stays bf16).
-        residual: y = conv(x) + b + residual, the ResidualBlock's shortcut add fused into this conv's epilogue.
+        residual: y = conv(x) + b + residual, the ResidualBlock's shortcut add fused into this conv's epilogue;
+        residual_up: the residual is [n, ho/2, wo/2, cout] and is added through a nearest-neighbour 2x upsampling (the 1x1
+        UpsampleConv shortcut computed on the small grid, never materialised at the output resolution).
         up_op: the Upsample2Op that produced x (UpsampleConv): in programs that need no gradient through this conv the
         pair runs as ONE folded launch on the small input (rcgan_upconv2d_fprop) and the upsample is skipped."""
         prog = cur()
@@ -109,8 +127,13 @@ class ConvOp(Op):
         self.act_bwd_fused = False       # set by the consumer whose dgrad applies act'(y) while writing y's gradient
         oshape = (n, cout) if len(x.shape) == 2 else (n, ho, wo, cout)
         assert not (pre_norm and self.act != _C.ACT_NONE)
-        assert residual is None or (self.act == _C.ACT_NONE and not pre_norm and tuple(residual.shape) == tuple(oshape)
+        self.res_up = bool(residual_up)
+        rshape = (n, ho // 2, wo // 2, cout) if residual_up else oshape
+        assert residual is None or (self.act == _C.ACT_NONE and not pre_norm and tuple(residual.shape) == tuple(rshape)
                                     and residual.ld == residual.c and residual.dtype == x.dtype)
+        assert not residual_up or (residual is not None and ho % 2 == 0 and wo % 2 == 0)
+        self.y2 = None                   # second output relu(y), attached on demand (emit_relu)
+        self.y2_bwd_fused = False
         self.y = prog.new(oshape, _C.F32 if pre_norm else x.dtype, grad_dtype=x.dtype)
         self.desc = ConvDesc(n, h, wd, cin, ho, wo, cout, kh, kw, stride, pt, pl, x.ld, self.y.ld, x.dtype)
         self.inputs, self.outputs = (x, w, b, residual), (self.y,)
@@ -157,6 +180,24 @@ class ConvOp(Op):
             prog.ws.request(_C.load().rcgan_conv2d_wgrad_workspace(self.tgdesc))
         prog.add(self)
 
+    def _plain_tc_fprop(self):
+        """the forward is ONE tensor-core fprop launch with a bf16 result: the fused epilogues (rcgan_conv2d_fprop_ex) apply"""
+        return (self.x.dtype == _C.BF16 and self.y.dtype == _C.BF16 and self.pack is not None and self.patch is None
+                and self.tpatch is None and self.up_op is None and bool(_C.load().rcgan_conv_uses_tensor_cores(self.desc, 0)))
+
+    def can_emit_relu(self):
+        return FUSE_RELU_OUT and self.y2 is None and self.act == _C.ACT_NONE and self._plain_tc_fprop()
+
+    def emit_relu(self):
+        """second output relu(y) written by this conv's epilogue (the next block's `nonlinearity(inputs)`, gan_resnet.py:318)"""
+        prog = cur()
+        assert self.can_emit_relu() and prog.ops[self.index] is self
+        self.y2 = prog.new(self.y.shape, self.y.dtype)
+        self.y2.base.producer = self
+        self.outputs = (self.y, self.y2)
+        derive(self.y, self.y2)
+        return self.y2
+
     def _plain_tc_dgrad(self):
         """the input gradient is ONE tensor-core dgrad launch with a bf16 result (no patch / scatter / transposed special path)"""
         return (self.x.dtype == _C.BF16 and self.x.grad_dtype == _C.BF16 and self.pack is not None and self.patch is None
@@ -165,7 +206,23 @@ class ConvOp(Op):
     def plan_bwd(self, prog):
         nx, nw, nb, nr = self.need
         # (reverse program order: the residual's gradient is claimed first, as the separate AddOp used to do)
-        self.acc_r = self.claim(self.res) if (nr and self.res is not None) else 0
+        self.alias_r = False
+        if nr and self.res is not None and not self.res_up:
+            # same-size residual: its gradient STARTS as dL/dy -> share the buffer when everything else that writes it runs
+            # after this op's backward (i.e. precedes this op in program order); see AddOp.plan_bwd
+            r, y = self.res.base, self.y.base
+            self.alias_r = bool(ALIAS_RESIDUAL and needs(self.y) and r is self.res and y is self.y and not r.is_variable
+                                and not r.grad_written and r._grad is not None and y._grad is not None
+                                and r._grad.numel() == y._grad.numel() and r._grad.dtype == y._grad.dtype
+                                and all(o.index < self.index for o in grad_writer_ops(r) if o is not self))
+        if self.alias_r:
+            self.res.base._grad = self.y.base._grad
+            self.res.base.grad_written = True
+            self.acc_r = 0
+        else:
+            self.acc_r = self.claim(self.res) if (nr and self.res is not None) else 0
+        # relu(y) as second output whose consumer did not fuse the relu's backward: fold it into dL/dy first thing in backward
+        self.acc_y2 = self.claim(self.y) if (self.y2 is not None and needs(self.y2) and not self.y2_bwd_fused) else None
         # The activation IN FRONT of this conv differentiated inside the dgrad that produces its gradient (rcgan_conv_epilogue.mask):
         # x = act(raw) was written by an ActOp, or by the fused epilogue activation of the producing conv, and this conv is its only
         # reader -> the dgrad multiplies by act'(x) as it stores; for an ActOp it stores straight into raw's gradient and the ActOp
@@ -177,6 +234,9 @@ class ConvOp(Op):
                     and prod.x.grad_dtype == _C.BF16 and not prod.x.is_variable):
                 self.dx_target, self.dx_mask = prod.x, (prod.act, prod.leak)
                 prod.bwd_fused = True
+            elif isinstance(prod, ConvOp) and prod.y2 is not None and prod.y2.base is self.x.base:
+                self.dx_target, self.dx_mask = prod.y, (_C.ACT_RELU, 0.0)
+                prod.y2_bwd_fused = True
             elif (isinstance(prod, (ConvOp, DeconvOp)) and prod.act in (_C.ACT_RELU, _C.ACT_LRELU) and prod.y.base is self.x.base
                   and prod.y.dtype == _C.BF16):
                 self.dx_mask = (prod.act, prod.leak)
@@ -229,6 +289,13 @@ class ConvOp(Op):
             d, xin = self.gdesc, dp(self.patch)
         if self.pack_owner:
             call('rcgan_conv_wpack', d, dp(self.w), None, pp(self.pack), stream_ptr())
+        if self.res_up or self.y2 is not None or (self.res is not None and self._plain_tc_fprop()):
+            if getattr(self, 'ep_fwd', None) is None:
+                self.ep_fwd = _C.ConvEpilogue(res=dp(self.res), res_up=int(self.res_up), ld_res=self.res.ld if self.res is not None else 0,
+                                              out2=dp(self.y2), out2_act=_C.ACT_RELU if self.y2 is not None else 0)
+            call('rcgan_conv2d_fprop_ex', d, xin, pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act, self.leak,
+                 ctypes.byref(self.ep_fwd), stream_ptr())
+            return
         if self.res is not None:
             call('rcgan_conv2d_fprop_res', d, xin, dp(self.w), pp(self.pack), dp(self.b), dp(self.res), dp(self.y), self.y.dtype,
                  self.act, self.leak, stream_ptr())
@@ -242,7 +309,13 @@ class ConvOp(Op):
         nx, nw, nb, nr = self.need
         st = stream_ptr()
         y, dy = self.y, gp(self.y)
-        if nr and self.res is not None:
+        if self.acc_y2 is not None:
+            y2 = self.y2
+            call('rcgan_act_bwd', gp(y2), dp(y2), dy, y2.rows, y2.c, y2.ld, y2.ld, y.ld, y2.dtype, _C.ACT_RELU, 0.0, self.acc_y2, st)
+        if nr and self.res is not None and self.res_up:
+            rn, rh, rw = spatial(self.res)
+            call('rcgan_upsample2_bwd', dy, gp(self.res), rn, rh, rw, self.res.c, self.res.grad_dtype, self.acc_r, st)
+        elif nr and self.res is not None and not self.alias_r:
             call('rcgan_copy_acc', dy, gp(self.res), self.res.numel(), self.res.grad_dtype, self.acc_r, st)
         if self.act != _C.ACT_NONE and not self.act_bwd_fused:
             call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
@@ -455,6 +528,7 @@ class ActOp(Op):
         self.y = prog.new(x.shape, x.dtype)
         self.inputs, self.outputs = (x,), (self.y,)
         self.bwd_fused = False           # the consuming conv's dgrad writes act'(y) * gradient straight into x's gradient
+        derive(x, self.y)
         prog.add(self)
 
     def plan_bwd(self, prog):
@@ -942,7 +1016,7 @@ class AddOp(Op):
         # everything that still reads the buffer as dL/dy, i.e. they precede b's producer in program order, and that producer does
         # not modify its output gradient in place
         pb = getattr(b, 'producer', None)
-        others = [o for o in getattr(a, 'readers', []) if o is not self]
+        others = [o for o in grad_writer_ops(a) if o is not self]
         self.alias_a = bool(ALIAS_RESIDUAL and self.need[0] and ok(a, self.a) and a is not b
                             and (not self.alias_b or (pb is not None and getattr(pb, 'act', None) == _C.ACT_NONE
                                                       and all(o.index < pb.index for o in others))))

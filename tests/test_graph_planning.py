@@ -36,10 +36,52 @@ def test_residual_add_aliases_sole_reader_gradient_and_orders_writers():
     # reverse sweep: h's gradient STARTS as the sum's gradient (same buffer, no copy: h's other reader, the relu, precedes c's
     # producer in program order); the relu's backward is fused into the dgrad of the conv that reads it, which accumulates
     # act'(relu output) * gradient straight into h's gradient
-    assert z.alias_a and h.grad.data_ptr() == z.y.grad.data_ptr() and z.acc_a == 0
+    # (not here: the conv that would accumulate into h's gradient is also the one that still reads the buffer as dL/dc)
+    assert not z.alias_a and h.grad.data_ptr() != z.y.grad.data_ptr() and z.acc_a == 0
     assert r.bwd_fused and cop.dx_target is h and cop.dx_mask == (_C.ACT_RELU, 0.2) and cop.acc_x == 1
     # parameter gradients always accumulate into the zeroed arena
     assert c2.acc_w == 1 and c2.acc_x == 1 and z2.acc_b == 0
+
+
+def test_residual_block_keeps_one_gradient_buffer_and_fuses_the_relus():
+    """the reference's pre-activation block x -> relu -> Conv1(+relu) -> Conv2 -> (+x) (gan_resnet.py:275-328, D blocks 3-6)"""
+    st, v = store_with(w0=(3, 3, 64, 64), w1=(3, 3, 64, 64), w2=(3, 3, 64, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x0 = p.input('x', [2, 8, 8, 64], _C.BF16)
+        x = ConvOp(x0, v['w0'], None).y
+        a = ActOp(x, 'relu')
+        c1 = ConvOp(a.y, v['w1'], None, act='relu')
+        c2 = ConvOp(c1.y, v['w2'], None)
+        z = AddOp(x, c2.y)
+        MeanHWOp(z.y)
+    st.finalize()
+    p.finalize([v['w0'], v['w1'], v['w2']])
+    # both branches of the add share dL/dz's buffer: c2 reads it as dL/dy, c1's dgrad later accumulates relu'(a) * g into it as dL/dx
+    assert z.alias_a and z.alias_b and x.grad.data_ptr() == z.y.grad.data_ptr() == c2.y.grad.data_ptr()
+    assert a.bwd_fused and c1.dx_target is x and c1.acc_x == 1 and c1.dx_mask[0] == _C.ACT_RELU
+    # Conv1's own relu is differentiated by Conv2's dgrad as it writes dL/d(c1.y)
+    assert c1.act_bwd_fused and c2.dx_mask[0] == _C.ACT_RELU and c2.dx_target is c1.y and c2.acc_x == 0
+
+
+def test_fused_residual_and_second_relu_output():
+    """Conv2's epilogue adds the shortcut and also writes relu(y) for the next block; the next block's Conv1 sends its input
+    gradient straight into dL/dy through relu'(.)"""
+    st, v = store_with(w0=(3, 3, 64, 64), w1=(3, 3, 64, 64), w2=(3, 3, 64, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x0 = p.input('x', [2, 8, 8, 64], _C.BF16)
+        c0 = ConvOp(x0, v['w0'], None)
+        assert c0.can_emit_relu()
+        r = c0.emit_relu()
+        c1 = ConvOp(r, v['w1'], None, act='relu')
+        c2 = ConvOp(c1.y, v['w2'], None, residual=c0.y)
+        MeanHWOp(c2.y)
+    st.finalize()
+    p.finalize([v['w0'], v['w1'], v['w2']])
+    assert c0.y2 is r and c0.y2_bwd_fused and c0.acc_y2 is None
+    assert c1.dx_target is c0.y and c1.acc_x == 1 and c1.dx_mask == (_C.ACT_RELU, 0.0)
+    assert c2.alias_r and c0.y.grad.data_ptr() == c2.y.grad.data_ptr()
 
 
 def test_gradients_are_only_planned_for_the_requested_variables():
