@@ -13,12 +13,12 @@ import torch
 
 from .. import _C, scope as S
 from ..graph import I32, Program, VariableStore, tf_adam_lr
-from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, ConcatRowsOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
+from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, ConcatRowsOp, ConvOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
                      SoftmaxRowsOp, Upsample2Op, adam_step)
 from . import ops as lib_ops
 
 NO_OPS = 'NO_OPS'
-FUSE_RESIDUAL = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL', '0') == '1'
+FUSE_RESIDUAL = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL', '1') == '1'
 # 3x3 ConvMeanPool / UpsampleConv as ONE 4x4 stride-2 conv / conv2d_transpose with the folded filter; 0 = A/B switch
 FOLD_RESAMPLE = __import__('os').environ.get('RCGAN_FOLD', '1') == '1'
 Z_DIM, VOCAB_SIZE, EMBEDDING_DIM, IMG_SIZE, IMG_DIM, OUTPUT_DIM = 128, 10, 300, 32, 3, 3072
@@ -52,15 +52,22 @@ class Net:
         with S.variable_scope(name):
             if 'G.' in name and labels is not None:
                 return lib_ops.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, fuse_act=fuse_act)
+        if fuse_act == 'relu':
+            # D: the bare nonlinearity(inputs) (:318).  When `inputs` is the output of a conv with a fused-epilogue path (the previous
+            # block's Conv2 + shortcut), that conv's epilogue writes relu(inputs) as a second output: no separate pass
+            prod = getattr(inputs.base, 'producer', None)
+            if FUSE_RESIDUAL and isinstance(prod, ConvOp) and prod.y.base is inputs.base and prod.can_emit_relu():
+                return prod.emit_relu()
         return ActOp(inputs, fuse_act).y if fuse_act else inputs
 
     @staticmethod
     def ConvMeanPool(inputs, output_dim, filter_size=3, stride=1, name=None, spectral_normed=False, update_collection=None,
-                     inputs_norm=False, he_init=True, biases=True):
-        """:231-241"""
+                     inputs_norm=False, he_init=True, biases=True, residual=None):
+        """:231-241 (residual: the block's shortcut, added by the folded conv's epilogue)"""
         if FOLD_RESAMPLE and filter_size == 3 and inputs.shape[1] % 2 == 0 and inputs.shape[2] % 2 == 0:
             return lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
-                                  update_collection=update_collection, he_init=he_init, biases=biases, fold='pool')
+                                  update_collection=update_collection, he_init=he_init, biases=biases, fold='pool', residual=residual)
+        assert residual is None
         out = lib_ops.Conv2D(inputs, inputs.shape[-1], output_dim, filter_size, stride, name, spectral_normed=spectral_normed,
                              update_collection=update_collection, he_init=he_init, biases=biases)
         return Pool2Op(out).y
@@ -111,7 +118,9 @@ class Net:
             # bit, ConvMeanPool_1x1(x) == Conv_1x1(MeanPool(x)) up to fp32 summation order.  Running the conv on the SMALL
             # grid is a 4x flop / traffic cut (legal for parity; rooflines still use the reference flops).
             if resample == 'up':
-                shortcut = Upsample2Op(lib_ops.Conv2D(inputs, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)).y
+                shortcut = lib_ops.Conv2D(inputs, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)
+                if not FUSE_RESIDUAL:
+                    shortcut = Upsample2Op(shortcut).y
             elif resample == 'down':
                 shortcut = lib_ops.Conv2D(Pool2Op(inputs).y, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)
             else:
@@ -124,12 +133,13 @@ class Net:
             # D: Normalize is the identity (NORMALIZATION_D = False), so N2 + nonlinearity is a bare relu on Conv1's output:
             # it rides in Conv1's epilogue instead of a separate pass
             output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, fuse_act='relu', **kw)
-        if resample == 'down' or not FUSE_RESIDUAL:
+        if not FUSE_RESIDUAL or (resample == 'down' and not FOLD_RESAMPLE):
             output = conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, **kw)
             return AddOp(shortcut, output).y
-        # `shortcut + output` (:328) in Conv2's epilogue (rcgan_conv2d_fprop_res).  Bit-identical, but measured SLOWER end to end
-        # (28.3 -> 28.6 ms/iteration at B=256: the residual loads sit in the one-tile kernel's exposed epilogue and the backward
-        # still needs one copy of dy), hence opt-in: RCGAN_FUSE_RESIDUAL=1.
+        # `shortcut + output` (:328) in Conv2's epilogue (rcgan_conv2d_fprop_ex): bit-identical to the separate add; an 'up' block's
+        # shortcut stays at half resolution and is upsampled by the epilogue's index map
+        if resample == 'up':
+            return conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, residual=shortcut, residual_up=True, **kw)
         return conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, residual=shortcut, **kw)
 
     def OptimizedResBlockDisc1(self, inputs, spectral_normed=False, update_collection=None, inputs_norm=False, biases=True):
@@ -137,6 +147,8 @@ class Net:
         kw = dict(spectral_normed=spectral_normed, update_collection=update_collection, biases=biases)
         shortcut = self.MeanPoolConv(inputs, output_dim=self.DIM_D, filter_size=1, name='D.Block.1.Shortcut', he_init=False, **kw)
         output = lib_ops.Conv2D(inputs, IMG_DIM, self.DIM_D, 3, 1, 'D.Block.1.Conv1', he_init=True, fuse_act='relu', **kw)
+        if FUSE_RESIDUAL and FOLD_RESAMPLE:
+            return self.ConvMeanPool(output, self.DIM_D, filter_size=3, name='D.Block.1.Conv2', he_init=True, residual=shortcut, **kw)
         output = self.ConvMeanPool(output, self.DIM_D, filter_size=3, name='D.Block.1.Conv2', he_init=True, **kw)
         return AddOp(shortcut, output).y
 

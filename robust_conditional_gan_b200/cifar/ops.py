@@ -5,7 +5,7 @@ import torch
 from .. import scope as S
 from .. import sn
 from ..graph import cur
-from ..nnops import BatchNormOp, ConvOp, DeconvOp, FoldWeightOp, GatherRowsOp
+from ..nnops import AddOp, BatchNormOp, ConvOp, DeconvOp, FoldWeightOp, GatherRowsOp, Upsample2Op
 
 
 def _uniform(stdev):
@@ -21,12 +21,16 @@ def _const(v):
 
 def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name=None, conv_type='conv2d', channel_multiplier=0,
            padding='SAME', spectral_normed=False, update_collection=None, inputs_norm=False, he_init=True, mask_type=None,
-           weightnorm=None, biases=True, gain=1., fuse_act=None, pre_norm=False, residual=None, up_op=None, fold=None):
+           weightnorm=None, biases=True, gain=1., fuse_act=None, pre_norm=False, residual=None, up_op=None, fold=None,
+           residual_up=False):
     """cifar10/common/ops/conv2d.py:31-218, plain conv2d branch: uniform He/Glorot init (:83-127), spectral norm under
     scope `filters` (:169-171), stride-`stride` SAME conv (:181-187), + Biases (:212-216).
     fold='pool': the caller mean-pools this 3x3 conv's output (ConvMeanPool) -> ONE 4x4 stride-2 conv with the folded filter;
     fold='up': the caller feeds the 2x nearest-neighbour upsampling of `inputs` (UpsampleConv; pass the SMALL tensor) -> ONE
-    4x4 stride-2 conv2d_transpose.  Variables, initialisers and the spectral norm are those of the 3x3 filter."""
+    4x4 stride-2 conv2d_transpose.  Variables, initialisers and the spectral norm are those of the 3x3 filter.
+    residual (+ residual_up): `shortcut + output` of the calling ResidualBlock (gan_resnet.py:328) added in this conv's epilogue;
+    residual_up: the shortcut is still at HALF resolution (1x1 UpsampleConv computed on the small grid) and is upsampled on the
+    fly.  Where the conv has no fused-epilogue path the same result is produced with explicit upsample / add kernels."""
     if conv_type != 'conv2d' or channel_multiplier or mask_type is not None or weightnorm or inputs_norm or padding != 'SAME':
         raise NotImplementedError('only the plain conv2d branch is reachable from gan_resnet.py')
     assert inputs.shape[-1] == input_dim
@@ -40,14 +44,21 @@ def Conv2D(inputs, input_dim, output_dim, filter_size=3, stride=1, name=None, co
             with S.variable_scope('filters'):
                 w = sn.spectral_normed_weight(filters, update_collection=update_collection)
         b = S.get_variable('Biases', [output_dim], _const(0.)) if biases else None
-    if fold is not None:
+    if fold == 'up':
         assert filter_size == 3 and stride == 1 and residual is None and up_op is None
-        w4 = FoldWeightOp(w, fold).w4
-        if fold == 'pool':
-            return ConvOp(inputs, w4, b, 2, fuse_act, pre_norm=pre_norm).y
         n, h, wd = inputs.shape[0], inputs.shape[1], inputs.shape[2]
-        return DeconvOp(inputs, w4, b, (2 * h, 2 * wd), 2, fuse_act, pre_norm=pre_norm).y
-    return ConvOp(inputs, w, b, stride, fuse_act, pre_norm=pre_norm, residual=residual, up_op=up_op).y
+        return DeconvOp(inputs, FoldWeightOp(w, fold).w4, b, (2 * h, 2 * wd), 2, fuse_act, pre_norm=pre_norm).y
+    if fold == 'pool':
+        assert filter_size == 3 and stride == 1 and up_op is None
+        op = ConvOp(inputs, FoldWeightOp(w, fold).w4, b, 2, fuse_act, pre_norm=pre_norm)
+    else:
+        op = ConvOp(inputs, w, b, stride, fuse_act, pre_norm=pre_norm, up_op=up_op)
+    if residual is None:
+        return op.y
+    if op._plain_tc_fprop() or not residual_up:
+        op.attach_residual(residual, residual_up)
+        return op.y
+    return AddOp(Upsample2Op(residual).y if residual_up else residual, op.y).y
 
 
 def Linear(inputs, input_dim, output_dim, name=None, spectral_normed=False, update_collection=None, reuse=None,

@@ -176,7 +176,7 @@ template <int BN, int ST> struct Cfg {
 // 1x1 256->256 conv at 512x32x32 were those stores).  Instead each warp stages its 32 rows in shared memory (row pitch
 // padded by 16 B: conflict-free 16-byte accesses) and then writes whole rows, consecutive lanes on consecutive 16-byte
 // pieces.  Only the owning warp touches its slab, so __syncwarp() orders the two phases.
-template <int BN, int AVAIL, typename TO>
+template <int BN, int AVAIL, typename TO, int U = 4>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
                                             int n0, uint32_t tempty_bar = 0, int bn_lim = BN) {
   constexpr int VEC = 16 / (int)sizeof(TO);
@@ -280,7 +280,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
       // The extra operands (mask, residual / old value) are global loads in the store loop: U pieces per lane are put in flight
       // before the first one is consumed (a dependent load-use chain per piece made this epilogue slower than the tile's main
       // loop: 25.8 vs 24.2 ms per iteration with the separate passes)
-      constexpr int U = 4;
       const int lpr = ncols / VEC;
       const int drow = 32 / lpr, dpiece = 32 - drow * lpr;
       int row = lane / lpr, piece = lane - row * lpr;
@@ -310,21 +309,21 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
         for (int u = 0; u < U; u++) {
           if (!live[u]) continue;
           __nv_bfloat162* c = reinterpret_cast<__nv_bfloat162*>(&q[u]);
-          if (mask) {
-            const __nv_bfloat162* mm = reinterpret_cast<const __nv_bfloat162*>(&mq[u]);
+          // fp32 throughout, ONE rounding at the end: exactly what rcgan_act_bwd (dx (=|+=) dy * act'(y)) and rcgan_add compute
+          const __nv_bfloat162* mm = reinterpret_cast<const __nv_bfloat162*>(&mq[u]);
+          const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&aq[u]);
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const float2 fm = __bfloat1622float2(mm[e]), fc = __bfloat1622float2(c[e]);
-              c[e] = __floats2bfloat162_rn(fm.x > 0.f ? fc.x : mleak * fc.x, fm.y > 0.f ? fc.y : mleak * fc.y);
+          for (int e = 0; e < 4; e++) {
+            float2 fc = __bfloat1622float2(c[e]);
+            if (mask) {
+              const float2 fm = __bfloat1622float2(mm[e]);
+              fc.x = fm.x > 0.f ? fc.x : mleak * fc.x; fc.y = fm.y > 0.f ? fc.y : mleak * fc.y;
             }
-          }
-          if (addsrc) {
-            const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&aq[u]);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const float2 fa = __bfloat1622float2(a[e]), fc = __bfloat1622float2(c[e]);
-              c[e] = __floats2bfloat162_rn(fa.x + fc.x, fa.y + fc.y);
+            if (addsrc) {
+              const float2 fa = __bfloat1622float2(a[e]);
+              fc.x += fa.x; fc.y += fa.y;
             }
+            c[e] = __floats2bfloat162_rn(fc.x, fc.y);
           }
           *reinterpret_cast<uint4*>(out + off[u]) = q[u];
           if (out2) {
@@ -343,7 +342,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
         const unsigned long long o = rowoff[row];
         if (o == ~0ull) continue;
         float x = to_f(reinterpret_cast<const TO*>(slab + row * PITCH)[cc]);
-        if (mask) x = to_f(from_f<TO>(to_f(mask[o + n0 + cc]) > 0.f ? x : mleak * x));
+        if (mask) x = to_f(mask[o + n0 + cc]) > 0.f ? x : mleak * x;
         if (addsrc) x += to_f(addsrc[(up ? rowoff_res[row] : o) + n0 + cc]);
         const TO v = from_f<TO>(x);
         out[o + n0 + cc] = v;
@@ -659,7 +658,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < MT; j++)
-        tc_epilogue<BN, C::EPI_BYTES, TO>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
+        tc_epilogue<BN, C::EPI_BYTES, TO, 8>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
                                           j == MT - 1 ? smem_u32(&tempty[a]) : 0u, bn);
     }
     tc_fence_before();

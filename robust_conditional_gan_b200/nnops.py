@@ -185,6 +185,17 @@ class ConvOp(Op):
         return (self.x.dtype == _C.BF16 and self.y.dtype == _C.BF16 and self.pack is not None and self.patch is None
                 and self.tpatch is None and self.up_op is None and bool(_C.load().rcgan_conv_uses_tensor_cores(self.desc, 0)))
 
+    def attach_residual(self, residual, up=False):
+        """y = conv(x) + b + [upsample2](residual), decided right after construction (the caller first asks _plain_tc_fprop())"""
+        prog = cur()
+        assert self.res is None and prog.ops[-1] is self and self.act == _C.ACT_NONE and self.y.dtype == self.x.dtype
+        n, ho, wo = spatial(self.y)
+        rshape = (n, ho // 2, wo // 2, self.y.c) if up else tuple(self.y.shape)
+        assert tuple(residual.shape) == rshape and residual.ld == residual.c and residual.dtype == self.x.dtype
+        assert not up or (ho % 2 == 0 and wo % 2 == 0 and self._plain_tc_fprop())
+        self.res, self.res_up = residual, bool(up)
+        self.inputs = (self.x, self.w, self.b, residual)
+
     def can_emit_relu(self):
         return FUSE_RELU_OUT and self.y2 is None and self.act == _C.ACT_NONE and self._plain_tc_fprop()
 

@@ -61,6 +61,7 @@ def relu_flips(prog, rec):
     for o in prog.ops:
         if isinstance(o, nnops.BatchNormOp) and o.act == _C.ACT_RELU: masks.append(o.y.torch() > 0)
         elif isinstance(o, nnops.ConvOp) and o.act == _C.ACT_RELU: masks.append(o.y.torch() > 0)
+        elif isinstance(o, nnops.ConvOp) and o.y2 is not None: masks.append(o.y2.torch() > 0)   # relu(y) as second output
         elif isinstance(o, nnops.ActOp) and o.act == _C.ACT_RELU: masks.append(o.y.torch() > 0)
         elif isinstance(o, nnops.MeanHWOp) and o.relu: masks.append(o.x.torch() > 0)
     assert len(masks) == len(rec), (len(masks), len(rec))
