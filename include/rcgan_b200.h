@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 6
+#define RCGAN_ABI_VERSION 8
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -135,6 +135,9 @@ int rcgan_im2col(const rcgan_conv_desc* d, const void* x, void* patches, int ldp
  * this filter, so its backward runs as patch-matrix GEMMs like the few-input-channel convs above; applied to the GEMM's
  * filter gradient (cin/cout swapped) the same call maps it back. */
 int rcgan_wflip(const float* w, float* out, int kh, int kw, int cin, int cout, int accumulate, void* stream);
+/* `count` fp32 copies dst[i][0..numel[i]) = src[i][...] in one launch: the u <- u_new assignments of all spectral norms after a
+ * step (mnist/sn.py:62-71, update_collection=None) */
+int rcgan_copy_batched(int count, const float* const* src, float* const* dst, const long* numel, void* stream);
 /* 3x3 filter folded with a 2x resampling into a 4x4 stride-2 filter (both maps linear; SURVEY section 7: "ConvMeanPool == 4x4-s2
  * conv and Upsample+3x3 == four 2x2 sub-pixel convs are algorithmic flop reductions, legal for results parity").
  *   mode 0: ConvMeanPool (cifar10/gan_resnet.py:231-241): meanpool2(conv3x3_SAME(x, w)) == conv4x4_stride2_SAME(x, w4), w4 HWIO
@@ -193,11 +196,13 @@ size_t rcgan_bn_workspace(int samples, int hw, int c);
 int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale, const float* offset,
                  const int* labels, float eps, int act, float leak, int train, float decay, float* moving_mean,
                  float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream);
-/* dx (=|+=) ; dscale/doffset [n_labels, c] (=|+=).  y is the activated forward output. */
+/* dx (=|+=) ; dscale/doffset [n_labels, c] (=|+=).  y is the activated forward output; with `offset` (the forward's table)
+ * given and act relu / lrelu, the activation mask is re-derived from x as the sign of the forward pre-activation and y is not
+ * read (may be NULL): 5 instead of 7 tensor passes. */
 int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype, int ydtype,
                  const float* scale, const int* labels, int n_labels, const float* save, int act, float leak,
                  float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws, size_t ws_bytes,
-                 void* stream);
+                 const float* offset, void* stream);
 /* Batch norm with the label concat that follows it in the MNIST generator fused in (mnist/model.py:714-728: h = relu(bn(.)),
  * then concat([h, y]) / conv_cond_concat(h, yb)): y has row stride ldy >= c + c2 (a multiple of 8), its channels [c, c + c2)
  * receive yb[sample, :] (fp32 [samples, c2]), the rest of the padding is left untouched; the backward reads dy / y with the
@@ -208,7 +213,7 @@ int rcgan_bn_fwd_cat(const void* x, void* y, int ldy, const float* yb, int c2, i
 int rcgan_bn_bwd_cat(const void* dy, const void* x, const void* y, int ldy, void* dx, int samples, int hw, int c, int xdtype,
                      int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act, float leak,
                      float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws, size_t ws_bytes,
-                     void* stream);
+                     const float* offset, void* stream);
 
 /* ---------------------------------------------------------------- spectral norm
  * spectral_normed_weight (mnist/sn.py:17-75 == cifar10/common/ops/sn.py), one power iteration.

@@ -328,6 +328,8 @@ class RCGANCifar(object):
         self._host_losses = {p.name: torch.zeros(max(len(p.loss_names), 1), dtype=torch.float32).pin_memory()
                              for p in (self.d_prog, self.g_prog)}
         self.iteration = 0
+        self._g_weights_dirty = True
+        self.store.on_load.append(lambda: setattr(self, '_g_weights_dirty', True))
 
     # ------------------------------------------------------------------ steps
     def _push_lr(self, key, value):
@@ -340,12 +342,12 @@ class RCGANCifar(object):
         from ..parallel import allreduce_sum_
         allreduce_sum_(group.grads, self.world_size)
 
-    def _body_a(self, prog, keys):
+    def _body_a(self, prog, keys, refresh_foreign=True):
         for k in keys:
             if k in self.groups:
                 g = self.groups[k]
                 _C.call('rcgan_zero', g.grads.data_ptr(), g.numel * 4, _C.stream_ptr())
-        prog.run_forward()
+        prog.run_forward(refresh_foreign)
         prog.run_backward()
 
     def _body_b(self, prog, keys):
@@ -387,29 +389,35 @@ class RCGANCifar(object):
         for k, g in self.groups.items():
             g.m.copy_(snap['__m_' + k]); g.v.copy_(snap['__v_' + k])
 
-    def _step(self, prog, keys, tag, lrs):
+    def _step(self, prog, keys, tag, lrs, refresh_foreign=True):
         for k in keys:
             if k in self.groups:
                 self.groups[k].t += 1
                 self._push_lr(k, tf_adam_lr(lrs[k], 0.0, 0.9, self.groups[k].t))
+        if not refresh_foreign:
+            tag += '_keep'            # a second captured graph: the other optimizer's folds / weight packs are not refreshed
         if self.world_size > 1:
-            self._run(tag + '_a', lambda: self._body_a(prog, keys))
+            self._run(tag + '_a', lambda: self._body_a(prog, keys, refresh_foreign))
             for k in keys:
                 if k in self.groups:
                     self._allreduce(self.groups[k])
             self._run(tag + '_b', lambda: self._body_b(prog, keys))
         else:
-            self._run(tag, lambda: (self._body_a(prog, keys), self._body_b(prog, keys)))
+            self._run(tag, lambda: (self._body_a(prog, keys, refresh_foreign), self._body_b(prog, keys)))
 
     def d_step(self, it=None):
         it = self.iteration if it is None else it
-        self._step(self.d_prog, ('d',), 'd', {'d': self.FLAGS.lr * lr_decay(it)})
+        # the generator's folded filters / weight packs inside the D program only change with a G step (or a load): of the
+        # N_CRITIC discriminator steps of an iteration only the first refreshes them
+        refresh, self._g_weights_dirty = self._g_weights_dirty, False
+        self._step(self.d_prog, ('d',), 'd', {'d': self.FLAGS.lr * lr_decay(it)}, refresh_foreign=refresh)
 
     def g_step(self, it=None):
         it = self.iteration if it is None else it
         F = self.FLAGS
         clr = F.lr * F.confuse_multiplier * (lr_decay(it) if F.confuse_lr_decay else 1.0)
         self._step(self.g_prog, ('g', 'c'), 'g', {'g': F.lr * lr_decay(it), 'c': clr})
+        self._g_weights_dirty = True
 
     def feed(self, prog, **feeds):
         for name, src in feeds.items():

@@ -315,13 +315,16 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
 #pragma unroll
           for (int e = 0; e < 4; e++) {
             float2 fc = __bfloat1622float2(c[e]);
+            float2 sl = make_float2(1.f, 1.f);
             if (mask) {
               const float2 fm = __bfloat1622float2(mm[e]);
-              fc.x = fm.x > 0.f ? fc.x : mleak * fc.x; fc.y = fm.y > 0.f ? fc.y : mleak * fc.y;
+              sl.x = fm.x > 0.f ? 1.f : mleak; sl.y = fm.y > 0.f ? 1.f : mleak;
             }
-            if (addsrc) {
+            if (addsrc) {       // explicit fma / mul: the same operation rcgan_act_bwd performs (bit-identical results)
               const float2 fa = __bfloat1622float2(a[e]);
-              fc.x += fa.x; fc.y += fa.y;
+              fc.x = __fmaf_rn(fc.x, sl.x, fa.x); fc.y = __fmaf_rn(fc.y, sl.y, fa.y);
+            } else {
+              fc.x = __fmul_rn(fc.x, sl.x); fc.y = __fmul_rn(fc.y, sl.y);
             }
             c[e] = __floats2bfloat162_rn(fc.x, fc.y);
           }
@@ -342,8 +345,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
         const unsigned long long o = rowoff[row];
         if (o == ~0ull) continue;
         float x = to_f(reinterpret_cast<const TO*>(slab + row * PITCH)[cc]);
-        if (mask) x = to_f(mask[o + n0 + cc]) > 0.f ? x : mleak * x;
-        if (addsrc) x += to_f(addsrc[(up ? rowoff_res[row] : o) + n0 + cc]);
+        const float sl = (mask && !(to_f(mask[o + n0 + cc]) > 0.f)) ? mleak : 1.f;
+        x = addsrc ? __fmaf_rn(x, sl, to_f(addsrc[(up ? rowoff_res[row] : o) + n0 + cc])) : __fmul_rn(x, sl);
         const TO v = from_f<TO>(x);
         out[o + n0 + cc] = v;
         if (out2) out2[o + n0 + cc] = from_f<TO>(fmaxf(to_f(v), 0.f));

@@ -240,26 +240,39 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
 template <typename TX, typename TY, int V>
 __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
                                                              const TY* __restrict__ y, Geo g, const float* __restrict__ save,
-                                                             int act, float leak, float* __restrict__ ws) {
+                                                             int act, float leak, float* __restrict__ ws,
+                                                             const float* __restrict__ scale, const float* __restrict__ offset,
+                                                             const int* __restrict__ labels) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float sh[];
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
   const int chunk = blockIdx.y;
   const int r0 = chunk * g.chunk_rows, r1 = min(g.rows, r0 + g.chunk_rows);
-  float s1[V], s2[V], mean[V], istd[V];
+  float s1[V], s2[V], mean[V], istd[V], ca[V], cb[V];
 #pragma unroll
-  for (int i = 0; i < V; i++) { s1[i] = 0.f; s2[i] = 0.f; mean[i] = 0.f; istd[i] = 0.f; }
+  for (int i = 0; i < V; i++) { s1[i] = 0.f; s2[i] = 0.f; mean[i] = 0.f; istd[i] = 0.f; ca[i] = 0.f; cb[i] = 0.f; }
+  // relu / lrelu: the sign of the forward pre-activation a*x + b (same expression as bn_apply_kernel) IS the mask y > 0, so
+  // the output tensor is not read back (2 of the 7 tensor passes of the backward)
+  const bool from_x = offset != nullptr && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU);
   if (cv < g.cg) {
 #pragma unroll
     for (int i = 0; i < V; i++) { mean[i] = save[cv * V + i]; istd[i] = save[g.c + cv * V + i]; }
+    if (from_x) {
+      const size_t tab = (size_t)(labels ? labels[r0 / g.hw] : 0) * g.c + (size_t)cv * V;
+#pragma unroll
+      for (int i = 0; i < V; i++) { ca[i] = istd[i] * scale[tab + i]; cb[i] = fmaf(-mean[i], ca[i], offset[tab + i]); }
+    }
 #pragma unroll 4
     for (int r = r0 + lr; r < r1; r += g.LR) {
       float vd[V], vx[V], vy[V];
       const size_t o = (size_t)r * g.c + (size_t)cv * V, oy = (size_t)r * g.ldy + (size_t)cv * V;
       load_vec<TY, V>(dy + oy, vd);
       load_vec<TX, V>(x + o, vx);
-      if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + oy, vy);
+      if (from_x) {
+#pragma unroll
+        for (int i = 0; i < V; i++) vy[i] = fmaf(vx[i], ca[i], cb[i]);
+      } else if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + oy, vy);
 #pragma unroll
       for (int i = 0; i < V; i++) {
         float gg = vd[i];
@@ -356,7 +369,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
                                                         const TY* __restrict__ y, TY* __restrict__ dx, Geo g,
                                                         const float* __restrict__ scale, const int* __restrict__ labels,
                                                         const float* __restrict__ save, const float* __restrict__ AB,
-                                                        int act, float leak, int accumulate) {
+                                                        int act, float leak, int accumulate, const float* __restrict__ offset) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int lc = threadIdx.x % g.LC, lr = threadIdx.x / g.LC;
   const int cv = blockIdx.x * g.LC + lc;
@@ -364,12 +377,14 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
   const int r0 = blockIdx.y * g.chunk_rows, r1 = min(g.rows, r0 + g.chunk_rows);
   const int ch = cv * V;
   const size_t tab = (size_t)(labels ? labels[r0 / g.hw] : 0) * g.c + ch;
-  float c1[V], c2[V], c3[V], mean[V];
+  float c1[V], c2[V], c3[V], mean[V], cb[V];
+  const bool from_x = offset != nullptr && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU);   // see bn_bwd_partial_kernel
 #pragma unroll
   for (int k = 0; k < V; k++) {
     const float istd = save[g.c + ch + k];
     mean[k] = save[ch + k];
     c1[k] = istd * scale[tab + k];
+    cb[k] = from_x ? fmaf(-mean[k], c1[k], offset[tab + k]) : 0.f;
     c2[k] = -istd * istd * AB[g.c + ch + k];
     c3[k] = -istd * AB[ch + k];
   }
@@ -379,7 +394,10 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
     float vd[V], vx[V], vy[V], o[V];
     load_vec<TY, V>(dy + offy, vd);
     load_vec<TX, V>(x + off, vx);
-    if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + offy, vy);
+    if (from_x) {
+#pragma unroll
+      for (int k = 0; k < V; k++) vy[k] = fmaf(vx[k], c1[k], cb[k]);
+    } else if (act != RCGAN_ACT_NONE) load_vec<TY, V>(y + offy, vy);
     if (accumulate) load_vec<TY, V>(dx + off, o);
 #pragma unroll
     for (int k = 0; k < V; k++) {
@@ -489,19 +507,20 @@ extern "C" int rcgan_bn_fwd_cat(const void* x, void* y, int ldy, const float* yb
 static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
                        int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
                        float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
-                       size_t ws_bytes, void* stream, int ldy) {
+                       size_t ws_bytes, void* stream, int ldy, const float* offset) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0 && n_labels > 0, "bn_bwd: bad shape");
   RCGAN_CHECK_ARG(ldy >= c && (ldy == c || ldy % 8 == 0), "bn_bwd: bad dy/y row stride");
   if (int e = check_types(xdtype, ydtype, "bn_bwd")) return e;
   RCGAN_CHECK_ARG(dy && x && dx && scale && save && dscale && doffset, "bn_bwd: null pointer");
-  RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y, "bn_bwd: activation needs y");
+  RCGAN_CHECK_ARG(act == RCGAN_ACT_NONE || y || (offset && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU)),
+                  "bn_bwd: the activation's backward needs y, or offset for relu / lrelu");
   cudaStream_t st = as_stream(stream);
   Geo g = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? stats_vmax() : 4);
   g.ldy = ldy;
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
-  BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(bn_bwd_partial_kernel<TX, TY, VV>, grid, 256, shb, st, (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws));
+  BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(bn_bwd_partial_kernel<TX, TY, VV>, grid, 256, shb, st, (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws, scale, offset, labels));
   RCGAN_LAUNCH_CHECK("bn_bwd_partial");
   launch_pdl(bn_bwd_finalize_kernel, ceil_div(c, 8), 256, 0, st, g, (float*)ws, scale, labels, n_labels, dscale, doffset,
                                                             accumulate_param);
@@ -510,7 +529,7 @@ static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, i
   Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
   ga.ldy = ldy;
   BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
-                                        leak, accumulate_dx));
+                                        leak, accumulate_dx, offset));
   RCGAN_LAUNCH_CHECK("bn_bwd_dx");
   return 0;
 }
@@ -518,17 +537,17 @@ static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, i
 extern "C" int rcgan_bn_bwd(const void* dy, const void* x, const void* y, void* dx, int samples, int hw, int c, int xdtype,
                             int ydtype, const float* scale, const int* labels, int n_labels, const float* save, int act,
                             float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param, void* ws,
-                            size_t ws_bytes, void* stream) {
+                            size_t ws_bytes, const float* offset, void* stream) {
   return bn_bwd_impl(dy, x, y, dx, samples, hw, c, xdtype, ydtype, scale, labels, n_labels, save, act, leak, dscale, doffset,
-                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, c);
+                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, c, offset);
 }
 
 extern "C" int rcgan_bn_bwd_cat(const void* dy, const void* x, const void* y, int ldy, void* dx, int samples, int hw, int c,
                                 int xdtype, int ydtype, const float* scale, const int* labels, int n_labels, const float* save,
                                 int act, float leak, float* dscale, float* doffset, int accumulate_dx, int accumulate_param,
-                                void* ws, size_t ws_bytes, void* stream) {
+                                void* ws, size_t ws_bytes, const float* offset, void* stream) {
   return bn_bwd_impl(dy, x, y, dx, samples, hw, c, xdtype, ydtype, scale, labels, n_labels, save, act, leak, dscale, doffset,
-                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, ldy);
+                     accumulate_dx, accumulate_param, ws, ws_bytes, stream, ldy, offset);
 }
 
 extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, int ldy, void* dx, int samples, int hw, int c, int dtype,
@@ -547,7 +566,7 @@ extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, int ldy, void* 
   ga.ldy = ldy;
   BN_DISPATCH(dtype, dtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy,
                                              (const TX*)dy, (const TY*)y, (TY*)dx, ga, scale, labels, save, (const float*)ws, act,
-                                             leak, accumulate_dx));
+                                             leak, accumulate_dx, (const float*)nullptr));
   RCGAN_LAUNCH_CHECK("bn_infer_bwd");
   return 0;
 }

@@ -131,6 +131,7 @@ class VariableStore:
         self.groups = {}
         self.finalized = False
         self.scope = []
+        self.on_load = []              # callbacks after load_state_dict (cached derived state, e.g. weight packs, is stale)
 
     def full_name(self, name):
         return '/'.join(self.scope + [name])
@@ -175,6 +176,8 @@ class VariableStore:
     def load_state_dict(self, sd):
         for n, t in sd.items():
             self.vars[n].data.copy_(torch.as_tensor(t).to(self.vars[n].data.device, torch.float32).reshape(-1))
+        for cb in self.on_load:
+            cb()
 
 
 class Workspace:
@@ -200,6 +203,7 @@ class Op:
     gradient buffer, whether this op is the first writer (overwrite) or a later one (accumulate)."""
     inputs = ()
     outputs = ()
+    foreign = False
     # an op whose inputs are parameters only (spectral norm, filter folds): Program.run_forward runs these first, followed by ONE
     # batched refresh of every tensor-core weight pack, and run_backward runs their backward last
     weight_only = False
@@ -245,6 +249,8 @@ class Program:
         self.packs = {}             # id(weight base) -> bf16 tensor-core weight pack (torch uint8 buffer)
         self.pack_jobs = []         # (desc, weight tensor, pack buffer) refreshed in one launch at the start of every run
         self._pack_args = None
+        self._pack_args_own = None
+        self._update_args = None
         self.finalized = False
 
     def __enter__(self):
@@ -295,17 +301,24 @@ class Program:
         self.pack_jobs.append((desc, w, buf))
         return True
 
-    def _refresh_packs(self):
+    def _refresh_packs(self, refresh_foreign=True):
         if not self.pack_jobs:
             return
         if self._pack_args is None:
             import ctypes
-            n = len(self.pack_jobs)
-            PA = ctypes.c_void_p * n
-            self._pack_args = (n, PA(*[ctypes.addressof(d) for d, _, _ in self.pack_jobs]),
-                               PA(*[w.data.data_ptr() for _, w, _ in self.pack_jobs]), PA(*[b.data_ptr() for _, _, b in self.pack_jobs]))
-        n, descs, ws, packs = self._pack_args
-        call('rcgan_conv_wpack_batched', n, descs, ws, packs, stream_ptr())
+
+            def args(jobs):
+                n = len(jobs)
+                PA = ctypes.c_void_p * max(n, 1)
+                return (n, PA(*[ctypes.addressof(d) for d, _, _ in jobs]), PA(*[w.data.data_ptr() for _, w, _ in jobs]),
+                        PA(*[b.data_ptr() for _, _, b in jobs]))
+            self._pack_args = args(self.pack_jobs)
+            # (variables are shared between programs, so their foreign-ness is decided against THIS program's wrt set)
+            foreign = lambda w: (id(w.base) not in self.wrt) if w.is_variable else getattr(w.base, 'foreign', False)
+            self._pack_args_own = args([j for j in self.pack_jobs if not foreign(j[1])])
+        n, descs, ws, packs = self._pack_args if refresh_foreign else self._pack_args_own
+        if n:
+            call('rcgan_conv_wpack_batched', n, descs, ws, packs, stream_ptr())
 
     def loss_slot(self, name):
         self.loss_names.append(name)
@@ -346,17 +359,35 @@ class Program:
                 t._grad = torch.zeros(t._data.numel(), dtype=TORCH_DTYPE[t.grad_dtype], device=self.device)
         for op in reversed(self.ops):
             op.plan_bwd(self)
+        # weight-only ops whose parameters are all outside `wrt` ("foreign": another optimizer's variables)
+        for op in self.ops:
+            op.foreign = False
+            if op.weight_only:
+                src = set()
+                for t in op.inputs:
+                    if t is None:
+                        continue
+                    src |= {id(t.base)} if t.is_variable else getattr(t.base, 'src_vars', set())
+                for u in getattr(op, 'state_inputs', ()):
+                    src.add(id(u.base))
+                op.foreign = bool(src) and not (src & wrt) and not getattr(op, 'updates_state', False)
+                for o in op.outputs:
+                    o.base.src_vars = src
+                    o.base.foreign = op.foreign
         self.ws.allocate(self.device)
         self.losses = torch.zeros(max(len(self.loss_names), 1), dtype=torch.float32, device=self.device)
         self.finalized = True
 
     # ---- execution (enqueue only; never synchronises)
-    def run_forward(self):
+    def run_forward(self, refresh_foreign=True):
+        """refresh_foreign=False: the folds / weight packs that depend only on variables this program does NOT train are taken
+        as still valid from the previous run (the caller knows those variables have not changed since: the generator's weights
+        over the discriminator steps of one iteration)"""
         call('rcgan_zero', self.losses.data_ptr(), self.losses.numel() * 4, stream_ptr())
         for op in self.ops:
-            if op.weight_only:
+            if op.weight_only and (refresh_foreign or not op.foreign):
                 op.forward(self)
-        self._refresh_packs()
+        self._refresh_packs(refresh_foreign)
         for op in self.ops:
             if not op.weight_only:
                 op.forward(self)
@@ -370,8 +401,16 @@ class Program:
                 op.backward(self)
 
     def run_updates(self):
-        for dst, src in self.updates:
-            call('rcgan_copy_acc', src.data.data_ptr(), dst.data.data_ptr(), dst.numel(), _C.F32, 0, stream_ptr())
+        if not self.updates:
+            return
+        if self._update_args is None:
+            import ctypes
+            n = len(self.updates)
+            PA, LA = ctypes.c_void_p * n, ctypes.c_long * n
+            self._update_args = (n, PA(*[s.data.data_ptr() for _, s in self.updates]), PA(*[d.data.data_ptr() for d, _ in self.updates]),
+                                 LA(*[d.numel() for d, _ in self.updates]))
+        n, srcs, dsts, numels = self._update_args
+        call('rcgan_copy_batched', n, srcs, dsts, numels, stream_ptr())
 
     def loss_dict(self, host):
         return {n: float(host[i]) for i, n in enumerate(self.loss_names)}

@@ -9,8 +9,11 @@ from . import _C
 from ._C import ConvDesc, call, stream_ptr
 from .graph import Op, Tensor, cur, is_static_weight, needs, round_up, same_pad
 
-# A/B switches of the fused-epilogue planning (default on)
-FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '1') == '1'
+# A/B switches of the fused-epilogue planning.  The activation backward inside the dgrad epilogue is bit-identical but measured
+# SLOWER (25.6 vs 23.8 ms per CIFAR iteration): its extra operand is a per-lane global load in a 4-warp epilogue, which cannot
+# keep enough bytes in flight for the short-K discriminator layers (the folded stride-2 conv has K = 512 per output tile and
+# would need ~35 GB/s per SM) -- it needs a TMA-staged mask tile; off by default until then
+FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '0') == '1'
 ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
 FUSE_RELU_OUT = os.environ.get('RCGAN_FUSE_RELU_OUT', '1') == '1'
 
@@ -515,7 +518,7 @@ class BatchNormOp(Op):
             dxp, accx = (gp(self.x), self.acc_x) if nx else (self.dx_dummy.data_ptr(), 0)
             call('rcgan_bn_bwd_cat', gp(self.y), dp(self.x), dp(self.y), self.y.ld, dxp, self.samples, self.hw, self.c, self.x.dtype,
                  self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels, self.save[0].data_ptr(), self.act, self.leak, dsc, dof,
-                 accx, accp, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+                 accx, accp, prog.ws.ptr(), prog.ws.bytes, dp(self.offset), stream_ptr())
             return
         xs, ys, gs = self.x.data.element_size(), self.y.data.element_size(), self.y.grad.element_size()
         for g in range(self.groups):
@@ -527,7 +530,7 @@ class BatchNormOp(Op):
             call('rcgan_bn_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), dxp,
                  self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels,
                  self.save[g].data_ptr(), self.act, self.leak, dsc, dof, accx, accp if g == 0 else 1, prog.ws.ptr(),
-                 prog.ws.bytes, stream_ptr())
+                 prog.ws.bytes, dp(self.offset), stream_ptr())
 
 
 class ActOp(Op):
@@ -673,6 +676,7 @@ class SpectralNormOp(Op):
         self.batched = bool(W.is_variable and u.is_variable)
         self.weight_only = self.batched
         self.wbar.static_weight = self.batched
+        self.updates_state = bool(update)          # u moves every run: never skippable as "unchanged since the last run"
 
     def plan_bwd(self, prog):
         self.acc_w = self.claim(self.W) if self.need[0] else 0

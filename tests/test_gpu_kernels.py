@@ -56,7 +56,12 @@ def test_bn_fwd_bwd(lib, samples, hw, c, act, xdt, dtype):
     dg, db = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
     # backward uses the oracle's y to decide the activation mask identically on both sides
     call('rcgan_bn_bwd', dyd.data_ptr(), xd.data_ptr(), y.data_ptr(), dx.data_ptr(), samples, hw, c, xdt, dtype,
-         keep(dev(gamma)), None, 1, save.data_ptr(), A, 0.2, dg.data_ptr(), db.data_ptr(), 0, 0, ws.data_ptr(), nb, st())
+         keep(dev(gamma)), None, 1, save.data_ptr(), A, 0.2, dg.data_ptr(), db.data_ptr(), 0, 0, ws.data_ptr(), nb, None, st())
+    # the product's form: the relu / lrelu mask re-derived from x (sign of the forward pre-activation) instead of reading y back
+    dx2, dg2, db2 = torch.zeros_like(dx), torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    call('rcgan_bn_bwd', dyd.data_ptr(), xd.data_ptr(), None, dx2.data_ptr(), samples, hw, c, xdt, dtype,
+         keep(dev(gamma)), None, 1, save.data_ptr(), A, 0.2, dg2.data_ptr(), db2.data_ptr(), 0, 0, ws.data_ptr(), nb, keep(dev(beta)), st())
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
     tol = TOL[dtype] * (3 if dtype == _C.BF16 else 1)
     assert relerr(dx.float(), xr.grad) < tol
     assert relerr(dg, gr.grad) < tol and relerr(db, br.grad) < tol
@@ -99,7 +104,11 @@ def test_bn_with_fused_label_concat(lib, samples, hw, c, c2, xdt, dtype):
     dx = torch.zeros(samples, hw, c, device='cuda', dtype=td)
     dg, db = torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
     call('rcgan_bn_bwd_cat', dyd.data_ptr(), xd.data_ptr(), y.data_ptr(), ld, dx.data_ptr(), samples, hw, c, xdt, dtype,
-         keep(dev(gamma)), None, 1, save.data_ptr(), _C.ACT_RELU, 0.0, dg.data_ptr(), db.data_ptr(), 0, 0, ws.data_ptr(), nb, st())
+         keep(dev(gamma)), None, 1, save.data_ptr(), _C.ACT_RELU, 0.0, dg.data_ptr(), db.data_ptr(), 0, 0, ws.data_ptr(), nb, None, st())
+    dx2, dg2, db2 = torch.zeros_like(dx), torch.zeros(c, device='cuda'), torch.zeros(c, device='cuda')
+    call('rcgan_bn_bwd_cat', dyd.data_ptr(), xd.data_ptr(), None, ld, dx2.data_ptr(), samples, hw, c, xdt, dtype, keep(dev(gamma)), None, 1,
+         save.data_ptr(), _C.ACT_RELU, 0.0, dg2.data_ptr(), db2.data_ptr(), 0, 0, ws.data_ptr(), nb, keep(dev(beta)), st())
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
     tol = TOL[dtype] * (3 if dtype == _C.BF16 else 1)
     assert relerr(dx.float(), xr.grad) < tol
     assert relerr(dg, gr.grad) < tol and relerr(db, br.grad) < tol
@@ -130,7 +139,11 @@ def test_cond_batchnorm(lib, n, hh, c, xdt, dtype):
     assert relerr(y.float(), yr) < TOL[dtype]
     ds, do = torch.ones(10, c, device='cuda'), torch.ones(10, c, device='cuda')
     call('rcgan_bn_bwd', dyd.data_ptr(), xd.data_ptr(), y.data_ptr(), dx.data_ptr(), n, hw, c, xdt, dtype, keep(dev(scale)),
-         lab.data_ptr(), 10, save.data_ptr(), _C.ACT_RELU, 0.0, ds.data_ptr(), do.data_ptr(), 0, 0, ws.data_ptr(), nb, st())
+         lab.data_ptr(), 10, save.data_ptr(), _C.ACT_RELU, 0.0, ds.data_ptr(), do.data_ptr(), 0, 0, ws.data_ptr(), nb, None, st())
+    dx2, ds2, do2 = torch.zeros_like(dx), torch.ones(10, c, device='cuda'), torch.ones(10, c, device='cuda')
+    call('rcgan_bn_bwd', dyd.data_ptr(), xd.data_ptr(), None, dx2.data_ptr(), n, hw, c, xdt, dtype, keep(dev(scale)), lab.data_ptr(), 10,
+         save.data_ptr(), _C.ACT_RELU, 0.0, ds2.data_ptr(), do2.data_ptr(), 0, 0, ws.data_ptr(), nb, keep(dev(offset)), st())
+    assert torch.equal(dx2, dx) and torch.equal(ds2, ds) and torch.equal(do2, do)
     tol = TOL[dtype] * (3 if dtype == _C.BF16 else 1)
     assert relerr(dx.float(), xr.grad) < tol
     assert relerr(ds, sr.grad) < tol and relerr(do, orf.grad) < tol

@@ -1,13 +1,20 @@
 """Host-side planning logic of the static-program runtime (graph.py / nnops.py) on a CPU-only box: programs are BUILT
 and PLANNED here (buffers on the CPU, library loaded for its host-only shape queries); nothing is launched."""
+import pytest
 import torch
 
-from robust_conditional_gan_b200 import _C, scope as S
+from robust_conditional_gan_b200 import _C, nnops, scope as S
 from robust_conditional_gan_b200.graph import Program, VariableStore
 from robust_conditional_gan_b200.nnops import (ActOp, AddOp, BatchNormOp, CastOp, ChannelLossOp, ConvOp, DeconvOp, MeanHWOp,
                                                SpectralNormOp, Upsample2Op)
 
 DEV = torch.device('cpu')
+
+
+@pytest.fixture(autouse=True)
+def fused_act_backward_on(monkeypatch):
+    """the planning of the (opt-in, RCGAN_FUSE_ACT_BWD=1) activation backward inside the dgrad epilogue is covered here too"""
+    monkeypatch.setattr(nnops, 'FUSE_ACT_BWD', True)
 
 
 def store_with(**shapes):

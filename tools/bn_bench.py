@@ -44,7 +44,7 @@ def main():
             def bwd():
                 _C.call('rcgan_bn_bwd', dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), n, hw, c, _C.BF16, _C.BF16,
                         scale.data_ptr(), lp, L, save.data_ptr(), _C.ACT_RELU, 0.0, dscale.data_ptr(), doffset.data_ptr(), 0, 0,
-                        ws.data_ptr(), wsb, st)
+                        ws.data_ptr(), wsb, offset.data_ptr(), st)
             res = []
             for fn in (fwd, bwd):
                 fn()
