@@ -1355,7 +1355,7 @@ extern "C" int rcgan_conv_wpack_batched(int count, const rcgan_conv_desc* const*
       WpackItem& t = b.it[k];
       t.w = w[i0 + k]; t.packF = pk; t.packD = pk + g.offD; t.taps = g.taps; t.cin = d->cin; t.cout = d->cout;
       t.kpadF = g.kpadF; t.kpadD = g.kpadD;
-      t.nblk = (int)(items < 2 * RCGAN_NUM_SMS ? items : 2 * RCGAN_NUM_SMS);
+      t.nblk = (int)(items < 8 * RCGAN_NUM_SMS ? items : 8 * RCGAN_NUM_SMS);
       if (t.nblk > max_blk) max_blk = t.nblk;
     }
     launch_pdl(wpack_batched_kernel, dim3(max_blk, n), 256, 0, as_stream(stream), b);

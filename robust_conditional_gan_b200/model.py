@@ -523,6 +523,10 @@ class DCGAN(object):
             self.batch_size = saved_B
         rp.finalize([self.z_recover, self.y_logit_recover])
         self._r_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # graphs captured over a previous recover program replay ITS buffers: drop them (a second build_recover /
+        # recover_labels call starts from freshly initialised z_recover / y_logit_recover, like the reference's re-initialisation)
+        for key in [k_ for k_ in self._graphs if k_.startswith('recover_')]:
+            del self._graphs[key]
         return rp
 
     def _r_body(self, lr):
@@ -562,19 +566,57 @@ class DCGAN(object):
             zero_one = float((1.0 - (ya * onehot).sum(-1)).mean())
         return y_rec, mse, zero_one
 
+    def noise_schedule(self, epoch):
+        """mnist/model.py:293-321 (--add_noise, run_rcgany.sh): the one-coin confusion matrix the labels are re-noised with at
+        the start of `epoch`.  Returns (noise_alpha, noise_C)."""
+        cfg, k = self.config, self.y_dim
+        alpha_start = (self.noise_alpha - (1. - self.alpha) / (k - 1)) / (self.alpha - (1. - self.alpha) / (k - 1))
+        alpha_start = min(1.0, alpha_start)
+        if self.noise_alpha > 0.9:
+            raise ValueError('same rate activated, but effective noise alpha {} > 0.9!'.format(self.noise_alpha))
+        if alpha_start == 1.:
+            end_epoch = cfg.noise_start
+        else:
+            end_epoch = cfg.noise_start + ((cfg.noise_end - cfg.noise_start) / (0.9 - self.noise_alpha) * (self.alpha - self.noise_alpha))
+            end_epoch = min(cfg.noise_end, end_epoch)
+        if epoch < cfg.noise_start:
+            noise_alpha = alpha_start
+        elif epoch < end_epoch:
+            noise_alpha = alpha_start + (1. - alpha_start) * (epoch - cfg.noise_start) / (end_epoch - cfg.noise_start)
+        else:
+            noise_alpha = 1.0
+        noise_alpha = min(1.0, noise_alpha)
+        return noise_alpha, one_coin_confusion(noise_alpha, k)
+
+    def renoise_labels(self, epoch):
+        """mnist/model.py:323-333: data_y_real / data_y_fake are re-drawn through noise_C, sample by sample (real then fake), from
+        the same numpy stream -- on the device, bit-exact (rcgan_sample_renoise_mnist).  Cumulative, as in the reference: the
+        labels of the previous epoch are the input."""
+        _, noise_C = self.noise_schedule(epoch)
+        real, fake = self.sampler_state.renoise_mnist(self.data_y_real.argmax(-1), self.data_y_fake.argmax(-1), noise_C)
+        eye = np.eye(self.y_dim)
+        self.data_y_real, self.data_y_fake = eye[real], eye[fake]
+
     def train(self, config=None, max_iters=None, log_every=100):
-        """mnist/model.py:249-491 hot loop over self.data_* (logging evals, checkpoints, sample grids and the
-        frozen-classifier metric are outside the hot path and not reproduced)."""
+        """mnist/model.py:249-491 hot loop over self.data_*: the sample_z draw (:274), per epoch the --add_noise re-noising of
+        the real / fake labels (:293-333), per batch the z draw (:342) and 1 D + 2 G(+C) steps (:344-372) -- every random number
+        from the one numpy-legacy stream seeded in load_mnist, so batch_z and the labels follow the reference's stream position.
+        (Logging evals, checkpoints every 500 steps (`save`), sample grids and the frozen-classifier metric are outside the hot
+        path; see checkpoint.py / metrics.py.)"""
         config = config or self.config
         n = len(self.data_X)
         batch_idxs = min(n, config.train_size) // config.batch_size
         B = config.batch_size
         start_time = time.time()
         pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).pin_memory()
-        X, yr, yg, yf, yw = (pin(self.data_X), pin(self.data_y_real), pin(self.data_y_gen), pin(self.data_y_fake),
-                             pin(self.data_y_real_weights))
+        X, yg, yw = pin(self.data_X), pin(self.data_y_gen), pin(self.data_y_real_weights)
+        yr, yf = pin(self.data_y_real), pin(self.data_y_fake)
+        self.sample_z = self.sampler_state.uniform(-1, 1, self.sample_num * self.z_dim).reshape(self.sample_num, self.z_dim)
         it = 0
         for epoch in range(config.epoch):
+            if self.add_noise:
+                self.renoise_labels(epoch)
+                yr, yf = pin(self.data_y_real), pin(self.data_y_fake)
             for idx in range(0, int(batch_idxs)):
                 sl = slice(idx * B, (idx + 1) * B)
                 batch_z = self.sampler_state.uniform(-1, 1, B * self.z_dim).reshape(B, self.z_dim)

@@ -254,3 +254,47 @@ def test_full_batch_properties(lib):
     for n, v in V.items():
         if n.endswith('spectral_norm/u'):
             assert abs(float(v.data.norm()) - 1.0) < 1e-4, n
+
+
+def test_train_loop_follows_the_reference_random_stream(lib):
+    """DCGAN.train (mnist/model.py:249-372) with --add_noise (run_rcgany.sh): the sample_z draw, the per-epoch re-noising of the
+    real / fake labels (:293-333) and every batch_z come from the ONE numpy-legacy stream seeded in load_mnist -- replayed here
+    with numpy itself: labels after each epoch's re-noise and every batch_z must be identical."""
+    N, B = 200, 32
+    rs = np.random.RandomState(0)
+    X, y = rs.rand(N, 28, 28, 1).astype(np.float32), rs.randint(10, size=N)
+    kw = dict(RUNS['rcgan'])
+    flags = default_flags(batch_size=B, alpha=0.3, add_noise=True, noise_alpha=0.2, noise_start=1, noise_end=4, epoch=3,
+                          train_size=N, perm_regularizer=True, **kw)
+    model = DCGAN(batch_size=B, sample_num=B, algorithm='rcgan', estimate_confuse=False, perm_regularizer=True, alpha=0.3,
+                  disc_type='projection', add_noise=True, noise_alpha=0.2, config=flags, precision='fp32', use_cuda_graph=False,
+                  data=(X, y))
+    seen = []
+    model.train_iteration = lambda fetch_losses=False, **f: seen.append({k: torch.as_tensor(v).cpu().numpy().copy() for k, v in f.items()})
+    model.train(flags, log_every=10 ** 9)
+    # ---- the same sequence with numpy (the reference's own dependency), literally as mnist/model.py does it
+    C = OS.one_coin_confusion(0.3)
+    ref = OS.mnist_labels_numpy(y, C, real_match=False, seed=547, shuffle=True)      # leaves np.random at the post-sampler state
+    sample_z = np.random.uniform(-1, 1, size=(B, 100))
+    assert np.array_equal(model.sample_z.cpu().numpy(), sample_z.astype(np.float32))
+    y_real, y_fake = ref['y_real'], ref['y_fake']
+    it = 0
+    for epoch in range(3):
+        na, noise_C = model.noise_schedule(epoch)
+        y_real, y_fake = OS.mnist_renoise_numpy(y_real, y_fake, noise_C)
+        for idx in range(N // B):
+            z = np.random.uniform(-1, 1, [B, 100]).astype(np.float32)
+            got = seen[it]
+            assert np.array_equal(got['batch_z'], z), (epoch, idx)
+            assert np.array_equal(got['batch_labels_real'], y_real[idx * B:(idx + 1) * B]), (epoch, idx)
+            assert np.array_equal(got['batch_labels_fake'], y_fake[idx * B:(idx + 1) * B]), (epoch, idx)
+            assert np.array_equal(got['batch_labels_gen'], ref['y_gen'][idx * B:(idx + 1) * B])
+            it += 1
+    assert it == len(seen)
+    # the schedule itself (:293-321): alpha_start, linear ramp between noise_start and end_epoch, 1.0 afterwards
+    a0 = (0.2 - 0.7 / 9) / (0.3 - 0.7 / 9)
+    assert abs(model.noise_schedule(0)[0] - a0) < 1e-12 and model.noise_schedule(50)[0] == 1.0
+    end = min(4, 1 + (4 - 1) / (0.9 - 0.2) * (0.3 - 0.2))
+    assert abs(model.noise_schedule(1)[0] - a0) < 1e-12
+    mid = 1 + 0.5 * (end - 1)
+    assert model.noise_schedule(int(end) + 1)[0] == 1.0 and a0 < model.noise_schedule(mid)[0] < 1.0
