@@ -21,6 +21,7 @@ NO_OPS = 'NO_OPS'
 FUSE_RESIDUAL = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL', '1') == '1'
 # 3x3 ConvMeanPool / UpsampleConv as ONE 4x4 stride-2 conv / conv2d_transpose with the folded filter; 0 = A/B switch
 FOLD_RESAMPLE = __import__('os').environ.get('RCGAN_FOLD', '1') == '1'
+SPLIT_GRAPH = __import__('os').environ.get('RCGAN_DP_SPLIT_GRAPH', '0') == '1'
 Z_DIM, VOCAB_SIZE, EMBEDDING_DIM, IMG_SIZE, IMG_DIM, OUTPUT_DIM = 128, 10, 300, 32, 3, 3072
 N_CRITIC, GEN_BS_MULTIPLE = 5, 2
 
@@ -329,6 +330,11 @@ class RCGANCifar(object):
                              for p in (self.d_prog, self.g_prog)}
         self.iteration = 0
         self._g_weights_dirty = True
+        self.reducers = {}
+        if self.world_size > 1 and not SPLIT_GRAPH:
+            from ..parallel import GradReducer
+            self.reducers = {'d_step': GradReducer(self.d_prog, self.store, ('d',), self.world_size),
+                             'g_step': GradReducer(self.g_prog, self.store, ('g', 'c'), self.world_size)}
         self.store.on_load.append(lambda: setattr(self, '_g_weights_dirty', True))
 
     # ------------------------------------------------------------------ steps
@@ -371,7 +377,8 @@ class RCGANCifar(object):
             torch.cuda.synchronize()
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # (thread-local capture mode: NCCL's watchdog thread keeps polling its events while collectives are captured)
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world_size > 1 else 'global'):
                 fn()
             self._restore(snap)
             self._graphs[name] = g
@@ -396,14 +403,24 @@ class RCGANCifar(object):
                 self._push_lr(k, tf_adam_lr(lrs[k], 0.0, 0.9, self.groups[k].t))
         if not refresh_foreign:
             tag += '_keep'            # a second captured graph: the other optimizer's folds / weight packs are not refreshed
-        if self.world_size > 1:
+        if self.world_size > 1 and SPLIT_GRAPH:
+            # (A/B switch RCGAN_DP_SPLIT_GRAPH=1: the round-1 form, one blocking all-reduce per arena between two graph halves)
             self._run(tag + '_a', lambda: self._body_a(prog, keys, refresh_foreign))
             for k in keys:
                 if k in self.groups:
                     self._allreduce(self.groups[k])
             self._run(tag + '_b', lambda: self._body_b(prog, keys))
-        else:
-            self._run(tag, lambda: (self._body_a(prog, keys, refresh_foreign), self._body_b(prog, keys)))
+            return
+        # one graph per step; with world_size > 1 the gradient buckets are all-reduced from inside the backward sweep
+        # (parallel.GradReducer hooks) and joined in front of Adam
+        red = self.reducers.get(prog.name)
+
+        def body():
+            self._body_a(prog, keys, refresh_foreign)
+            if red is not None:
+                red.wait()
+            self._body_b(prog, keys)
+        self._run(tag, body)
 
     def d_step(self, it=None):
         it = self.iteration if it is None else it

@@ -160,9 +160,17 @@ class VariableStore:
                 off += round_up(v.numel(), 64)
             g.numel = off
             g.params = torch.zeros(off, dtype=torch.float32, device=self.device)
-            g.grads = torch.zeros(off, dtype=torch.float32, device=self.device)
             g.m = torch.zeros(off, dtype=torch.float32, device=self.device)
             g.v = torch.zeros(off, dtype=torch.float32, device=self.device)
+        # the gradient arenas of all groups are slices of ONE buffer: groups trained by the same step (generator + confusion
+        # matrix) are adjacent, so one collective covers them
+        self.all_grads = torch.zeros(sum(g.numel for g in self.groups.values()), dtype=torch.float32, device=self.device)
+        pos = 0
+        for g in sorted(self.groups.values(), key=lambda g_: {'g': 0, 'c': 1}.get(g_.name, 2)):
+            g.grad_offset = pos
+            g.grads = self.all_grads[pos:pos + g.numel]
+            pos += g.numel
+        for g in self.groups.values():
             for v in g.vars:
                 seg = g.params[v.offset:v.offset + v.numel()]
                 seg.copy_(v._data)
@@ -251,6 +259,7 @@ class Program:
         self._pack_args = None
         self._pack_args_own = None
         self._update_args = None
+        self.after_backward = {}    # op index -> [callable]; index len(ops) = before the sweep starts
         self.finalized = False
 
     def __enter__(self):
@@ -393,12 +402,16 @@ class Program:
                 op.forward(self)
 
     def run_backward(self):
+        """reverse program order (the weight-only ops too: a fold's backward directly follows its conv's, the batched spectral-norm
+        backward sits at the first normalised weight, i.e. after everything that feeds it).  after_backward[i]: callables run once
+        op i's backward is enqueued -- the data-parallel reducer launches a gradient bucket there (parallel.GradReducer)."""
+        hooks = self.after_backward
+        for h in hooks.get(len(self.ops), ()):
+            h()
         for op in reversed(self.ops):
-            if not op.weight_only:
-                op.backward(self)
-        for op in reversed(self.ops):
-            if op.weight_only:
-                op.backward(self)
+            op.backward(self)
+            for h in hooks.get(op.index, ()):
+                h()
 
     def run_updates(self):
         if not self.updates:

@@ -25,6 +25,8 @@ from .graph import Program, VariableStore, tf_adam_lr
 from .nnops import (CastOp, ChannelLossOp, ConcatRowsOp, ConvOp, LogitLossOp, MeanHWOp, RecoverMSEOp, SigmoidCEOp, SoftmaxRowsOp, adam_step)
 from .sampler import LabelNoiseSampler, class_dependent_confusion, one_coin_confusion
 
+SPLIT_GRAPH = __import__('os').environ.get('RCGAN_DP_SPLIT_GRAPH', '0') == '1'   # A/B: blocking all-reduce between two graph halves
+
 LOSS_MODES = {'hinge': (_C.HINGE_D_REAL, _C.HINGE_D_FAKE, _C.HINGE_G), 'ce': (_C.CE_D_REAL, _C.CE_D_FAKE, _C.CE_G)}
 
 
@@ -334,6 +336,11 @@ class DCGAN(object):
         self._lr_ring = torch.zeros(4096, dtype=torch.float32).pin_memory()
         self._lr_pos = 0
         self._graphs = {}
+        self.reducers = {}
+        if self.world_size > 1 and not SPLIT_GRAPH:
+            from .parallel import GradReducer
+            self.reducers = {'d_step': GradReducer(self.d_prog, self.store, ('d',), self.world_size),
+                             'g_step': GradReducer(self.g_prog, self.store, ('g', 'c'), self.world_size)}
         self._host_losses = {p.name: torch.zeros(max(len(p.loss_names), 1), dtype=torch.float32).pin_memory()
                              for p in (self.d_prog, self.g_prog)}
         self.counter = 0
@@ -393,7 +400,8 @@ class DCGAN(object):
             torch.cuda.synchronize()
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # (thread-local capture mode: NCCL's watchdog thread keeps polling its events while collectives are captured)
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world_size > 1 else 'global'):
                 fn()
             self._restore(snap)
             self._graphs[name] = g
@@ -422,10 +430,12 @@ class DCGAN(object):
         g = self.groups['d']
         g.t += 1
         self._push_lr('d', tf_adam_lr(cfg.learning_rate, cfg.beta1, 0.999, g.t))
-        if self.world_size > 1:
+        if self.world_size > 1 and SPLIT_GRAPH:
             self._run('d_a', self._d_body_a); self._allreduce(g); self._run('d_b', self._d_body_b)
         else:
-            self._run('d', lambda: (self._d_body_a(), self._d_body_b()))
+            # one graph per step; the gradient buckets are all-reduced from inside the backward sweep (parallel.GradReducer)
+            red = self.reducers.get('d_step')
+            self._run('d', lambda: (self._d_body_a(), red.wait() if red is not None else None, self._d_body_b()))
 
     def g_step(self):
         cfg = self.config
@@ -436,14 +446,15 @@ class DCGAN(object):
             c = self.groups['c']
             c.t += 1
             self._push_lr('c', tf_adam_lr(cfg.learning_rate * cfg.confuse_multiplier, cfg.beta1, 0.999, c.t))
-        if self.world_size > 1:
+        if self.world_size > 1 and SPLIT_GRAPH:
             self._run('g_a', self._g_body_a)
             self._allreduce(g)
             if 'c' in self.groups:
                 self._allreduce(self.groups['c'])
             self._run('g_b', self._g_body_b)
         else:
-            self._run('g', lambda: (self._g_body_a(), self._g_body_b()))
+            red = self.reducers.get('g_step')
+            self._run('g', lambda: (self._g_body_a(), red.wait() if red is not None else None, self._g_body_b()))
 
     def feed(self, batch_images=None, batch_z=None, batch_labels_real=None, batch_labels_gen=None, batch_labels_fake=None,
              batch_labels_real_weights=None):

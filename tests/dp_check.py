@@ -51,15 +51,31 @@ def main():
     other = flat.clone()
     dist.broadcast(other, src=0)
     same = bool(torch.equal(flat, other))
+    # G step from the same initial state: the bucketed all-reduce (generator arena + confusion_logits, launched from inside the
+    # backward sweep) against the R-tower generator cost
+    model.store.load_state_dict(P)
     model.g_step(1)
     torch.cuda.synchronize()
+    tr = OC.Trainer(OC.init_params(ocfg, seed=1, dtype=torch.float64), ocfg)
+    names = tr.gn + ['confusion_logits']
+    tr._req(names)
+    cost = sum(OC.gen_cost(tr.P, tower(r), ocfg)[0]['gen_cost'] for r in range(world)) / world
+    gs = dict(zip(names, torch.autograd.grad(cost, [tr.P[k] for k in names], allow_unused=True)))
+    worst_g = 0.0
+    for v in model.gen_params + model.c_params:
+        ref = gs[v.name]
+        if ref is None or float(ref.norm()) < 1e-10:
+            continue
+        got = v.grad.double().cpu().reshape(ref.shape) / world
+        worst_g = max(worst_g, float((got - ref).norm() / ref.norm()))
     flatg = model.groups['g'].params.clone(); og = flatg.clone(); dist.broadcast(og, src=0)
-    res = torch.tensor([worst, 0.0 if same else 1.0, 0.0 if torch.equal(flatg, og) else 1.0], device='cuda', dtype=torch.float64)
+    nb = {k: len(r.buckets) for k, r in model.reducers.items()}
+    res = torch.tensor([worst, 0.0 if same else 1.0, 0.0 if torch.equal(flatg, og) else 1.0, worst_g], device='cuda', dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print('DP_CHECK world=%d worst_D_grad_relerr=%.2e params_diverged_D=%d params_diverged_G=%d' % (
-            world, float(res[0]), int(res[1]), int(res[2])))
-        assert float(res[0]) < 3e-2 and int(res[1]) == 0 and int(res[2]) == 0
+        print('DP_CHECK world=%d worst_D_grad_relerr=%.2e worst_G_grad_relerr=%.2e params_diverged_D=%d params_diverged_G=%d buckets=%s' % (
+            world, float(res[0]), float(res[3]), int(res[1]), int(res[2]), nb))
+        assert float(res[0]) < 3e-2 and float(res[3]) < 3e-2 and int(res[1]) == 0 and int(res[2]) == 0
     dist.destroy_process_group()
 
 
