@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 8
+#define RCGAN_ABI_VERSION 9
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -320,6 +320,13 @@ int rcgan_mt_uniform(uint32_t* state, float* out, long n, double lo, double hi, 
 /* CIFAR real-data preprocessing (gan_resnet.py:548-552): int32 CHW [n,3072] in [0,255] ->
  * 2*(v/256 - .5) + noise[n,3072 NHWC-ordered after transpose] (noise may be NULL), NHWC, activation dtype */
 int rcgan_preprocess_cifar(const int32_t* chw, const float* noise, void* out, int n, int dtype, void* stream);
+/* the same from uint8 pixels: a quarter of the host -> device bytes of the int32 placeholder */
+int rcgan_preprocess_cifar_u8(const uint8_t* chw, const float* noise, void* out, int n, int dtype, void* stream);
+/* In-graph random inputs: out[i] = a + b * N(0,1) (normal != 0: tf.random_normal([n, 128]), gan_resnet.py:363-364) or U[a, b)
+ * (tf.random_uniform(0, 1/128) dequantisation noise, :550).  Philox4x32-10 keyed by `seed`, counter = (element block, *step_dev,
+ * stream_id): the step is read from device memory, so a captured CUDA graph draws new numbers on every replay. */
+int rcgan_random_fill(float* out, long n, int normal, float a, float b, unsigned long long seed, const long* step_dev,
+                      unsigned stream_id, void* stream);
 
 #ifdef __cplusplus
 }

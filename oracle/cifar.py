@@ -83,7 +83,11 @@ def init_params(cfg, seed=0, dtype=torch.float64):
     P[D + 'Embedding.Label/embedding_map'] = ((torch.rand((VOCAB, EMB), generator=g, dtype=torch.float64) * 2 - 1) * 0.08).to(dtype)
     lin(D + 'D.Embedding_y', EMB, dim, True)
     if cfg.perm_classifier:
-        lin(D + 'D.d_perm_classifier_h1', 3072, VOCAB, True)
+        if getattr(cfg, 'perm_type', 'linear') == '2layer':          # gan_resnet.py:467-480
+            lin(D + 'D.d_perm_classifier_h1', 3072, 128, True)
+            lin(D + 'D.d_perm_classifier_h2', 128, VOCAB, True)
+        else:
+            lin(D + 'D.d_perm_classifier_h1', 3072, VOCAB, True)
     if cfg.algorithm == 'rcgan-u':
         if cfg.confuse_init:
             aa = 7.0 if cfg.confuse_init_diag > 0.99 else np.log(VOCAB * cfg.confuse_init_diag / (1. - cfg.confuse_init_diag))
@@ -193,8 +197,12 @@ def Discriminator_projection(ctx, labels):
 
 
 def perm_classifier(ctx, x):
-    """gan_resnet.py:458-466 (perm_type linear)."""
-    return Linear(ctx, x.reshape(x.shape[0], -1), 'Discriminator/D.d_perm_classifier_h1', True)
+    """gan_resnet.py:456-483: perm_type 'linear' (one SN-Linear) or '2layer' (two, no nonlinearity between them) -- told apart
+    by the presence of the second layer's weights."""
+    h = Linear(ctx, x.reshape(x.shape[0], -1), 'Discriminator/D.d_perm_classifier_h1', True)
+    if 'Discriminator/D.d_perm_classifier_h2/W' in ctx.P:
+        h = Linear(ctx, h, 'Discriminator/D.d_perm_classifier_h2', True)
+    return h
 
 
 def confusion_matrix(P, cfg, dtype):

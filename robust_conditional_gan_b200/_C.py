@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 8        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 9        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -117,6 +117,8 @@ _SIGS = {
     'rcgan_sample_labels_cifar': (c_int, [P, P, c_int, P, c_int, P, P, P]),
     'rcgan_mt_uniform': (c_int, [P, P, c_long, c_double, c_double, P]),
     'rcgan_preprocess_cifar': (c_int, [P, P, P, c_int, c_int, P]),
+    'rcgan_preprocess_cifar_u8': (c_int, [P, P, P, c_int, c_int, P]),
+    'rcgan_random_fill': (c_int, [P, c_long, c_int, c_float, c_float, ctypes.c_ulonglong, P, c_uint32, P]),
 }
 EXPORTS = sorted(_SIGS)
 

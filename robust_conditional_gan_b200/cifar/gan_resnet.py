@@ -12,8 +12,9 @@ import numpy as np
 import torch
 
 from .. import _C, scope as S
-from ..graph import I32, Program, VariableStore, tf_adam_lr
-from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, ConcatRowsOp, ConvOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, SigmoidCEOp,
+from ..graph import I32, U8, Program, VariableStore, tf_adam_lr
+from ..nnops import (ActOp, AddOp, CastOp, ChannelLossOp, ConcatRowsOp, ConvOp, GatherRowsOp, MeanHWOp, Pool2Op, PreprocessCifarOp, RandomFillOp,
+                     SigmoidCEOp,
                      SoftmaxRowsOp, Upsample2Op, adam_step)
 from . import ops as lib_ops
 
@@ -39,8 +40,11 @@ def default_flags(**kw):
 class Net:
     """The module-level constants + network functions of gan_resnet.py, bound to one configuration."""
 
-    def __init__(self, algorithm, dim_g=128, dim_d=128):
+    def __init__(self, algorithm, dim_g=128, dim_d=128, towers=1, perm_type='linear'):
         self.ALGORITHM, self.DIM_G, self.DIM_D = algorithm, dim_g, dim_d
+        # towers > 1: the reference's in-process towers (gan_resnet.py:183-192, 529-546) -- the batch of this process is `towers`
+        # equal sample ranges; only the generator's conditional batch norms see the difference (statistics per tower)
+        self.towers, self.perm_type = towers, perm_type
 
     # gan_resnet.py:199-205
     @staticmethod
@@ -52,7 +56,8 @@ class Net:
         conditional batch norm in G, identity in D."""
         with S.variable_scope(name):
             if 'G.' in name and labels is not None:
-                return lib_ops.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, fuse_act=fuse_act)
+                return lib_ops.cond_batchnorm(name, [0, 1, 2], inputs, labels=labels, n_labels=10, fuse_act=fuse_act,
+                                              groups=self.towers)
         if fuse_act == 'relu':
             # D: the bare nonlinearity(inputs) (:318).  When `inputs` is the output of a conv with a fused-epilogue path (the previous
             # block's Conv2 + shortcut), that conv's epilogue writes relu(inputs) as a second output: no separate pass
@@ -188,12 +193,17 @@ class Net:
             return lib_ops.Linear(embedding_y, EMBEDDING_DIM, self.DIM_D, 'D.Embedding_y', spectral_normed=True,
                                   update_collection=update_collection, biases=True)
 
-    @staticmethod
-    def perm_classifier(x, reuse=False):
-        """:458-466 (perm_type 'linear'); x fp32 [n,32,32,3]."""
+    def perm_classifier(self, x, reuse=False):
+        """:456-483; x fp32 [n,32,32,3].  'linear': one SN-Linear 3072 -> 10; '2layer': SN-Linear 3072 -> 128 -> 10 (no
+        nonlinearity in between, as in the reference)."""
         with S.variable_scope("Discriminator"):
             flat = x.view([x.shape[0], OUTPUT_DIM])
-            return lib_ops.Linear(flat, OUTPUT_DIM, VOCAB_SIZE, 'D.d_perm_classifier_h1', spectral_normed=True, biases=True)
+            if self.perm_type == 'linear':
+                return lib_ops.Linear(flat, OUTPUT_DIM, VOCAB_SIZE, 'D.d_perm_classifier_h1', spectral_normed=True, biases=True)
+            if self.perm_type == '2layer':
+                hidden = lib_ops.Linear(flat, OUTPUT_DIM, 128, 'D.d_perm_classifier_h1', spectral_normed=True, biases=True)
+                return lib_ops.Linear(hidden, 128, VOCAB_SIZE, 'D.d_perm_classifier_h2', spectral_normed=True, biases=True)
+            raise ValueError('Unknown perm_type {}'.format(self.perm_type))
 
 
 def _group_of(name):
@@ -216,17 +226,27 @@ class RCGANCifar(object):
     """The graph of gan_resnet.main() (:498-817) for ONE tower and its training iteration (:919-947)."""
 
     def __init__(self, flags=None, tower_batch=32, device='cuda', precision='bf16', seed=0, world_size=1, rank=0, dim=128,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, rng='fed', towers=1):
+        """rng: 'fed' -- the generator noise and the dequantisation noise are program inputs (parity tests, the benchmark's
+        host-fed leg); 'device' -- they are drawn in-graph like the reference's tf.random_normal / tf.random_uniform
+        (gan_resnet.py:363-364, 550) by a Philox kernel keyed by (seed, rank, step): nothing but pixels and labels crosses PCIe."""
         self.FLAGS = flags if flags is not None else default_flags()
-        self.n = tower_batch                       # BATCH_SIZE / len(DEVICES)
+        # tower_batch = BATCH_SIZE / len(DEVICES); towers = towers of THIS process (1: towers are ranks; 2 reproduces the
+        # reference's single-GPU graph, DEVICES = [gpu0, gpu0]: conditional-BN statistics over each half of the batch)
+        self.towers = int(towers)
+        self.n = tower_batch * self.towers
         self.device = torch.device(device)
         self.act_dtype = {'bf16': _C.BF16, 'fp32': _C.F32}[precision]
         self.world_size, self.rank, self.seed, self.dim = world_size, rank, seed, dim
         self.use_cuda_graph = use_cuda_graph
+        self.rng = rng
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._step_ring = torch.zeros(1024, dtype=torch.int64).pin_memory()
+        self._step_count = 0
         if self.FLAGS.algorithm not in ('rcgan', 'rcgan-u', 'biased', 'unbiased'):
             raise ValueError('unknown algorithm ' + str(self.FLAGS.algorithm))
-        if getattr(self.FLAGS, 'perm_type', 'linear') != 'linear':
-            raise NotImplementedError("perm_type '2layer' is not built")
+        if getattr(self.FLAGS, 'perm_type', 'linear') not in ('linear', '2layer'):
+            raise ValueError('Unknown perm_type {}'.format(self.FLAGS.perm_type))
         if not _C.load().rcgan_device_ok():
             raise _C.RcganError('rcgan_b200 needs an sm_100 device: ' + _C.last_error())
         a = self.FLAGS.alpha
@@ -261,20 +281,25 @@ class RCGANCifar(object):
     def build(self):
         F, n, dev = self.FLAGS, self.n, self.device
         alg = F.algorithm
-        net = self.net = Net(alg, self.dim, self.dim)
+        net = self.net = Net(alg, self.dim, self.dim, self.towers, getattr(F, 'perm_type', 'linear'))
         self.store = VariableStore(dev, _group_of)
         S.set_store(self.store, self.seed)
         onehot = lambda prog, lab: GatherRowsOp(self._eye(prog), lab).out
         # ---------------- D step (:526-697)
         self.d_prog = dp_ = Program('d_step', dev, self.act_dtype)
         with dp_:
-            raw = dp_.input('all_real_data_int', [n, OUTPUT_DIM], I32)
+            raw = dp_.input('all_real_data_int', [n, OUTPUT_DIM], U8)           # pixels travel as bytes (the reference: int32)
             labels = dp_.input('all_real_labels', [n, 1], I32)
             labels_random = dp_.input('all_random_labels', [n, 1], I32)
             labels_biased = dp_.input('all_labels_biased', [n, 1], I32)
             inv_w = dp_.input('all_labels_inv_weights', [n, VOCAB_SIZE])
-            noise = dp_.input('noise', [n, Z_DIM])
-            dq = dp_.input('dequant_noise', [n, OUTPUT_DIM])           # tf.random_uniform(0, 1/128), fed (zeros for parity)
+            rseed = (self.seed * 1000003 + self.rank) & 0xffffffffffff
+            if self.rng == 'device':
+                noise = RandomFillOp([n, Z_DIM], True, 0.0, 1.0, rseed, self.rng_step).y
+                dq = RandomFillOp([n, OUTPUT_DIM], False, 0.0, 1.0 / 128, rseed, self.rng_step).y
+            else:
+                noise = dp_.input('noise', [n, Z_DIM])
+                dq = dp_.input('dequant_noise', [n, OUTPUT_DIM])       # tf.random_uniform(0, 1/128), fed (zeros for parity)
             real32 = PreprocessCifarOp(raw, dq, _C.F32).y
             real = CastOp(real32, self.act_dtype).y
             fake = net.Generator(n, labels_random, noise=CastOp(noise, self.act_dtype).y)
@@ -297,7 +322,8 @@ class RCGANCifar(object):
         self.g_prog = gp_ = Program('g_step', dev, self.act_dtype)
         with gp_:
             m = GEN_BS_MULTIPLE * n
-            noise = gp_.input('noise', [m, Z_DIM])
+            noise = (RandomFillOp([m, Z_DIM], True, 0.0, 1.0, rseed, self.rng_step).y if self.rng == 'device'
+                     else gp_.input('noise', [m, Z_DIM]))
             lab_rand = gp_.input('all_random_labels_G', [m, 1], I32)
             lab_bias = gp_.input('all_labels_biased_G', [m, 1], I32)
             fakeG = net.Generator(m, lab_rand, noise=CastOp(noise, self.act_dtype).y, reuse=True)
@@ -397,6 +423,12 @@ class RCGANCifar(object):
             g.m.copy_(snap['__m_' + k]); g.v.copy_(snap['__v_' + k])
 
     def _step(self, prog, keys, tag, lrs, refresh_foreign=True):
+        if self.rng == 'device':
+            # the in-graph random inputs are keyed by the step count, read from device memory by the captured graph
+            self._step_count += 1
+            i = self._step_count % self._step_ring.numel()
+            self._step_ring[i] = self._step_count
+            self.rng_step.copy_(self._step_ring[i:i + 1], non_blocking=True)
         for k in keys:
             if k in self.groups:
                 self.groups[k].t += 1
@@ -438,7 +470,7 @@ class RCGANCifar(object):
 
     def feed(self, prog, **feeds):
         for name, src in feeds.items():
-            if src is None:
+            if src is None or name not in prog.inputs:      # (rng='device': noise / dequant_noise are not inputs)
                 continue
             t = prog.inputs[name]
             src = torch.as_tensor(src)
@@ -446,6 +478,33 @@ class RCGANCifar(object):
             if src.dtype != want:
                 src = src.to(want)
             t.data.copy_(src.reshape(-1), non_blocking=True)
+
+    def sample(self, labels, noise=None):
+        """fixed_noise_samples / samples_100 (gan_resnet.py:820-850): Generator(len(labels), labels, noise) in the training
+        graph's mode (conditional BN over the sample batch -- the reference's generator has no inference mode).
+        Returns float32 [N,32,32,3] NHWC in [-1,1]."""
+        labels = np.asarray(labels).reshape(-1)
+        N = len(labels)
+        if getattr(self, '_s_prog_n', None) != N:
+            S.set_store(self.store, self.seed)
+            self.s_prog = sp = Program('sampler', self.device, self.act_dtype)
+            towers, self.net.towers = self.net.towers, 1
+            try:
+                with sp:
+                    nz = sp.input('noise', [N, Z_DIM])
+                    lab = sp.input('labels', [N, 1], I32)
+                    img = self.net.Generator(N, lab, noise=CastOp(nz, self.act_dtype).y, reuse=True)
+                    self._s_out = CastOp(img, _C.F32).y
+            finally:
+                self.net.towers = towers
+            sp.finalize([])
+            self._s_prog_n = N
+        if noise is None:
+            noise = torch.randn(N, Z_DIM)
+        self.feed(self.s_prog, noise=noise, labels=labels)
+        self.s_prog.run_forward()
+        torch.cuda.current_stream().synchronize()
+        return self._s_out.torch().float().cpu().numpy().reshape(N, IMG_SIZE, IMG_SIZE, IMG_DIM)
 
     def fetch_losses(self):
         for p in (self.d_prog, self.g_prog):

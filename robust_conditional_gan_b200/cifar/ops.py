@@ -75,7 +75,7 @@ def Linear(inputs, input_dim, output_dim, name=None, spectral_normed=False, upda
 
 
 def cond_batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update_moving_stats=True, fused=True, labels=None,
-                   n_labels=None, fuse_act=None):
+                   n_labels=None, fuse_act=None, groups=1):
     """cifar10/common/ops/normalization.py:27-59: moments over [0,1,2], per-label offset/scale tables, eps 1e-5, no
     moving statistics.  labels: int32 graph tensor [n]."""
     if list(axes) != [0, 1, 2]:
@@ -84,7 +84,7 @@ def cond_batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update
     with S.variable_scope('CondBatchNorm'):
         offset_m = S.get_variable('offset', [n_labels, c], _const(0.))
         scale_m = S.get_variable('scale', [n_labels, c], _const(1.))
-    return BatchNormOp(inputs, scale_m, offset_m, labels, None, True, 1e-5, 0.9, fuse_act).y
+    return BatchNormOp(inputs, scale_m, offset_m, labels, None, True, 1e-5, 0.9, fuse_act, groups=groups).y
 
 
 def embed_y(inputs, vocab_size, embedding_dim, word2vec_file=None, name='Embedding.Label'):

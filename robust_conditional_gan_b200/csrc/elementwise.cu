@@ -625,7 +625,8 @@ __global__ void __launch_bounds__(256) copy_batched_kernel(const __grid_constant
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
-__global__ void preprocess_cifar_kernel(const int32_t* __restrict__ chw, const float* __restrict__ noise, void* out_,
+template <typename TI>
+__global__ void preprocess_cifar_kernel(const TI* __restrict__ chw, const float* __restrict__ noise, void* out_,
                                         int n, int is_bf16) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   long total = (long)n * 3072;
@@ -924,7 +925,64 @@ extern "C" int rcgan_copy_batched(int count, const float* const* src, float* con
 
 extern "C" int rcgan_preprocess_cifar(const int32_t* chw, const float* noise, void* out, int n, int dtype, void* stream) {
   RCGAN_CHECK_ARG(n > 0 && (dtype == RCGAN_F32 || dtype == RCGAN_BF16), "preprocess_cifar: bad args");
-  launch_pdl(preprocess_cifar_kernel, grid_for((long)n * 3072, 256), 256, 0, as_stream(stream), chw, noise, out, n, dtype == RCGAN_BF16);
+  launch_pdl(preprocess_cifar_kernel<int32_t>, grid_for((long)n * 3072, 256), 256, 0, as_stream(stream), chw, noise, out, n, dtype == RCGAN_BF16);
   RCGAN_LAUNCH_CHECK("preprocess_cifar");
+  return 0;
+}
+
+extern "C" int rcgan_preprocess_cifar_u8(const uint8_t* chw, const float* noise, void* out, int n, int dtype, void* stream) {
+  RCGAN_CHECK_ARG(chw && out && n > 0 && (dtype == RCGAN_F32 || dtype == RCGAN_BF16), "preprocess_cifar_u8: bad args");
+  launch_pdl(preprocess_cifar_kernel<uint8_t>, grid_for((long)n * 3072, 256), 256, 0, as_stream(stream), chw, noise, out, n, dtype == RCGAN_BF16);
+  RCGAN_LAUNCH_CHECK("preprocess_cifar_u8");
+  return 0;
+}
+
+// ---- in-graph random inputs (tf.random_normal / tf.random_uniform of gan_resnet.py:363-364, 550): Philox4x32-10, one counter
+// block per 4 outputs, keyed by (seed, step) with the step read from device memory so a captured graph draws fresh numbers
+// every replay.  (TensorFlow's own stream is not reproducible outside TensorFlow; parity tests feed these inputs explicitly.)
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__global__ void random_fill_kernel(float* __restrict__ out, long n, int normal, float a, float b, unsigned long long seed,
+                                   const long* __restrict__ step_dev, unsigned stream_id) {
+  pdl_sync();
+  const unsigned long long step = step_dev ? (unsigned long long)*step_dev : 0ull;
+  const long nq = (n + 3) / 4;
+  GRID_STRIDE(q, nq) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)((unsigned long long)q >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ stream_id};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float v[4];
+    if (normal) {
+      // Box-Muller on (0,1] x [0,1): a + b * N(0,1)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const float u1 = ((c[2 * h] >> 8) + 1) * (1.0f / 16777216.0f), u2 = (c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        v[2 * h] = fmaf(b, r * cs, a); v[2 * h + 1] = fmaf(b, r * sn, a);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = fmaf((c[j] >> 8) * (1.0f / 16777216.0f), b - a, a);     // U[a, b)
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (4 * q + j < n) out[4 * q + j] = v[j];
+  }
+}
+
+extern "C" int rcgan_random_fill(float* out, long n, int normal, float a, float b, unsigned long long seed, const long* step_dev,
+                                 unsigned stream_id, void* stream) {
+  RCGAN_CHECK_ARG(out && n > 0, "random_fill: bad args");
+  launch_pdl(random_fill_kernel, grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream), out, n, normal, a, b, seed, step_dev, stream_id);
+  RCGAN_LAUNCH_CHECK("random_fill");
   return 0;
 }

@@ -19,7 +19,8 @@ from . import _C
 from ._C import ConvDesc, call, ptr, stream_ptr
 
 I32 = 100   # host-side dtype tag for integer label tensors (never passed to the library as an activation dtype)
-TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16, I32: torch.int32}
+U8 = 101    # raw image bytes (CIFAR pixels)
+TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16, I32: torch.int32, U8: torch.uint8}
 
 
 def same_pad(size, k, stride):

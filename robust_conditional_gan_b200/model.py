@@ -14,6 +14,7 @@ h6 = h4 + <h3, h5(y)>, so ONE trunk evaluation plus the fused channel loss gives
 (checked against the literal 10-call oracle in tests/).
 """
 import math
+import os
 import time
 from types import SimpleNamespace
 
@@ -561,7 +562,20 @@ class DCGAN(object):
 
     def recover_labels(self, sample_actual, y_actual=None, recover_epoch=1000, learning_rate=500.0, log_every=100):
         """The reference's loop (:622-640) on a given batch of real images; returns (y_recover [R,k], mse_loss,
-        zero_one_loss = tf.losses.cosine_distance(y_actual, one_hot(argmax y_recover)) = 1 - accuracy)."""
+        zero_one_loss = tf.losses.cosine_distance(y_actual, one_hot(argmax y_recover)) = 1 - accuracy).
+        Called as the reference does, `recover_labels(config)` (mnist/main.py:142, model.py:494-640), it restores the latest
+        checkpoint (:497-502), draws recover_batch_size random rows of self.data_X from the numpy stream (:613-617) and runs
+        recover_epoch steps at recover_learning_rate."""
+        if hasattr(sample_actual, 'recover_batch_size'):
+            config = sample_actual
+            could_load, _ = self.load(self.checkpoint_dir)
+            if not could_load:
+                raise Exception(" [!] Load failed...")
+            idx = np.random.randint(len(self.data_X), size=[config.recover_batch_size])
+            y_rec, mse, zo = self.recover_labels(self.data_X[idx], self.data_y_actual[idx], config.recover_epoch,
+                                                 config.recover_learning_rate, log_every)
+            print("Recover: mse_loss: %.5g, zeroone_loss: %.5g" % (mse, zo))
+            return y_rec, mse, zo
         if not hasattr(self, 'r_prog') or self.recover_R != len(sample_actual):
             self.build_recover(len(sample_actual))
         mse = None
@@ -576,6 +590,30 @@ class DCGAN(object):
             onehot = torch.eye(self.y_dim)[y_rec.argmax(-1)]
             zero_one = float((1.0 - (ya * onehot).sum(-1)).mean())
         return y_rec, mse, zero_one
+
+    # ------------------------------------------------------------------ checkpoints (mnist/model.py:836-867)
+    @property
+    def model_dir(self):
+        return "{}_{}_{}_{}".format(self.dataset_name, self.batch_size, self.output_height, self.output_width)
+
+    def save(self, checkpoint_dir, step):
+        """:842-851: every global variable under its TF name + the Adam slots, `DCGAN.model-<step>` (checkpoint.py)"""
+        from . import checkpoint
+        return checkpoint.save(self, os.path.join(checkpoint_dir, self.model_dir), "DCGAN.model", step)
+
+    def load(self, checkpoint_dir):
+        """:853-867 -> (could_load, counter)"""
+        from . import checkpoint
+        print(" [*] Reading checkpoints...")
+        if checkpoint_dir is None:
+            return False, 0
+        path = checkpoint.latest_checkpoint(os.path.join(checkpoint_dir, self.model_dir))
+        if path and os.path.exists(path + '.npz'):
+            checkpoint.restore(self, path)      # (captured graphs read parameters / Adam state from fixed addresses: no re-capture)
+            print(" [*] Success to read {}".format(os.path.basename(path)))
+            return True, checkpoint.step_of(path)
+        print(" [*] Failed to find a checkpoint")
+        return False, 0
 
     def noise_schedule(self, epoch):
         """mnist/model.py:293-321 (--add_noise, run_rcgany.sh): the one-coin confusion matrix the labels are re-noised with at
@@ -624,6 +662,13 @@ class DCGAN(object):
         yr, yf = pin(self.data_y_real), pin(self.data_y_fake)
         self.sample_z = self.sampler_state.uniform(-1, 1, self.sample_num * self.z_dim).reshape(self.sample_num, self.z_dim)
         it = 0
+        counter = 1
+        could_load, checkpoint_counter = self.load(self.checkpoint_dir)          # :284-290
+        if could_load:
+            counter = checkpoint_counter
+            print(" [*] Load SUCCESS")
+        else:
+            print(" [!] Load failed...")
         for epoch in range(config.epoch):
             if self.add_noise:
                 self.renoise_labels(epoch)
@@ -638,5 +683,10 @@ class DCGAN(object):
                     print("Epoch: [%2d] [%4d/%4d] time: %4.4f, d_loss: %.8f, g_loss: %.8f" % (
                         epoch, idx, batch_idxs, time.time() - start_time, losses['d_loss'], losses['g_loss']))
                 it += 1
+                counter += 1
+                if self.checkpoint_dir is not None and np.mod(counter, 500) == 2:     # :489-490
+                    self.save(self.checkpoint_dir, counter)
                 if max_iters is not None and it >= max_iters:
+                    if self.checkpoint_dir is not None:
+                        self.save(self.checkpoint_dir, counter)
                     return

@@ -441,7 +441,7 @@ class BatchNormOp(Op):
         prog = cur()
         n, h, w = spatial(x)
         self.x, self.scale, self.offset, self.labels = x, scale, offset, labels
-        assert n % groups == 0 and (groups == 1 or labels is None)
+        assert n % groups == 0
         self.groups, self.samples, self.hw, self.c = groups, n // groups, h * w, x.c
         assert x.ld == x.c
         self.n_labels = scale.numel() // x.c
@@ -475,6 +475,10 @@ class BatchNormOp(Op):
             # parameter gradients only: with a concat output dx cannot alias y.grad (different row stride)
             self.dx_dummy = torch.zeros(self.x.data.numel(), dtype=self.y.data.dtype, device=prog.device)
 
+    def _lab(self, g):
+        """labels of sample range g (int32 [n])"""
+        return None if self.labels is None else dp(self.labels) + 4 * g * self.samples
+
     def _off(self, ptr, g, esz):
         """pointer to sample range g of a [groups*samples*hw, c] buffer"""
         return None if ptr is None else ptr + g * self.samples * self.hw * self.c * esz
@@ -491,7 +495,7 @@ class BatchNormOp(Op):
         xs, ys = self.x.data.element_size(), self.y.data.element_size()
         for g in range(self.groups):
             call('rcgan_bn_fwd', self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), self.samples, self.hw, self.c,
-                 self.x.dtype, self.y.dtype, dp(self.scale), dp(self.offset), dp(self.labels), self.eps, self.act, self.leak,
+                 self.x.dtype, self.y.dtype, dp(self.scale), dp(self.offset), self._lab(g), self.eps, self.act, self.leak,
                  1 if self.train else 0, self.decay, mm, mv, self.save[g].data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
 
     def backward(self, prog):
@@ -506,7 +510,7 @@ class BatchNormOp(Op):
                 for g in range(self.groups):
                     call('rcgan_bn_infer_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.y), g, ys), self.y.ld,
                          self._off(gp(self.x), g, self.x.grad.element_size()), self.samples, self.hw, self.c, self.y.dtype,
-                         dp(self.scale), dp(self.labels), self.save[g].data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
+                         dp(self.scale), self._lab(g), self.save[g].data_ptr(), self.act, self.leak, self.acc_x, prog.ws.ptr(),
                          prog.ws.bytes, stream_ptr())
             return
         if self.dummy is not None:
@@ -528,7 +532,7 @@ class BatchNormOp(Op):
             else:
                 dxp, accx = self._off(gp(self.x), g, self.x.grad.element_size()), self.acc_x
             call('rcgan_bn_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), dxp,
-                 self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels,
+                 self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale), self._lab(g), self.n_labels,
                  self.save[g].data_ptr(), self.act, self.leak, dsc, dof, accx, accp if g == 0 else 1, prog.ws.ptr(),
                  prog.ws.bytes, dp(self.offset), stream_ptr())
 
@@ -1139,8 +1143,31 @@ class PreprocessCifarOp(Op):
         self.y.base.needs_grad = False
 
     def forward(self, prog):
-        call('rcgan_preprocess_cifar', self.raw.data.data_ptr(), None if self.noise is None else self.noise.data.data_ptr(),
-             dp(self.y), self.n, self.y.dtype, stream_ptr())
+        fn = 'rcgan_preprocess_cifar_u8' if self.raw.data.dtype == torch.uint8 else 'rcgan_preprocess_cifar'
+        call(fn, self.raw.data.data_ptr(), None if self.noise is None else self.noise.data.data_ptr(), dp(self.y), self.n,
+             self.y.dtype, stream_ptr())
+
+
+class RandomFillOp(Op):
+    """An in-graph random input: tf.random_normal([n, 128]) (gan_resnet.py:363-364) / tf.random_uniform([n, 3072], 0, 1/128)
+    (:550).  `step` is a device int64 the host bumps before every step, so captured graphs draw fresh numbers on replay."""
+    _streams = 0
+
+    def __init__(self, shape, normal, a, b, seed, step_dev):
+        prog = cur()
+        self.y = prog.new(shape, _C.F32)
+        self.normal, self.a, self.b, self.seed, self.step_dev = int(normal), float(a), float(b), int(seed), step_dev
+        RandomFillOp._streams += 1
+        self.stream_id = RandomFillOp._streams
+        self.inputs, self.outputs = (), (self.y,)
+        prog.add(self)
+
+    def plan(self, prog):
+        self.y.base.needs_grad = False
+
+    def forward(self, prog):
+        call('rcgan_random_fill', dp(self.y), self.y.numel(), self.normal, self.a, self.b, self.seed, self.step_dev.data_ptr(),
+             self.stream_id, stream_ptr())
 
 
 def adam_step(group, lr_t_dev, b1, b2, eps, grad_scale=1.0):

@@ -175,3 +175,76 @@ def test_iteration_schedule_and_graph(lib):
     assert abs(out1['disc_real_l'] + out1['disc_fake_l'] - float(tr.last['d']['disc_wgan'])) < 2e-2
     assert abs(out1['gen_wgan'] - float(tr.last['g']['gen_wgan'])) < 2e-2
     assert all(np.isfinite(v) for v in out1.values())
+
+
+def test_two_layer_perm_classifier(lib):
+    """--perm_type 2layer (gan_resnet.py:467-480): SN-Linear 3072 -> 128 -> 10; D step (real images) and G step (generated)."""
+    flags = default_flags(algorithm='rcgan-u', alpha=0.5, perm_classifier=True, perm_multiplier=2.0, confuse_init=True, perm_type='2layer')
+    ocfg = OC.default_config(algorithm='rcgan-u', alpha=0.5, perm_classifier=True, perm_multiplier=2.0, confuse_init=True, dim=32,
+                             perm_type='2layer')
+    model = RCGANCifar(flags, tower_batch=6, precision='fp32', dim=32, use_cuda_graph=False)
+    P = OC.init_params(ocfg, seed=1, dtype=torch.float64)
+    assert set(P) == set(model.store.vars), set(P) ^ set(model.store.vars)
+    model.store.load_state_dict(P)
+    tr = OC.Trainer(P, ocfg)
+    b = OC.synthetic_batch(6, seed=3, dtype=torch.float64)
+    feed_d(model, b); feed_g(model, b)
+    tr.d_step(b, 0); model.d_step(0)
+    torch.cuda.synchronize()
+    got = model.d_prog.loss_dict(model.d_prog.losses.cpu())
+    assert abs(got['perm_classifier_real_loss'] - float(tr.last['d']['perm_real'])) < 1e-4
+    pc = [v for v in model.disc_params if 'perm_classifier' in v.name]
+    assert len(pc) == 4
+    check_grads(pc, tr.last['d_grads'], 2e-4, '2layer perm classifier')
+    model.store.load_state_dict({k: v.detach() for k, v in tr.P.items()})
+    tr.g_step(b, 1); model.g_step(1)
+    torch.cuda.synchronize()
+    got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
+    assert abs(got['perm_classifier_fake_loss'] - float(tr.last['g']['perm_fake'])) < 1e-4
+    check_grads(model.gen_params + model.c_params, tr.last['g_grads'], 5e-4, '2layer G')
+
+
+@pytest.mark.parametrize('precision,dim,tol', [('fp32', 32, 3e-4), ('bf16', 128, 2e-1)])
+def test_two_towers_in_one_process(lib, precision, dim, tol):
+    """The reference's single-GPU graph (DEVICES = [gpu0, gpu0], gan_resnet.py:183-192): two towers of BATCH_SIZE/2 whose costs are
+    averaged -- conditional-BN statistics per tower.  One process with towers=2 must equal the oracle's two-tower cost and differ
+    from one big tower."""
+    n = 4
+    flags = default_flags(algorithm='rcgan', alpha=0.5)
+    ocfg = OC.default_config(algorithm='rcgan', alpha=0.5, dim=dim)
+    model = RCGANCifar(flags, tower_batch=n, precision=precision, dim=dim, use_cuda_graph=False, towers=2)
+    P = OC.init_params(ocfg, seed=1, dtype=torch.float64)
+    g = torch.Generator().manual_seed(7)
+    for k in P:
+        if k.endswith('/scale') or k.endswith('/offset'):
+            P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=g, dtype=torch.float64)
+    model.store.load_state_dict(P)
+    full = OC.synthetic_batch(2 * n, seed=3, dtype=torch.float64)
+    feed_g(model, full)
+    model.g_step(1)
+    torch.cuda.synchronize()
+    tower = lambda r: {k: (v[r * (v.shape[0] // 2):(r + 1) * (v.shape[0] // 2)] if torch.is_tensor(v) else v) for k, v in full.items()}
+    tr = OC.Trainer(P, ocfg)
+    tr._req(tr.gn)
+    cost = sum(OC.gen_cost(tr.P, tower(r), ocfg)[0]['gen_cost'] for r in range(2)) / 2
+    ref = dict(zip(tr.gn, torch.autograd.grad(cost, [tr.P[k] for k in tr.gn], allow_unused=True)))
+    got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
+    assert abs(got['gen_wgan'] - float(cost)) < (1e-4 if precision == 'fp32' else 2e-2)
+    ref = {k: (v if v is not None else torch.zeros_like(tr.P[k])) for k, v in ref.items()}
+    check_grads(model.gen_params, ref, tol, 'two towers ' + precision)
+    if precision == 'fp32':
+        tr._req(tr.gn)
+        big = OC.gen_cost(tr.P, full, ocfg)[0]['gen_cost']
+        gb = dict(zip(tr.gn, torch.autograd.grad(big, [tr.P[k] for k in tr.gn], allow_unused=True)))
+        k = 'Generator/G.Block.1.Conv1/Filters'
+        assert relerr(gb[k], ref[k]) > 1e-3            # per-tower statistics matter
+
+
+def test_generator_sampler(lib):
+    """RCGANCifar.sample == the oracle's Generator on the same noise / labels (gan_resnet.py:820-829 fixed_noise_samples)"""
+    model, tr, b = build('rcgan', 4, 'fp32', 32, perm=False)
+    labels = np.repeat(np.arange(10), 2)
+    noise = torch.randn(20, 128, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    got = model.sample(labels, noise=noise)
+    ref = OC.Generator(OC.Ctx(tr.P, False), noise, torch.as_tensor(labels), 32)
+    assert got.shape == (20, 32, 32, 3) and relerr(torch.as_tensor(got), ref) < 1e-4
