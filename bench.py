@@ -488,11 +488,13 @@ def run_ours(args, wl):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     B = wl['batch']
     bench = make_bench(wl, args.precision, world, rank)
+    dp_model = bench.m
     r = time_workload(bench, args.steps, args.warmup, world, local, True)
     h2d, d2h = bench.h2d, bench.d2h
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            from robust_conditional_gan_b200.parallel import shutdown
+            shutdown([bench.m])
         return
     pk = peaks()
     result = {
@@ -547,9 +549,10 @@ def run_ours(args, wl):
         cores = os.cpu_count()
         v, t_it, sample, n = cpu_sample(wl, cores, 3, 1, budget_s=45.0)
         result['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample}
-    print(json.dumps(result))
+    print(json.dumps(result), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        from robust_conditional_gan_b200.parallel import shutdown
+        shutdown([] if world == 1 else [dp_model])
 
 
 def main():

@@ -116,14 +116,24 @@ def _w(ctx, name, key, sn, uname):
     return w
 
 
-def Conv2D(ctx, x, name, sn):
-    """conv2d.py:169-216: SN under scope `filters`, stride-1 SAME conv, + Biases."""
-    return O.conv2d(x, _w(ctx, name, '/Filters', sn, '/filters/spectral_norm/u'), 1) + ctx.P[name + '/Biases']
+def Conv2D(ctx, x, name, sn, fold=None):
+    """conv2d.py:169-216: SN under scope `filters`, stride-1 SAME conv, + Biases.
+    Under O.bf16_storage() the weight is rounded as the product's tensor-core pack is; fold ('pool' | 'up', emulation only): the
+    caller's 2x resampling folded into a 4x4 stride-2 filter exactly as the product does (O.fold4) -- the fold is computed from
+    the fp32 weight and the FOLDED filter is what gets rounded."""
+    w = _w(ctx, name, '/Filters', sn, '/filters/spectral_norm/u')
+    b = ctx.P[name + '/Biases']
+    if fold == 'pool':
+        return O.conv2d(x, O.qw(O.fold4(w, 0)), 2) + b
+    if fold == 'up':
+        return O.conv2d_transpose(x, O.qw(O.fold4(w, 1)), (2 * x.shape[1], 2 * x.shape[2]), 2) + b
+    return O.conv2d(x, O.qw(w), 1) + b
 
 
-def Linear(ctx, x, name, sn):
-    """linear.py:161-180."""
-    return x @ _w(ctx, name, '/W', sn, '/spectral_norm/u') + ctx.P[name + '/b']
+def Linear(ctx, x, name, sn, tc=False):
+    """linear.py:161-180.  tc: a linear the product runs on the tensor cores (bf16 weight pack) in bf16 mode."""
+    w = _w(ctx, name, '/W', sn, '/spectral_norm/u')
+    return x @ (O.qw(w) if tc else w) + ctx.P[name + '/b']
 
 
 def mean_pool(x):
@@ -145,6 +155,8 @@ def Normalize(ctx, name, x, labels):
 
 def ResidualBlock(ctx, x, name, sn, resample, labels, cin, cout):
     """gan_resnet.py:275-328."""
+    if O.emulating():
+        return _ResidualBlock_bf16(ctx, x, name, sn, resample, labels, cin, cout)
     if resample == 'down':
         conv1 = lambda t: Conv2D(ctx, t, name + '.Conv1', sn)
         conv2 = lambda t: mean_pool(Conv2D(ctx, t, name + '.Conv2', sn))
@@ -165,28 +177,57 @@ def ResidualBlock(ctx, x, name, sn, resample, labels, cin, cout):
     return shortcut + out
 
 
+def _ResidualBlock_bf16(ctx, x, name, sn, resample, labels, cin, cout):
+    """The same block with the product's dataflow and bf16 storage points (robust_conditional_gan_b200/cifar/gan_resnet.py
+    ResidualBlock): 1x1 shortcuts on the small grid, ConvMeanPool / UpsampleConv as folded 4x4 stride-2 filters, the shortcut added
+    in Conv2's epilogue (the conv result is rounded when it is staged, the sum once more).  Mathematically identical to the block
+    above; only the rounding points differ from a plain cast-everything-to-bf16."""
+    q = O.q
+    if resample == 'up':
+        short = q(Conv2D(ctx, x, name + '.Shortcut', sn))                      # on the small grid; upsampled inside the add
+    elif resample == 'down':
+        short = q(Conv2D(ctx, q(mean_pool(x)), name + '.Shortcut', sn))
+    else:
+        short = x if cin == cout else q(Conv2D(ctx, x, name + '.Shortcut', sn))
+    out = q(torch.relu(Normalize(ctx, name + '.N1', x, labels)))
+    out = Conv2D(ctx, out, name + '.Conv1', sn, fold='up' if resample == 'up' else None)
+    out = q(torch.relu(Normalize(ctx, name + '.N2', q(out), labels))) if 'G.' in name else q(torch.relu(out))
+    out = q(Conv2D(ctx, out, name + '.Conv2', sn, fold='pool' if resample == 'down' else None))
+    return q((upsample(short) if resample == 'up' else short) + out)
+
+
 def Generator(ctx, noise, labels, dim=128):
     """gan_resnet.py:356-371.  Returns NHWC [n,32,32,3]."""
     n = 'Generator/'
-    out = Linear(ctx, noise, n + 'G.Input', False).reshape(-1, 4, 4, dim * 8)
+    q = O.q
+    out = q(Linear(ctx, q(noise), n + 'G.Input', False, tc=True)).reshape(-1, 4, 4, dim * 8)
     out = ResidualBlock(ctx, out, n + 'G.Block.1', False, 'up', labels, dim * 8, dim * 2)
     out = ResidualBlock(ctx, out, n + 'G.Block.2', False, 'up', labels, dim * 2, dim * 2)
     out = ResidualBlock(ctx, out, n + 'G.Block.3', False, 'up', labels, dim * 2, dim * 2)
-    out = torch.relu(Normalize(ctx, n + 'G.OutputNorm', out, labels))
-    return torch.tanh(Conv2D(ctx, out, n + 'G.Output', False))
+    out = q(torch.relu(Normalize(ctx, n + 'G.OutputNorm', out, labels)))
+    return q(torch.tanh(Conv2D(ctx, out, n + 'G.Output', False)))
 
 
 def Discriminator(ctx, x, dim=128):
     """gan_resnet.py:331-353, 374-412.  x NHWC [N,32,32,3] -> (output [N,dim], output_wgan [N])."""
     n = 'Discriminator/'
-    short = Conv2D(ctx, mean_pool(x), n + 'D.Block.1.Shortcut', True)
-    out = Conv2D(ctx, x, n + 'D.Block.1.Conv1', True)
-    out = mean_pool(Conv2D(ctx, torch.relu(out), n + 'D.Block.1.Conv2', True))
-    out = short + out
+    q = O.q
+    if O.emulating():
+        # the product's dataflow / storage points (see _ResidualBlock_bf16): image cast to bf16, pooled shortcut input stored, Conv2 +
+        # mean-pool as one folded stride-2 conv with the shortcut added in its epilogue; the [N, dim] head runs in fp32
+        x = q(x)
+        short = q(Conv2D(ctx, q(mean_pool(x)), n + 'D.Block.1.Shortcut', True))
+        out = q(torch.relu(Conv2D(ctx, x, n + 'D.Block.1.Conv1', True)))
+        out = q(short + q(Conv2D(ctx, out, n + 'D.Block.1.Conv2', True, fold='pool')))
+    else:
+        short = Conv2D(ctx, mean_pool(x), n + 'D.Block.1.Shortcut', True)
+        out = Conv2D(ctx, x, n + 'D.Block.1.Conv1', True)
+        out = mean_pool(Conv2D(ctx, torch.relu(out), n + 'D.Block.1.Conv2', True))
+        out = short + out
     out = ResidualBlock(ctx, out, n + 'D.Block.2', True, 'down', None, dim, dim)
     for i in range(3, 7):
         out = ResidualBlock(ctx, out, n + 'D.Block.%d' % i, True, None, None, dim, dim)
-    out = torch.relu(out).mean(dim=(1, 2))
+    out = q(torch.relu(out).mean(dim=(1, 2)))
     return out, Linear(ctx, out, n + 'D.Output', True).reshape(-1)
 
 

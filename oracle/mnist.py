@@ -141,11 +141,13 @@ def _conv(P, name, x, cfg_sn, upd):
         w, u_new, _ = O.spectral_normed_weight(w, P[name + '/spectral_norm/u'])
         if upd is not None:
             upd.set(name + '/spectral_norm/u', u_new)
-    return O.conv2d(x, w, 2) + P[name + '/biases']
+    return O.conv2d(x, O.qw(w), 2) + P[name + '/biases']       # (O.qw: identity unless O.bf16_storage() is active)
 
 
-def _lin(P, name, x):
-    return x @ P[name + '/Matrix'] + P[name + '/bias']
+def _lin(P, name, x, tc=False):
+    """tc: a linear the product runs on the tensor cores in bf16 mode (bf16 weight pack); the [B, 64] head and the classifier
+    run in fp32 there"""
+    return x @ (O.qw(P[name + '/Matrix']) if tc else P[name + '/Matrix']) + P[name + '/bias']
 
 
 def generator(P, z, y, cfg, train=True, upd=None):
@@ -154,17 +156,18 @@ def generator(P, z, y, cfg, train=True, upd=None):
     s_h, s_w = cfg.output_height, cfg.output_width
     s_h2, s_h4, s_w2, s_w4 = s_h // 2, s_h // 4, s_w // 2, s_w // 4
     n = 'generator/'
-    zc = torch.cat([z, y], 1)
-    h0 = torch.relu(_bn(P, n + 'g_bn0', _lin(P, n + 'g_h0_lin', zc), train, upd))
+    q, qw = O.q, O.qw              # bf16 storage points of the product (identity unless O.bf16_storage() is active)
+    zc = torch.cat([q(z), y], 1)
+    h0 = q(torch.relu(_bn(P, n + 'g_bn0', q(_lin(P, n + 'g_h0_lin', zc, tc=True)), train, upd)))
     h0 = torch.cat([h0, y], 1)
-    h1 = torch.relu(_bn(P, n + 'g_bn1', _lin(P, n + 'g_h1_lin', h0), train, upd))
+    h1 = q(torch.relu(_bn(P, n + 'g_bn1', q(_lin(P, n + 'g_h1_lin', h0, tc=True)), train, upd)))
     h1 = h1.reshape(B, s_h4, s_w4, cfg.gf_dim * 2)
     h1 = O.conv_cond_concat(h1, y)
-    h2 = O.conv2d_transpose(h1, P[n + 'g_h2/w'], (s_h2, s_w2)) + P[n + 'g_h2/biases']
-    h2 = torch.relu(_bn(P, n + 'g_bn2', h2, train, upd))
+    h2 = q(O.conv2d_transpose(h1, qw(P[n + 'g_h2/w']), (s_h2, s_w2)) + P[n + 'g_h2/biases'])
+    h2 = q(torch.relu(_bn(P, n + 'g_bn2', h2, train, upd)))
     h2 = O.conv_cond_concat(h2, y)
-    h3 = O.conv2d_transpose(h2, P[n + 'g_h3/w'], (s_h, s_w)) + P[n + 'g_h3/biases']
-    return torch.sigmoid(h3)
+    h3 = O.conv2d_transpose(h2, qw(P[n + 'g_h3/w']), (s_h, s_w)) + P[n + 'g_h3/biases']
+    return q(torch.sigmoid(h3))
 
 
 def discriminator(P, image, y, cfg, upd=None):
@@ -175,11 +178,12 @@ def discriminator(P, image, y, cfg, upd=None):
     if cfg.disc_type == 'projection':
         cc = lambda l, t: O.conv_cond_concat(t, y) if (cfg.concat_y and l in cfg.concat_y_layers) else t
         sn = cfg.spectral_norm
-        h0 = O.lrelu(_conv(P, n + 'd_h0_conv', cc(1, image), sn, upd))
-        h1 = O.lrelu(_bn(P, n + 'd_bn1', _conv(P, n + 'd_h1_conv', cc(2, h0), sn, upd), True, upd, track=False))
-        h2 = O.lrelu(_bn(P, n + 'd_bn2', _conv(P, n + 'd_h2_conv', cc(3, h1), sn, upd), True, upd, track=False))
-        h3 = O.lrelu(_bn(P, n + 'd_bn3', _conv(P, n + 'd_h3_conv', cc(4, h2), sn, upd), True, upd, track=False))
-        h3 = h3.mean(dim=(1, 2))
+        q = O.q                    # bf16 storage points of the product's trunk (identity unless O.bf16_storage() is active)
+        h0 = q(O.lrelu(_conv(P, n + 'd_h0_conv', cc(1, q(image)), sn, upd)))
+        h1 = q(O.lrelu(_bn(P, n + 'd_bn1', q(_conv(P, n + 'd_h1_conv', cc(2, h0), sn, upd)), True, upd, track=False)))
+        h2 = q(O.lrelu(_bn(P, n + 'd_bn2', q(_conv(P, n + 'd_h2_conv', cc(3, h1), sn, upd)), True, upd, track=False)))
+        h3 = q(O.lrelu(_bn(P, n + 'd_bn3', q(_conv(P, n + 'd_h3_conv', cc(4, h2), sn, upd)), True, upd, track=False)))
+        h3 = q(h3.mean(dim=(1, 2)))
         h4 = _lin(P, n + 'd_h4_lin', h3.reshape(B, -1))
         h5 = _lin(P, n + 'd_h5_y_lin', y.reshape(B, 10))
         return h4 + (h3 * h5).sum(1, keepdim=True)

@@ -103,3 +103,31 @@ class GradReducer:
         for w in self.pending:
             w.wait()                    # stream dependency only: the current stream waits for the collective's completion event
         self.pending = []
+
+
+def shutdown(models=(), grace_s=20.0):
+    """End of a multi-rank run: the step graphs hold captured NCCL collectives, and tearing the communicator down while they are
+    alive can block forever (seen on 2 x B200: the job printed its result and then sat in destroy_process_group until killed).
+    Order: flush output, barrier, release the captured graphs, then destroy the process group with a watchdog that ends the
+    process if the teardown does not return within grace_s."""
+    import gc
+    import sys
+    import threading
+    import torch.distributed as dist
+    sys.stdout.flush(); sys.stderr.flush()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    for m in models:
+        getattr(m, '_graphs', {}).clear()
+        for r in getattr(m, 'reducers', {}).values():
+            r.pending = []
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Timer(grace_s, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()

@@ -75,8 +75,10 @@ def main():
     if rank == 0:
         print('DP_CHECK world=%d worst_D_grad_relerr=%.2e worst_G_grad_relerr=%.2e params_diverged_D=%d params_diverged_G=%d buckets=%s' % (
             world, float(res[0]), float(res[3]), int(res[1]), int(res[2]), nb))
+        sys.stdout.flush()
         assert float(res[0]) < 3e-2 and float(res[3]) < 3e-2 and int(res[1]) == 0 and int(res[2]) == 0
-    dist.destroy_process_group()
+    from robust_conditional_gan_b200.parallel import shutdown
+    shutdown([model])
 
 
 if __name__ == '__main__':

@@ -298,3 +298,44 @@ def test_train_loop_follows_the_reference_random_stream(lib):
     assert abs(model.noise_schedule(1)[0] - a0) < 1e-12
     mid = 1 + 0.5 * (end - 1)
     assert model.noise_schedule(int(end) + 1)[0] == 1.0 and a0 < model.noise_schedule(mid)[0] < 1.0
+
+
+@pytest.mark.parametrize('run', ['rcgan', 'rcganu'])
+def test_bf16_step_matches_the_bf16_storage_oracle(lib, run):
+    """north_star's bf16 bar (per-layer gradients <= 1e-2 relative, losses <= 1e-3) against the oracle that rounds to bf16 exactly
+    where the product stores bf16 (oracle.nn.bf16_storage: activations, activation gradients, tensor-core weight packs; fp64
+    arithmetic in between).  This isolates implementation error from the quantisation gap that the comparison with the un-rounded
+    oracle (test_bf16_step_matches_oracle: 25 % / 35 % behind the batch-norm backwards) also contains."""
+    from oracle import nn as O
+    B = 32
+    model, tr, batch = build(run, B, 'bf16', use_graph=False)
+    feed(model, batch)
+    with O.bf16_storage():
+        tr.d_step(batch)
+    model.d_step()
+    torch.cuda.synchronize()
+    got = model.d_prog.loss_dict(model.d_prog.losses.cpu())
+    for k in ('d_loss_real', 'd_loss_fake', 'class_loss_real'):
+        assert abs(got[k] - float(tr.last['d'][k])) < 1e-3, (k, got[k], tr.last['d'][k])
+    errs = []
+    for v in model.d_vars:
+        ref = tr.last['d_grads'][v.name]
+        if float(ref.norm()) < 1e-9:
+            continue
+        errs.append((relerr(v.grad.reshape(ref.shape), ref), v.name))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 1e-2, errs[:8]
+    with O.bf16_storage():
+        tr.g_step(batch)
+    model.g_step()
+    torch.cuda.synchronize()
+    got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
+    assert abs(got['g_loss'] - float(tr.last['g']['g_loss'])) < 1e-3
+    errs = []
+    for v in model.g_vars + model.c_vars:
+        ref = tr.last['g_grads'][v.name]
+        if float(ref.norm()) < 1e-9:
+            continue
+        errs.append((relerr(v.grad.reshape(ref.shape), ref), v.name))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 1e-2, errs[:8]
