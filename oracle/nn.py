@@ -239,7 +239,12 @@ def emulating():
 
 def q(x):
     """an activation tensor the product keeps in HBM as bf16: the value AND its gradient are rounded"""
-    return _RoundBoth.apply(x) if _EMUL['on'] else x
+    if not _EMUL['on']:
+        return x
+    y = _RoundBoth.apply(x)
+    if _EMUL.get('trace') is not None:
+        _EMUL['trace'].append(y.detach())          # diagnostic: the sequence of stored tensors (tools/bf16_gap.py)
+    return y
 
 
 def qw(w):

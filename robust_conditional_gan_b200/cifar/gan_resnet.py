@@ -305,7 +305,9 @@ class RCGANCifar(object):
             fake = net.Generator(n, labels_random, noise=CastOp(noise, self.act_dtype).y)
             # one D pass over [real; fake] as the reference does (:558-583; D has no batch statistics, so the halves are
             # independent): every kernel of the trunk sees 2n samples instead of two launches of n
+            self.fake_D = fake
             h_all, psi_all = net.Discriminator(ConcatRowsOp(real, fake).y, None, update_collection=None)
+            self.h_all = h_all
             V = net.Discriminator_projection(None, update_collection=None)
             w_real = inv_w if alg == 'unbiased' else onehot(dp_, labels)
             if alg == 'rcgan-u':

@@ -95,7 +95,7 @@ def train(FLAGS, cfg, max_iters=None):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     os.makedirs(cfg['DIR'], exist_ok=True)
     logging.basicConfig(filename=FLAGS.log_file, level=logging.DEBUG if FLAGS.log_level == 'debug' else logging.INFO,
-                        format='%(asctime)s %(levelname)-8s %(message)s')
+                        format='%(asctime)s %(levelname)-8s %(message)s', force=True)
     logging.info('alpha = {}'.format(FLAGS.alpha))
     B = cfg['BATCH_SIZE']
     assert B % (world * FLAGS.towers) == 0, 'BATCH_SIZE must divide into ranks x towers'

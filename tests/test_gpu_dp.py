@@ -20,6 +20,6 @@ def test_two_rank_step_matches_two_tower_oracle(lib, split):
     port = 29600 + os.getpid() % 300 + int(split)
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', str(port), os.path.join(ROOT, 'tests', 'dp_check.py')], capture_output=True, text=True,
-                       env=env, timeout=600)
+                       env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'DP_CHECK world=2' in r.stdout, r.stdout[-2000:]

@@ -22,7 +22,7 @@ def test_mnist_main_trains_saves_restores_and_recovers(lib, tmp_path):
     ck = os.path.join(str(tmp_path), 'run', m1.model_dir)
     assert m1.model_dir == 'mnist_64_28_28' and checkpoint.latest_checkpoint(ck) is not None
     # second process-equivalent: same flags without --train -> load() finds the checkpoint (mnist/main.py:137-140), no training
-    argv2 = [a for a in argv if a != '--train']
+    argv2 = [a if a != '--train' else '--notrain' for a in argv]      # (the module-level FLAGS object persists inside one process)
     m2 = flags_lib.run(M.main, M.flags, argv2)
     for n, v in m1.store.vars.items():
         assert torch.equal(v.data, m2.store.vars[n].data), n
