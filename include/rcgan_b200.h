@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 9
+#define RCGAN_ABI_VERSION 10
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -115,7 +115,14 @@ typedef struct {
   const void* mask; int mask_act; float mask_leak;
   const void* res; int res_up; int ld_res;
   void* out2; int out2_act;
+  float* colstats;
 } rcgan_conv_epilogue;
+/* colstats: the batch-norm statistics pass of the layer that FOLLOWS this conv (normalization.py:38-41 moments over [0,1,2]),
+ * taken from the values as they are stored: every CTA of the persistent kernel writes its partial per-column sum and sum of
+ * squares, [RCGAN_COLSTATS_PARTS][2][N] floats followed by [RCGAN_COLSTATS_PARTS] row counts (rcgan_colstats_floats(N) in
+ * all); rcgan_bn_fwd_prestats merges them (Chan) instead of re-reading the tensor.  N in {64, 128, 256}, dense rows. */
+#define RCGAN_COLSTATS_PARTS 148
+size_t rcgan_colstats_floats(int n);
 int rcgan_conv2d_fprop_ex(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y, int out_dtype,
                           int act, float leak, const rcgan_conv_epilogue* ep, void* stream);
 int rcgan_conv2d_dgrad_ex(const rcgan_conv_desc* d, const void* dy, const void* wpack, const float* bias, void* dx, int out_dtype,
@@ -196,6 +203,11 @@ size_t rcgan_bn_workspace(int samples, int hw, int c);
 int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale, const float* offset,
                  const int* labels, float eps, int act, float leak, int train, float decay, float* moving_mean,
                  float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream);
+/* rcgan_bn_fwd in training mode with the batch statistics taken from a producing conv's epilogue partials (see
+ * rcgan_conv_epilogue.colstats): 1 read + 1 write of the activation instead of 2 reads + 1 write */
+int rcgan_bn_fwd_prestats(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
+                          const float* offset, const int* labels, float eps, int act, float leak, float decay, float* moving_mean,
+                          float* moving_var, float* save, const float* colstats, void* stream);
 /* dx (=|+=) ; dscale/doffset [n_labels, c] (=|+=).  y is the activated forward output; with `offset` (the forward's table)
  * given and act relu / lrelu, the activation mask is re-derived from x as the sign of the forward pre-activation and y is not
  * read (may be NULL): 5 instead of 7 tensor passes. */

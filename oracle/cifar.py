@@ -205,7 +205,7 @@ def Generator(ctx, noise, labels, dim=128):
     out = ResidualBlock(ctx, out, n + 'G.Block.2', False, 'up', labels, dim * 2, dim * 2)
     out = ResidualBlock(ctx, out, n + 'G.Block.3', False, 'up', labels, dim * 2, dim * 2)
     out = q(torch.relu(Normalize(ctx, n + 'G.OutputNorm', out, labels)))
-    return q(torch.tanh(Conv2D(ctx, out, n + 'G.Output', False)))
+    return q(torch.tanh(O.qg(Conv2D(ctx, out, n + 'G.Output', False))))
 
 
 def Discriminator(ctx, x, dim=128):

@@ -167,7 +167,7 @@ def generator(P, z, y, cfg, train=True, upd=None):
     h2 = q(torch.relu(_bn(P, n + 'g_bn2', h2, train, upd)))
     h2 = O.conv_cond_concat(h2, y)
     h3 = O.conv2d_transpose(h2, qw(P[n + 'g_h3/w']), (s_h, s_w)) + P[n + 'g_h3/biases']
-    return q(torch.sigmoid(h3))
+    return q(torch.sigmoid(O.qg(h3)))
 
 
 def discriminator(P, image, y, cfg, upd=None):
@@ -179,7 +179,7 @@ def discriminator(P, image, y, cfg, upd=None):
         cc = lambda l, t: O.conv_cond_concat(t, y) if (cfg.concat_y and l in cfg.concat_y_layers) else t
         sn = cfg.spectral_norm
         q = O.q                    # bf16 storage points of the product's trunk (identity unless O.bf16_storage() is active)
-        h0 = q(O.lrelu(_conv(P, n + 'd_h0_conv', cc(1, q(image)), sn, upd)))
+        h0 = q(O.lrelu(O.qg(_conv(P, n + 'd_h0_conv', cc(1, q(image)), sn, upd))))
         h1 = q(O.lrelu(_bn(P, n + 'd_bn1', q(_conv(P, n + 'd_h1_conv', cc(2, h0), sn, upd)), True, upd, track=False)))
         h2 = q(O.lrelu(_bn(P, n + 'd_bn2', q(_conv(P, n + 'd_h2_conv', cc(3, h1), sn, upd)), True, upd, track=False)))
         h3 = q(O.lrelu(_bn(P, n + 'd_bn3', q(_conv(P, n + 'd_h3_conv', cc(4, h2), sn, upd)), True, upd, track=False)))

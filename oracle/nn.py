@@ -233,6 +233,22 @@ class _RoundFwd(torch.autograd.Function):
         return g
 
 
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def qg(x):
+    """a pre-activation that exists only inside a conv epilogue: its VALUE is never stored, but its gradient is (the fused
+    activation's backward runs in place on the bf16 output gradient before dgrad / wgrad / the bias sum read it)"""
+    return _RoundBwd.apply(x) if _EMUL['on'] else x
+
+
 def emulating():
     return _EMUL['on']
 

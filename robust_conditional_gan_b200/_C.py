@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 9        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 10        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -35,7 +35,7 @@ DP = POINTER(ConvDesc)
 class ConvEpilogue(ctypes.Structure):
     """mirror of rcgan_conv_epilogue (include/rcgan_b200.h)"""
     _fields_ = [('mask', c_void_p), ('mask_act', c_int), ('mask_leak', c_float), ('res', c_void_p), ('res_up', c_int),
-                ('ld_res', c_int), ('out2', c_void_p), ('out2_act', c_int)]
+                ('ld_res', c_int), ('out2', c_void_p), ('out2_act', c_int), ('colstats', c_void_p)]
 
 
 EP = POINTER(ConvEpilogue)
@@ -85,6 +85,8 @@ _SIGS = {
                              P, P, c_size_t, P]),
     'rcgan_bn_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_int,
                              c_int, P, c_size_t, P, P]),
+    'rcgan_bn_fwd_prestats': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_float, c_int, c_float, c_float, P, P, P, P, P]),
+    'rcgan_colstats_floats': (c_size_t, [c_int]),
     'rcgan_bn_infer_bwd': (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_float, c_int, P, c_size_t, P]),
     'rcgan_bn_fwd_cat': (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_float, c_int, c_float, c_int, c_float,
                                  P, P, P, P, c_size_t, P]),

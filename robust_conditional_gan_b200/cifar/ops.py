@@ -84,7 +84,13 @@ def cond_batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update
     with S.variable_scope('CondBatchNorm'):
         offset_m = S.get_variable('offset', [n_labels, c], _const(0.))
         scale_m = S.get_variable('scale', [n_labels, c], _const(1.))
-    return BatchNormOp(inputs, scale_m, offset_m, labels, None, True, 1e-5, 0.9, fuse_act, groups=groups).y
+    # the statistics pass rides in the producing conv's epilogue when that conv runs the persistent tensor-core kernel
+    prod = getattr(inputs.base, 'producer', None)
+    stats_from = None
+    if (groups == 1 and isinstance(prod, (ConvOp, DeconvOp)) and prod.outputs[0].base is inputs.base and prod.outputs[0] is inputs
+            and prod.can_emit_colstats()):
+        stats_from = prod
+    return BatchNormOp(inputs, scale_m, offset_m, labels, None, True, 1e-5, 0.9, fuse_act, groups=groups, stats_from=stats_from).y
 
 
 def embed_y(inputs, vocab_size, embedding_dim, word2vec_file=None, name='Embedding.Label'):

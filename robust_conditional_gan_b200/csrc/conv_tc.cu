@@ -46,6 +46,7 @@ struct TcParams {
   float mask_leak;
   void* out2;                 // second output act2(final value), laid out like out
   int out2_act;
+  float* colstats;            // persistent kernel: per-CTA partial column sums / sums of squares of the stored output (batch-norm statistics)
   // TMA im2col A loader (one cp.async.bulk.tensor.im2col per K block instead of 1024 cp.async):
   // base pixel of GEMM row (n,a,b) = (im_h_lo + a*im_sh, im_w_lo + b*im_sw); tap t adds (toffh[t], toffw[t])
   int im_w_lo, im_h_lo, im_sw, im_sh;
@@ -178,7 +179,8 @@ template <int BN, int ST> struct Cfg {
 // pieces.  Only the owning warp touches its slab, so __syncwarp() orders the two phases.
 template <int BN, int AVAIL, typename TO, int U = 4>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
-                                            int n0, uint32_t tempty_bar = 0, int bn_lim = BN) {
+                                            int n0, uint32_t tempty_bar = 0, int bn_lim = BN, float* st_acc = nullptr,
+                                            int* st_cnt = nullptr) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   constexpr int PITCH = BN * (int)sizeof(TO) + 16;
   static_assert(4 * 32 * PITCH + 2048 <= AVAIL, "staging must fit the drained pipeline buffers");
@@ -273,7 +275,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
   const bool fast = p.ld_out % VEC == 0 && (reinterpret_cast<uintptr_t>(out + n0) & 15) == 0 && ncols >= VEC &&
                     (reinterpret_cast<uintptr_t>(addsrc) & 15) == 0 && (!up || p.ld_res % VEC == 0) &&
                     (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0;
-  if (sizeof(TO) == 2 && (mask || out2 || up)) {
+  if (sizeof(TO) == 2 && (mask || out2 || up || st_acc)) {
     // fused variant of the store loop (bf16 only): mask -> residual / accumulate -> store -> second output
     const float mleak = p.mask_act == RCGAN_ACT_LRELU ? p.mask_leak : 0.f;
     if (fast) {
@@ -329,6 +331,18 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
             c[e] = __floats2bfloat162_rn(fc.x, fc.y);
           }
           *reinterpret_cast<uint4*>(out + off[u]) = q[u];
+          if (st_acc) {
+            // batch-norm statistics of the tensor being stored (the bf16 values a separate statistics pass would read back):
+            // a lane owns the same 8 columns in every row it stores (ncols / 8 is a power of two <= 32), so the running
+            // sums stay in registers across all tiles of this persistent CTA
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float2 f = __bfloat1622float2(c[e]);
+              st_acc[2 * e] += f.x; st_acc[2 * e + 1] += f.y;
+              st_acc[8 + 2 * e] = fmaf(f.x, f.x, st_acc[8 + 2 * e]); st_acc[8 + 2 * e + 1] = fmaf(f.y, f.y, st_acc[8 + 2 * e + 1]);
+            }
+            (*st_cnt)++;
+          }
           if (out2) {
             const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
@@ -651,6 +665,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   if (warp < 4) {
     // =========================================================== epilogue warps
     int ti = 0;
+    float st_acc[16];
+    int st_cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) st_acc[j] = 0.f;
+    const bool stats = sizeof(TO) == 2 && p0.colstats != nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ti++) {
       const int a = ti & 1;
       int q;
@@ -661,8 +680,30 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < MT; j++)
-        tc_epilogue<BN, C::EPI_BYTES, TO, 8>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
-                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u, bn);
+        tc_epilogue<BN, C::EPI_BYTES, TO, 4>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
+                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u, bn, stats ? st_acc : nullptr, &st_cnt);
+    }
+    if (stats) {
+      // this CTA's partial (count, column sums, column sums of squares): lanes -> shared atomics -> one row of p0.colstats
+      // layout: [RCGAN_NUM_SMS][2][N] floats, then [RCGAN_NUM_SMS] row counts; CTAs that do not exist leave count 0
+      float* S = reinterpret_cast<float*>(epi);
+      int* Cn = reinterpret_cast<int*>(S + 2 * BN);
+      const int tid = warp * 32 + lane, lpr = bn / 8;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = tid; i < 2 * BN + 1; i += 128) S[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int col0 = (lane % lpr) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { atomicAdd(&S[col0 + j], st_acc[j]); atomicAdd(&S[BN + col0 + j], st_acc[8 + j]); }
+      atomicAdd(Cn, st_cnt);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p0.colstats + (size_t)blockIdx.x * 2 * p0.N;
+      for (int i = tid; i < p0.N; i += 128) { dst[i] = S[i]; dst[p0.N + i] = S[BN + i]; }
+      float* counts = p0.colstats + (size_t)RCGAN_NUM_SMS * 2 * p0.N;
+      if (tid == 0) {
+        counts[blockIdx.x] = (float)(*Cn / lpr);
+        for (int j = blockIdx.x + gridDim.x; j < RCGAN_NUM_SMS; j += gridDim.x) counts[j] = 0.f;
+      }
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -1288,7 +1329,8 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
   const int pm = persist_mode();
   const long big_tiles = (p.N > 128 && !p.out_f32) ? (long)((p.M + 127) / 128) * ((p.N + 255) / 256)
                                                    : (long)((p.M + 255) / 256) * ((p.N + 127) / 128);
-  const bool persist = im2col && pm != 0 && (pm == 2 || big_tiles >= 3 * RCGAN_NUM_SMS);
+  if (p.colstats && !im2col) { rcgan_set_error("conv_tc: column statistics need the TMA im2col path"); return RCGAN_EUNSUPPORTED; }
+  const bool persist = im2col && pm != 0 && (pm == 2 || p.colstats || big_tiles >= 3 * RCGAN_NUM_SMS);
   if (persist) {
     TcMulti mp;
     TcMaps amaps;
@@ -1302,6 +1344,9 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
 }
 
 }  // namespace
+
+extern "C" size_t rcgan_colstats_floats(int n) { return (size_t)RCGAN_COLSTATS_PARTS * (2 * (size_t)n + 1); }
+static_assert(RCGAN_COLSTATS_PARTS == RCGAN_NUM_SMS, "one partial per persistent CTA");
 
 extern "C" size_t rcgan_conv_wpack_bytes(const rcgan_conv_desc* d) {
   if (!d || !(fprop_ok(d) || dgrad_ok(d))) return 0;
@@ -1367,7 +1412,9 @@ extern "C" int rcgan_conv_wpack_batched(int count, const rcgan_conv_desc* const*
 // optional epilogue fusions -> kernel parameters (bf16 outputs only; the caller has validated the combination)
 static void set_epilogue(TcParams& p, const rcgan_conv_epilogue* ep) {
   p.res_up = 0; p.ld_res = 0; p.mask = nullptr; p.mask_act = 0; p.mask_leak = 0.f; p.out2 = nullptr; p.out2_act = 0;
+  p.colstats = nullptr;
   if (!ep) return;
+  p.colstats = ep->colstats;
   if (ep->res) { p.res = ep->res; p.res_up = ep->res_up; p.ld_res = ep->ld_res; }
   p.mask = ep->mask; p.mask_act = ep->mask_act; p.mask_leak = ep->mask_leak;
   p.out2 = ep->out2; p.out2_act = ep->out2_act;
@@ -1381,12 +1428,19 @@ static bool epilogue_ok(const rcgan_conv_epilogue* ep, int out_dtype, int accumu
   if (ep->out2 && ep->out2_act != RCGAN_ACT_RELU) return false;
   return true;
 }
+// column statistics need one N tile whose 16-byte pieces map to fixed lanes: N in {64, 128, 256}, dense rows, persistent kernel
+static bool colstats_ok(const rcgan_conv_epilogue* ep, int n, int ld_out) {
+  if (!ep || !ep->colstats) return true;
+  return (n == 64 || n == 128 || n == 256) && ld_out == n;
+}
 
 int rcgan_tc_fprop(const rcgan_conv_desc* d, const void* x, const void* wpack, const float* bias, const void* res, void* y,
                    int out_dtype, int act, float leak, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep) {
   *handled = 0;
   if (!fprop_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
-  if (!epilogue_ok(ep, out_dtype, 0, d->ho, d->wo)) { rcgan_set_error("conv2d_fprop_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED; }
+  if (!epilogue_ok(ep, out_dtype, 0, d->ho, d->wo) || !colstats_ok(ep, d->cout, d->ldy)) {
+    rcgan_set_error("conv2d_fprop_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED;
+  }
   PackGeo g = pack_geo(d);
   TcParams p;
   p.src = reinterpret_cast<const bf16*>(x);
@@ -1410,7 +1464,10 @@ int rcgan_tc_dgrad(const rcgan_conv_desc* d, const void* dy, const void* wpack, 
                    int act, float leak, int accumulate, cudaStream_t st, int* handled, const rcgan_conv_epilogue* ep) {
   *handled = 0;
   if (!dgrad_ok(d) || (out_dtype != RCGAN_BF16 && out_dtype != RCGAN_F32)) return 0;
-  if (!epilogue_ok(ep, out_dtype, accumulate, d->h, d->w)) { rcgan_set_error("conv2d_dgrad_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED; }
+  if (!epilogue_ok(ep, out_dtype, accumulate, d->h, d->w) || !colstats_ok(ep, d->cin, d->ldx) ||
+      (ep && ep->colstats && d->stride != 2 && d->stride != 1)) {
+    rcgan_set_error("conv2d_dgrad_ex: unsupported epilogue combination"); return RCGAN_EUNSUPPORTED;
+  }
   PackGeo g = pack_geo(d);
   const bf16* wD = reinterpret_cast<const bf16*>(wpack) + g.offD;
   const int s = d->stride;

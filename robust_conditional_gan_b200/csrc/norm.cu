@@ -175,6 +175,51 @@ __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(Geo g, const flo
   }
 }
 
+// statistics from the per-CTA partial sums a producing conv accumulated in its epilogue (rcgan_conv_epilogue.colstats:
+// [RCGAN_NUM_SMS][2][c] sums / sums of squares, then [RCGAN_NUM_SMS] row counts): one warp per channel, every partial is turned
+// into (n, mean, M2) in double and Chan-merged -- the subtraction sumsq - sum^2/n only ever spans one CTA's rows
+__global__ void __launch_bounds__(256) bn_stats_from_partials_kernel(int c, const float* __restrict__ parts, float eps, float decay,
+                                                                    float* mm, float* mv, float* __restrict__ save) {
+  pdl_sync();
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  const float* counts = parts + (size_t)RCGAN_NUM_SMS * 2 * c;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int k = lane; k < RCGAN_NUM_SMS; k += 32) {
+    const double nb = (double)counts[k];
+    if (nb <= 0.0) continue;
+    const double sb = (double)parts[(size_t)k * 2 * c + ch], qb = (double)parts[(size_t)k * 2 * c + c + ch];
+    const double mb = sb / nb, m2b = fmax(qb - sb * mb, 0.0);
+    const double nt = n + nb, delta = mb - mean;
+    mean += delta * (nb / nt);
+    m2 += m2b + delta * delta * (n * nb / nt);
+    n = nt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                 m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+    const double nt = n + nb;
+    if (nt > 0.0) {
+      const double delta = mb - mean;
+      mean += delta * (nb / nt);
+      m2 += m2b + delta * delta * (n * nb / nt);
+    }
+    n = nt;
+  }
+  if (lane == 0) {
+    const float var = (float)(m2 / n), fm = (float)mean, fn = (float)n;
+    save[ch] = fm;
+    save[c + ch] = rsqrtf(var + eps);
+    if (mm) {
+      const float unbiased = var * (fn / fmaxf(fn - 1.f, 1.f));
+      mm[ch] = decay * mm[ch] + (1.f - decay) * fm;
+      mv[ch] = decay * mv[ch] + (1.f - decay) * unbiased;
+    }
+  }
+}
+
 __global__ void bn_infer_stats_kernel(int c, const float* __restrict__ mm, const float* __restrict__ mv, float eps,
                                       float* __restrict__ save) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
@@ -459,7 +504,7 @@ extern "C" size_t rcgan_bn_workspace(int samples, int hw, int c) {
 static int bn_fwd_impl(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
                        const float* offset, const int* labels, float eps, int act, float leak, int train, float decay,
                        float* moving_mean, float* moving_var, float* save, void* ws, size_t ws_bytes, void* stream, int ldy,
-                       const float* yb, int c2) {
+                       const float* yb, int c2, const float* colstats = nullptr) {
   RCGAN_CHECK_ARG(samples > 0 && hw > 0 && c > 0, "bn_fwd: bad shape");
   RCGAN_CHECK_ARG(ldy >= c + c2 && (ldy == c || ldy % 8 == 0) && c2 >= 0 && (c2 == 0 || yb), "bn_fwd: bad concat geometry");
   if (int e = check_types(xdtype, ydtype, "bn_fwd")) return e;
@@ -467,7 +512,10 @@ static int bn_fwd_impl(const void* x, void* y, int samples, int hw, int c, int x
   RCGAN_CHECK_ARG((long)samples * hw * c < 2147483647L, "bn_fwd: too large");
   cudaStream_t st = as_stream(stream);
   Geo g = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? stats_vmax() : 4);
-  if (train) {
+  if (train && colstats) {
+    launch_pdl(bn_stats_from_partials_kernel, ceil_div(c, 8), 256, 0, st, c, colstats, eps, decay, moving_mean, moving_var, save);
+    RCGAN_LAUNCH_CHECK("bn_stats_from_partials");
+  } else if (train) {
     RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_fwd: workspace too small");
     dim3 grid(g.gx, g.nchunk);
     size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
@@ -494,6 +542,14 @@ extern "C" int rcgan_bn_fwd(const void* x, void* y, int samples, int hw, int c, 
                             void* stream) {
   return bn_fwd_impl(x, y, samples, hw, c, xdtype, ydtype, scale, offset, labels, eps, act, leak, train, decay, moving_mean,
                      moving_var, save, ws, ws_bytes, stream, c, nullptr, 0);
+}
+
+extern "C" int rcgan_bn_fwd_prestats(const void* x, void* y, int samples, int hw, int c, int xdtype, int ydtype, const float* scale,
+                                     const float* offset, const int* labels, float eps, int act, float leak, float decay,
+                                     float* moving_mean, float* moving_var, float* save, const float* colstats, void* stream) {
+  RCGAN_CHECK_ARG(colstats, "bn_fwd_prestats: null statistics");
+  return bn_fwd_impl(x, y, samples, hw, c, xdtype, ydtype, scale, offset, labels, eps, act, leak, 1, decay, moving_mean,
+                     moving_var, save, nullptr, 0, stream, c, nullptr, 0, colstats);
 }
 
 extern "C" int rcgan_bn_fwd_cat(const void* x, void* y, int ldy, const float* yb, int c2, int samples, int hw, int c, int xdtype,

@@ -16,6 +16,7 @@ from .graph import Op, Tensor, cur, is_static_weight, needs, round_up, same_pad
 FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '0') == '1'
 ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
 FUSE_RELU_OUT = os.environ.get('RCGAN_FUSE_RELU_OUT', '1') == '1'
+FUSE_BN_STATS = os.environ.get('RCGAN_FUSE_BN_STATS', '1') == '1'
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -199,6 +200,17 @@ class ConvOp(Op):
         self.res, self.res_up = residual, bool(up)
         self.inputs = (self.x, self.w, self.b, residual)
 
+    def can_emit_colstats(self):
+        """the following batch norm's statistics pass can ride in this conv's (persistent-kernel) epilogue"""
+        return (FUSE_BN_STATS and getattr(self, 'colstats', None) is None and self._plain_tc_fprop() and self.y.c in (64, 128, 256)
+                and self.y.ld == self.y.c and self.desc.kh * self.desc.kw > 1)
+
+    def emit_colstats(self):
+        assert self.can_emit_colstats()
+        self.colstats = torch.zeros(_C.load().rcgan_colstats_floats(self.y.c), dtype=torch.float32, device=cur().device)
+        self.ep_fwd = None
+        return self.colstats
+
     def can_emit_relu(self):
         return FUSE_RELU_OUT and self.y2 is None and self.act == _C.ACT_NONE and self._plain_tc_fprop()
 
@@ -303,10 +315,12 @@ class ConvOp(Op):
             d, xin = self.gdesc, dp(self.patch)
         if self.pack_owner:
             call('rcgan_conv_wpack', d, dp(self.w), None, pp(self.pack), stream_ptr())
-        if self.res_up or self.y2 is not None or (self.res is not None and self._plain_tc_fprop()):
+        colstats = getattr(self, 'colstats', None)
+        if self.res_up or self.y2 is not None or colstats is not None or (self.res is not None and self._plain_tc_fprop()):
             if getattr(self, 'ep_fwd', None) is None:
                 self.ep_fwd = _C.ConvEpilogue(res=dp(self.res), res_up=int(self.res_up), ld_res=self.res.ld if self.res is not None else 0,
-                                              out2=dp(self.y2), out2_act=_C.ACT_RELU if self.y2 is not None else 0)
+                                              out2=dp(self.y2), out2_act=_C.ACT_RELU if self.y2 is not None else 0,
+                                              colstats=pp(colstats))
             call('rcgan_conv2d_fprop_ex', d, xin, pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act, self.leak,
                  ctypes.byref(self.ep_fwd), stream_ptr())
             return
@@ -389,6 +403,17 @@ class DeconvOp(Op):
         self.scatter = ScatterDgrad(prog, self.desc, x.ld) if self.patch is not None else None
         prog.add(self)
 
+    def can_emit_colstats(self):
+        return (FUSE_BN_STATS and getattr(self, 'colstats', None) is None and self.x.dtype == _C.BF16 and self.y.dtype == _C.BF16
+                and self.pack is not None and self.patch is None and self.y.c in (64, 128, 256) and self.y.ld == self.y.c
+                and bool(_C.load().rcgan_conv_uses_tensor_cores(self.desc, 1)))
+
+    def emit_colstats(self):
+        assert self.can_emit_colstats()
+        self.colstats = torch.zeros(_C.load().rcgan_colstats_floats(self.y.c), dtype=torch.float32, device=cur().device)
+        self.ep_fwd = _C.ConvEpilogue(colstats=pp(self.colstats))
+        return self.colstats
+
     def plan_bwd(self, prog):
         nx, nw, nb = self.need
         self.acc_x = self.claim(self.x) if nx else 0
@@ -402,6 +427,10 @@ class DeconvOp(Op):
                  stream_ptr())
         if self.scatter is not None and self.scatter.ok:
             self.scatter.run(dp(self.w), dp(self.x), dp(self.y), self.y.dtype, dp(self.b), self.act, self.leak, 0, stream_ptr())
+            return
+        if getattr(self, 'colstats', None) is not None:
+            call('rcgan_conv2d_dgrad_ex', self.desc, dp(self.x), pp(self.pack), dp(self.b), dp(self.y), self.y.dtype, self.act, self.leak,
+                 0, ctypes.byref(self.ep_fwd), stream_ptr())
             return
         call('rcgan_conv2d_dgrad', self.desc, dp(self.x), dp(self.w), None if self.patch is not None else pp(self.pack),
              dp(self.b), dp(self.y), self.y.dtype, self.act,
@@ -433,7 +462,7 @@ class BatchNormOp(Op):
     labels int32 [n]: cond_batchnorm (cifar10/common/ops/normalization.py:27-59), tables [n_labels,c]."""
 
     def __init__(self, x, scale, offset, labels=None, moving=None, train=True, eps=1e-5, decay=0.9, act=None, leak=0.2, groups=1,
-                 concat_y=None):
+                 concat_y=None, stats_from=None):
         """concat_y (fp32 [n, c2]): the output is concat([act(BN(x)), y broadcast over H, W]) -- the generator's
         conv_cond_concat / concat right after each norm (mnist/model.py:714-728) -- written in the same pass.
         groups > 1: the batch is `groups` equal sample ranges with INDEPENDENT batch statistics (the reference's separate
@@ -444,6 +473,10 @@ class BatchNormOp(Op):
         assert n % groups == 0
         self.groups, self.samples, self.hw, self.c = groups, n // groups, h * w, x.c
         assert x.ld == x.c
+        # stats_from: the conv that produces x accumulates the batch statistics in its epilogue (emit_colstats): no statistics pass
+        self.stats_buf = None
+        if stats_from is not None and train and groups == 1 and concat_y is None:
+            self.stats_buf = stats_from.emit_colstats()
         self.n_labels = scale.numel() // x.c
         self.moving, self.train, self.eps, self.decay = moving, train, eps, decay
         self.act, self.leak = ACT[act], leak
@@ -491,6 +524,11 @@ class BatchNormOp(Op):
             call('rcgan_bn_fwd_cat', dp(self.x), dp(self.y), self.y.ld, dp(self.cat), self.c2, self.samples, self.hw, self.c,
                  self.x.dtype, self.y.dtype, dp(self.scale), dp(self.offset), dp(self.labels), self.eps, self.act, self.leak,
                  1 if self.train else 0, self.decay, mm, mv, self.save[0].data_ptr(), prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+            return
+        if self.stats_buf is not None:
+            call('rcgan_bn_fwd_prestats', dp(self.x), dp(self.y), self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale),
+                 dp(self.offset), dp(self.labels), self.eps, self.act, self.leak, self.decay, mm, mv, self.save[0].data_ptr(),
+                 pp(self.stats_buf), stream_ptr())
             return
         xs, ys = self.x.data.element_size(), self.y.data.element_size()
         for g in range(self.groups):

@@ -250,7 +250,7 @@ def test_generator_sampler(lib):
     assert got.shape == (20, 32, 32, 3) and relerr(torch.as_tensor(got), ref) < 1e-4
 
 
-def _calibrated(vars_, got_of, plain, emul, label, slack=1.6, floor=2e-3):
+def _calibrated(vars_, got_of, plain, emul, label, slack=2.0, floor=2e-3):
     """product-vs-fp64 error of every variable's gradient against what bf16 STORAGE alone costs (emulated-vs-fp64 oracle)"""
     rows = []
     for v in vars_:
@@ -271,7 +271,7 @@ def test_bf16_error_is_the_storage_quantisation_gap(lib, alg):
     gradients, weight packs incl. the folded filters) with fp64 arithmetic in between.
       * losses: product vs the storage-emulating oracle <= 1e-3 (north_star's loss bar; measured 5e-5);
       * generated images: product vs emulated <= 1e-2 (measured 7.5e-3 after 21 stored layers; 2e-5 after the first);
-      * every per-variable gradient: (product vs fp64) <= 1.6 x (emulated vs fp64) + 2e-3 -- a kernel defect of the size VERDICT r1
+      * every per-variable gradient: (product vs fp64) <= 2 x (emulated vs fp64) + 2e-3 -- a kernel defect of the size VERDICT r1
         worried about (10 % in a bf16-only path) sits 3-5x above the 1.3-3e-2 the discriminator's storage rounding costs.
     Element-exact agreement with the emulation is not attainable end to end: one bf16 rounding that lands on the other side of
     a tie (fp32 vs fp64 accumulation, 1 element in 1e4) perturbs everything downstream by a bf16 ulp, which re-randomises the

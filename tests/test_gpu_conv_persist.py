@@ -318,3 +318,54 @@ def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, vari
     assert torch.equal(y2[..., :cout], torch.relu(ref[..., :cout]))
     if ldy > cout:
         assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0 and float((y2[..., cout:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('shape,kind', [((64, 32, 32, 256, 256, 3, 1, 0, 0), 'fprop'), ((5, 16, 16, 128, 128, 3, 1, 0, 0), 'fprop'),
+                                        ((300, 8, 8, 64, 64, 3, 1, 0, 0), 'fprop'), ((130, 16, 16, 256, 256, 4, 2, 0, 0), 'deconv'),
+                                        ((3, 8, 8, 128, 256, 4, 2, 0, 0), 'deconv')])
+def test_epilogue_column_statistics(lib, shape, kind):
+    """rcgan_conv_epilogue.colstats: per-CTA partial sums / sums of squares / row counts of the STORED bf16 output, merged here on
+    the host, equal the moments of the tensor (what the following conditional batch norm needs: normalization.py:38-41);
+    rcgan_bn_fwd_prestats on them == rcgan_bn_fwd with its own statistics pass.  The persistent kernel is forced for small shapes."""
+    import ctypes
+    d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
+    n, h, w, cin, cout = shape[:5]
+    pack, wd = pack_for(lib, d, wt)
+    N = cout if kind == 'fprop' else cin
+    parts = torch.full((lib.rcgan_colstats_floats(N),), 7.0, device='cuda')
+    ep = _C.ConvEpilogue(colstats=parts.data_ptr())
+    if kind == 'fprop':
+        y = torch.zeros(n, ho, wo, cout, device='cuda', dtype=torch.bfloat16)
+        call('rcgan_conv2d_fprop_ex', d, xd.data_ptr(), pack.data_ptr(), keep(dev(b)), y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0,
+             ctypes.byref(ep), st())
+    else:       # the folded UpsampleConv: conv2d_transpose = dgrad of the 4x4 stride-2 conv, 4 parity problems in one launch
+        y = torch.zeros(n, h, w, cin, device='cuda', dtype=torch.bfloat16)
+        bias = torch.randn(cin, generator=torch.Generator().manual_seed(2))
+        call('rcgan_conv2d_dgrad_ex', d, dyd.data_ptr(), pack.data_ptr(), keep(dev(bias)), y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, 0,
+             ctypes.byref(ep), st())
+    torch.cuda.synchronize()
+    assert _C.last_conv_variant().startswith('conv_tc_persist<')
+    P = 148
+    sums = parts[:P * 2 * N].reshape(P, 2, N).double().cpu()
+    counts = parts[P * 2 * N:].double().cpu()
+    live = counts > 0
+    rows = y.numel() // N
+    assert int(counts.sum()) == rows and float(counts.min()) >= 0
+    yf = y.double().cpu().reshape(rows, N)
+    assert relerr(sums[live, 0].sum(0), yf.sum(0)) < 1e-5
+    assert relerr(sums[live, 1].sum(0), (yf * yf).sum(0)) < 1e-5
+    # the batch norm fed with these partials == the batch norm that reads the tensor twice
+    g = torch.Generator().manual_seed(4)
+    scale, offset = dev(torch.rand(10, N, generator=g) + 0.5), dev(torch.randn(10, N, generator=g))
+    spatial = y.shape[1] * y.shape[2]
+    lab = torch.randint(0, 10, (n,), generator=g).to(torch.int32).cuda()
+    nb = lib.rcgan_bn_workspace(n, spatial, N)
+    ws = torch.zeros(max(nb, 256), dtype=torch.uint8, device='cuda')
+    o1, o2 = torch.zeros_like(y), torch.zeros_like(y)
+    s1, s2 = torch.zeros(2 * N, device='cuda'), torch.zeros(2 * N, device='cuda')
+    call('rcgan_bn_fwd', y.data_ptr(), o1.data_ptr(), n, spatial, N, _C.BF16, _C.BF16, scale.data_ptr(), offset.data_ptr(), lab.data_ptr(),
+         1e-5, _C.ACT_RELU, 0.0, 1, 0.9, None, None, s1.data_ptr(), ws.data_ptr(), nb, st())
+    call('rcgan_bn_fwd_prestats', y.data_ptr(), o2.data_ptr(), n, spatial, N, _C.BF16, _C.BF16, scale.data_ptr(), offset.data_ptr(),
+         lab.data_ptr(), 1e-5, _C.ACT_RELU, 0.0, 0.9, None, None, s2.data_ptr(), parts.data_ptr(), st())
+    assert relerr(s2[:N], s1[:N]) < 1e-5 and relerr(s2[N:], s1[N:]) < 1e-5
+    assert relerr(o2.float(), o1.float()) < 1e-3

@@ -304,7 +304,7 @@ def test_train_loop_follows_the_reference_random_stream(lib):
 def test_bf16_error_is_the_storage_quantisation_gap(lib, run):
     """The MNIST counterpart of tests/test_gpu_cifar.py::test_bf16_error_is_the_storage_quantisation_gap: the oracle run plain
     (fp64) and with oracle.nn.bf16_storage() (rounding at the product's bf16 storage points); losses vs the emulation <= 2e-3,
-    every per-variable gradient: (product vs fp64) <= 1.6 x (emulated vs fp64) + 2e-3.  This replaces trust in the loose 25 % /
+    every per-variable gradient: (product vs fp64) <= 2 x (emulated vs fp64) + 2e-3.  This replaces trust in the loose 25 % /
     35 % bounds of test_bf16_step_matches_oracle: those ARE the storage gap behind three batch-norm backwards, and this test shows
     the kernels add nothing to it."""
     from oracle import nn as O
@@ -329,7 +329,7 @@ def test_bf16_error_is_the_storage_quantisation_gap(lib, run):
                 continue
             g = v.grad.reshape(a.shape)
             pa, ea = relerr(g, a), relerr(e, a)
-            if pa > 1.6 * ea + 2e-3:
+            if pa > 2.0 * ea + 2e-3:
                 bad.append((v.name, 'product-fp64 %.1e' % pa, 'storage-only %.1e' % ea, 'product-emulated %.1e' % relerr(g, e)))
         assert not bad, (label, bad[:8])
     calibrated(model.d_vars, 'd_grads', run + ' D')
