@@ -20,6 +20,10 @@ from . import ops as lib_ops
 
 NO_OPS = 'NO_OPS'
 FUSE_RESIDUAL = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL', '1') == '1'
+# ... in the discriminator too (its 128-channel convs are bound by the operand stream and their epilogue is NOT hidden: measured,
+# tools/epi_bench.py, the fused residual read costs +56 us on the 16x16 layer against ~22 us for the separate add kernel)
+FUSE_RESIDUAL_D = __import__('os').environ.get('RCGAN_FUSE_RESIDUAL_D', '0') == '1'
+FUSE_RELU_OUT_D = __import__('os').environ.get('RCGAN_FUSE_RELU_OUT_D', '1') == '1'
 # 3x3 ConvMeanPool / UpsampleConv as ONE 4x4 stride-2 conv / conv2d_transpose with the folded filter; 0 = A/B switch
 FOLD_RESAMPLE = __import__('os').environ.get('RCGAN_FOLD', '1') == '1'
 SPLIT_GRAPH = __import__('os').environ.get('RCGAN_DP_SPLIT_GRAPH', '0') == '1'
@@ -62,7 +66,7 @@ class Net:
             # D: the bare nonlinearity(inputs) (:318).  When `inputs` is the output of a conv with a fused-epilogue path (the previous
             # block's Conv2 + shortcut), that conv's epilogue writes relu(inputs) as a second output: no separate pass
             prod = getattr(inputs.base, 'producer', None)
-            if FUSE_RESIDUAL and isinstance(prod, ConvOp) and prod.y.base is inputs.base and prod.can_emit_relu():
+            if FUSE_RELU_OUT_D and isinstance(prod, ConvOp) and prod.y.base is inputs.base and prod.can_emit_relu():
                 return prod.emit_relu()
         return ActOp(inputs, fuse_act).y if fuse_act else inputs
 
@@ -125,7 +129,7 @@ class Net:
             # grid is a 4x flop / traffic cut (legal for parity; rooflines still use the reference flops).
             if resample == 'up':
                 shortcut = lib_ops.Conv2D(inputs, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)
-                if not FUSE_RESIDUAL:
+                if not (FUSE_RESIDUAL and ('G.' in name or FUSE_RESIDUAL_D)):
                     shortcut = Upsample2Op(shortcut).y
             elif resample == 'down':
                 shortcut = lib_ops.Conv2D(Pool2Op(inputs).y, input_dim, output_dim, 1, 1, name + '.Shortcut', he_init=False, **kw)
@@ -139,7 +143,8 @@ class Net:
             # D: Normalize is the identity (NORMALIZATION_D = False), so N2 + nonlinearity is a bare relu on Conv1's output:
             # it rides in Conv1's epilogue instead of a separate pass
             output = conv_1(output, filter_size=filter_size, name=name + '.Conv1', he_init=True, fuse_act='relu', **kw)
-        if not FUSE_RESIDUAL or (resample == 'down' and not FOLD_RESAMPLE):
+        fuse = FUSE_RESIDUAL and ('G.' in name or FUSE_RESIDUAL_D)
+        if not fuse or (resample == 'down' and not FOLD_RESAMPLE):
             output = conv_2(output, filter_size=filter_size, name=name + '.Conv2', he_init=True, **kw)
             return AddOp(shortcut, output).y
         # `shortcut + output` (:328) in Conv2's epilogue (rcgan_conv2d_fprop_ex): bit-identical to the separate add; an 'up' block's
@@ -153,7 +158,7 @@ class Net:
         kw = dict(spectral_normed=spectral_normed, update_collection=update_collection, biases=biases)
         shortcut = self.MeanPoolConv(inputs, output_dim=self.DIM_D, filter_size=1, name='D.Block.1.Shortcut', he_init=False, **kw)
         output = lib_ops.Conv2D(inputs, IMG_DIM, self.DIM_D, 3, 1, 'D.Block.1.Conv1', he_init=True, fuse_act='relu', **kw)
-        if FUSE_RESIDUAL and FOLD_RESAMPLE:
+        if FUSE_RESIDUAL and FUSE_RESIDUAL_D and FOLD_RESAMPLE:
             return self.ConvMeanPool(output, self.DIM_D, filter_size=3, name='D.Block.1.Conv2', he_init=True, residual=shortcut, **kw)
         output = self.ConvMeanPool(output, self.DIM_D, filter_size=3, name='D.Block.1.Conv2', he_init=True, **kw)
         return AddOp(shortcut, output).y

@@ -202,8 +202,11 @@ class ConvOp(Op):
 
     def can_emit_colstats(self):
         """the following batch norm's statistics pass can ride in this conv's (persistent-kernel) epilogue"""
+        # (only where the dispatch picks the persistent kernel anyway, >= 3 big tiles per SM: forcing it on a small layer costs more
+        # than the statistics pass it saves)
+        big_tiles = -(-self.y.rows // 128) if self.y.c > 128 else -(-self.y.rows // 256)
         return (FUSE_BN_STATS and getattr(self, 'colstats', None) is None and self._plain_tc_fprop() and self.y.c in (64, 128, 256)
-                and self.y.ld == self.y.c and self.desc.kh * self.desc.kw > 1)
+                and self.y.ld == self.y.c and big_tiles >= 3 * 148)
 
     def emit_colstats(self):
         assert self.can_emit_colstats()

@@ -261,6 +261,8 @@ def _calibrated(vars_, got_of, plain, emul, label, slack=2.0, floor=2e-3):
         rows.append((relerr(g, a), relerr(e, a), relerr(g, e), v.name.split('/', 1)[-1]))
     bad = [r for r in rows if r[0] > slack * r[1] + floor]
     assert not bad, (label, [(n_, 'product-fp64 %.1e' % pa, 'storage-only %.1e' % ea, 'product-emulated %.1e' % pe) for pa, ea, pe, n_ in bad[:8]])
+    mean_ratio = sum((r[0] + 1e-3) / (r[1] + 1e-3) for r in rows) / len(rows)
+    assert mean_ratio < 1.5, (label, 'mean error ratio product / storage-only', mean_ratio)
     return rows
 
 

@@ -304,7 +304,8 @@ def test_train_loop_follows_the_reference_random_stream(lib):
 def test_bf16_error_is_the_storage_quantisation_gap(lib, run):
     """The MNIST counterpart of tests/test_gpu_cifar.py::test_bf16_error_is_the_storage_quantisation_gap: the oracle run plain
     (fp64) and with oracle.nn.bf16_storage() (rounding at the product's bf16 storage points); losses vs the emulation <= 2e-3,
-    every per-variable gradient: (product vs fp64) <= 2 x (emulated vs fp64) + 2e-3.  This replaces trust in the loose 25 % /
+    every per-variable gradient: (product vs fp64) <= 2 x (emulated vs fp64) + 2e-3 (4 x for tensors under 4096 elements, which are
+    single draws of the rounding noise) and the mean ratio over the variables < 1.5.  This replaces trust in the loose 25 % /
     35 % bounds of test_bf16_step_matches_oracle: those ARE the storage gap behind three batch-norm backwards, and this test shows
     the kernels add nothing to it."""
     from oracle import nn as O
@@ -322,16 +323,19 @@ def test_bf16_error_is_the_storage_quantisation_gap(lib, run):
         assert abs(got[k] - float(tr_e.last['d'][k])) < 2e-3, (k, got[k], tr_e.last['d'][k])
 
     def calibrated(vars_, key, label):
-        bad = []
+        bad, ratios = [], []
         for v in vars_:
             a, e = tr.last[key][v.name], tr_e.last[key][v.name]
             if float(a.norm()) < 1e-9:
                 continue
             g = v.grad.reshape(a.shape)
             pa, ea = relerr(g, a), relerr(e, a)
-            if pa > 2.0 * ea + 2e-3:
+            ratios.append((pa + 1e-3) / (ea + 1e-3))
+            # small tensors (norm tables, the 10x10 confusion logits) are single draws of the rounding noise: wider band
+            if pa > (2.0 if a.numel() >= 4096 else 4.0) * ea + 2e-3:
                 bad.append((v.name, 'product-fp64 %.1e' % pa, 'storage-only %.1e' % ea, 'product-emulated %.1e' % relerr(g, e)))
         assert not bad, (label, bad[:8])
+        assert sum(ratios) / len(ratios) < 1.5, (label, 'mean error ratio product / storage-only', sum(ratios) / len(ratios))
     calibrated(model.d_vars, 'd_grads', run + ' D')
     tr_e.P = {k: v.detach().clone() for k, v in tr.P.items()}
     tr.g_step(batch)

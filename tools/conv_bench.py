@@ -19,6 +19,9 @@ SHAPES = [  # n, h, w, cin, cout, k
     (200704, 1, 1, 144, 25, 1, 7),
     (1024, 14, 14, 64, 138, 5, 6),
     (1024, 14, 14, 128, 138, 5, 6, 2),   # the conv g_h2 transposes (bench.py's MNIST roofline kernel is its dgrad)
+    (512, 16, 16, 128, 128, 3),          # 13: CIFAR D.Block.2 at [real; fake]
+    (512, 8, 8, 128, 128, 3),            # 14: CIFAR D.Block.3-6
+    (512, 16, 16, 128, 128, 4, 0, 2),    # 15: the folded ConvMeanPool of D.Block.2 (4x4 stride 2)
 ]
 
 
