@@ -184,7 +184,7 @@ class VariableStore:
 
     def load_state_dict(self, sd):
         for n, t in sd.items():
-            self.vars[n].data.copy_(torch.as_tensor(t).to(self.vars[n].data.device, torch.float32).reshape(-1))
+            self.vars[n].data.copy_(torch.as_tensor(t).detach().to(self.vars[n].data.device, torch.float32).reshape(-1))
         for cb in self.on_load:
             cb()
 

@@ -14,6 +14,13 @@ from robust_conditional_gan_b200.cifar.gan_resnet import RCGANCifar, default_fla
 from robust_conditional_gan_b200.parallel import shard
 
 
+def mark(rank, what):
+    """progress marker on stderr (a hang is located by the last marker of each rank)"""
+    if os.environ.get('DP_CHECK_TRACE'):
+        sys.stderr.write('[dp_check rank %d] %s\n' % (rank, what))
+        sys.stderr.flush()
+
+
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -32,8 +39,10 @@ def main():
                dequant_noise=torch.zeros(n, 3072))
     model.feed(model.g_prog, noise=mine['noise_G'], all_random_labels_G=mine['labels_random_G'],
                all_labels_biased_G=mine['labels_biased_G'])
+    mark(rank, 'fed')
     model.d_step(0)
     torch.cuda.synchronize()
+    mark(rank, 'd_step done')
     # reference: R towers in one process
     tr = OC.Trainer(P, ocfg)
     tr._req(tr.dn)
@@ -51,11 +60,13 @@ def main():
     other = flat.clone()
     dist.broadcast(other, src=0)
     same = bool(torch.equal(flat, other))
+    mark(rank, 'broadcast done')
     # G step from the same initial state: the bucketed all-reduce (generator arena + confusion_logits, launched from inside the
     # backward sweep) against the R-tower generator cost
     model.store.load_state_dict(P)
     model.g_step(1)
     torch.cuda.synchronize()
+    mark(rank, 'g_step done')
     tr = OC.Trainer(OC.init_params(ocfg, seed=1, dtype=torch.float64), ocfg)
     names = tr.gn + ['confusion_logits']
     tr._req(names)
@@ -71,7 +82,9 @@ def main():
     flatg = model.groups['g'].params.clone(); og = flatg.clone(); dist.broadcast(og, src=0)
     nb = {k: len(r.buckets) for k, r in model.reducers.items()}
     res = torch.tensor([worst, 0.0 if same else 1.0, 0.0 if torch.equal(flatg, og) else 1.0, worst_g], device='cuda', dtype=torch.float64)
+    mark(rank, 'oracle done')
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    mark(rank, 'final all_reduce done')
     if rank == 0:
         print('DP_CHECK world=%d worst_D_grad_relerr=%.2e worst_G_grad_relerr=%.2e params_diverged_D=%d params_diverged_G=%d buckets=%s' % (
             world, float(res[0]), float(res[3]), int(res[1]), int(res[2]), nb))
@@ -82,4 +95,11 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    except BaseException:
+        # a rank that dies with captured NCCL graphs alive can block in interpreter teardown: report and leave at once
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
