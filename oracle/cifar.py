@@ -205,7 +205,7 @@ def Generator(ctx, noise, labels, dim=128):
     out = ResidualBlock(ctx, out, n + 'G.Block.2', False, 'up', labels, dim * 2, dim * 2)
     out = ResidualBlock(ctx, out, n + 'G.Block.3', False, 'up', labels, dim * 2, dim * 2)
     out = q(torch.relu(Normalize(ctx, n + 'G.OutputNorm', out, labels)))
-    return q(torch.tanh(O.qg(Conv2D(ctx, out, n + 'G.Output', False))))
+    return O.stored_act(Conv2D(ctx, out, n + 'G.Output', False), 'tanh')
 
 
 def Discriminator(ctx, x, dim=128):
@@ -309,7 +309,7 @@ def gen_cost(P, batch, cfg):
     out = {'gen_wgan': cost}
     if cfg.perm_classifier:
         # perm_classifier never passes update_collection (gan_resnet.py:458-466) -> default None -> u IS updated here
-        pl = O.sigmoid_ce(perm_classifier(pctx, fake), eye[batch['labels_random_G']]).mean()
+        pl = O.sigmoid_ce(perm_classifier(pctx, O.qg(fake)), eye[batch['labels_random_G']]).mean()     # one rounding per gradient writer
         out['perm_fake'] = pl
         cost = cost + cfg.perm_multiplier * pl
     out['gen_cost'] = cost

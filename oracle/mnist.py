@@ -167,7 +167,7 @@ def generator(P, z, y, cfg, train=True, upd=None):
     h2 = q(torch.relu(_bn(P, n + 'g_bn2', h2, train, upd)))
     h2 = O.conv_cond_concat(h2, y)
     h3 = O.conv2d_transpose(h2, qw(P[n + 'g_h3/w']), (s_h, s_w)) + P[n + 'g_h3/biases']
-    return q(torch.sigmoid(O.qg(h3)))
+    return O.stored_act(h3, 'sigmoid')
 
 
 def discriminator(P, image, y, cfg, upd=None):
@@ -248,7 +248,9 @@ def losses(P, batch, cfg, C_actual=None, upd=None):
     out['d_loss_fake'], out['g_loss'] = d_loss_fake, g_loss
     if cfg.perm_regularizer:
         out['class_loss_real'] = O.sigmoid_ce(classifier(P, x), batch['y_real']).mean()
-        out['class_loss_fake'] = O.sigmoid_ce(classifier(P, G), batch['y_gen']).mean()
+        # (O.qg: in the product the classifier's gradient is WRITTEN to the image's bf16 gradient buffer before the discriminator's
+        # is accumulated into it -- one rounding per writer; identity outside the bf16 storage emulation)
+        out['class_loss_fake'] = O.sigmoid_ce(classifier(P, O.qg(G)), batch['y_gen']).mean()
     else:
         out['class_loss_real'] = torch.zeros((), dtype=dtype)
         out['class_loss_fake'] = torch.zeros((), dtype=dtype)

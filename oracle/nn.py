@@ -249,6 +249,34 @@ def qg(x):
     return _RoundBwd.apply(x) if _EMUL['on'] else x
 
 
+class _StoredAct(torch.autograd.Function):
+    """sigmoid / tanh fused into a conv epilogue: only the bf16-rounded OUTPUT is kept, and the backward derives the slope from it
+    (y(1-y), 1-y^2) -- near saturation that differs visibly from the slope at the unrounded value -- then rounds the gradient in
+    place"""
+    @staticmethod
+    def forward(ctx, x, kind):
+        y = (torch.sigmoid(x) if kind == 'sigmoid' else torch.tanh(x)).to(torch.bfloat16).to(x.dtype)
+        ctx.save_for_backward(y)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, = ctx.saved_tensors
+        slope = y * (1 - y) if ctx.kind == 'sigmoid' else 1 - y * y
+        return (g.to(torch.bfloat16).to(g.dtype) * slope).to(torch.bfloat16).to(g.dtype), None
+
+
+def stored_act(x, kind):
+    """sigmoid / tanh output of a conv epilogue (see _StoredAct); plain act(x) outside the emulation"""
+    if _EMUL['on']:
+        y = _StoredAct.apply(x, kind)
+        if _EMUL.get('trace') is not None:
+            _EMUL['trace'].append(y.detach())
+        return y
+    return torch.sigmoid(x) if kind == 'sigmoid' else torch.tanh(x)
+
+
 def emulating():
     return _EMUL['on']
 
