@@ -37,7 +37,7 @@ enum rcgan_loss_mode {
 };
 
 /* bumped on every signature change; robust_conditional_gan_b200/_C.py refuses a library whose version differs */
-#define RCGAN_ABI_VERSION 10
+#define RCGAN_ABI_VERSION 11
 const char* rcgan_last_error(void);
 int rcgan_abi_version(void);
 /* name of the kernel variant the last conv entry point (fprop / dgrad / wgrad / upconv) launched on the calling thread,
@@ -169,6 +169,11 @@ int rcgan_bias_act_fwd(const void* x, const float* bias, void* y, long rows, int
                        int act, float leak, void* stream);
 int rcgan_act_bwd(const void* dy, const void* y, void* dx, long rows, int c, int ld_dy, int ld_y, int ld_dx,
                   int dtype, int act, float leak, int accumulate, void* stream);
+/* rcgan_act_bwd in place followed by rcgan_colsum of the result, as ONE pass over dy: dy <- dy * act'(y); db (=|+=) column sums of
+ * the new dy -- the backward of a conv with a fused activation and a bias (mnist/ops.py:62-66 + lrelu, gan_resnet.py:318-325)
+ * starts with exactly these two steps.  Same roundings as the two kernels. */
+int rcgan_act_bwd_colsum(void* dy, const void* y, int rows, int c, int ld_dy, int ld_y, int dtype, int act, float leak, float* db,
+                         int accumulate, void* stream);
 /* out[r, 0:c1] = a[r,:], out[r, c1:c1+c2] = yb[r / rows_per_sample, :], out[r, c1+c2:ldo] = 0
  * (ops.conv_cond_concat mnist/ops.py:46-51 and the z|y, h|y concats of mnist/model.py:714-728);
  * yb is fp32 [samples, c2].  Backward: da (=|+=) dout[:, 0:c1]. */

@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 HINGE_D_REAL, HINGE_D_FAKE, HINGE_G, CE_D_REAL, CE_D_FAKE, CE_G = 0, 1, 2, 3, 4, 5
 MT_STATE_WORDS = 625
-ABI_VERSION = 10        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
+ABI_VERSION = 11        # == RCGAN_ABI_VERSION of include/rcgan_b200.h; bump both on every signature change
 
 
 class RcganError(RuntimeError):
@@ -62,6 +62,7 @@ _SIGS = {
     'rcgan_conv2d_wgrad': (c_int, [DP, P, P, P, c_int, P, c_size_t, P]),
     'rcgan_im2col': (c_int, [DP, P, P, c_int, P]),
     'rcgan_wflip': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'rcgan_act_bwd_colsum': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, c_int, P]),
     'rcgan_copy_batched': (c_int, [c_int, P, P, P, P]),
     'rcgan_wfold4': (c_int, [P, P, c_int, c_int, c_int, P]),
     'rcgan_wfold4_bwd': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

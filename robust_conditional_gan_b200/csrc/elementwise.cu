@@ -344,9 +344,12 @@ __global__ void colsum_kernel(const T* __restrict__ dy, int rows, int c, int ld,
 }
 
 // vector variant: LC lanes along 16-byte channel vectors x LR row lanes; one slab of rows per blockIdx.y
+// y != NULL: the fused activation backward of the layer first -- dy <- round(dy * act'(y)) in place (exactly rcgan_act_bwd), and
+// the column sums are taken of the rounded values (exactly rcgan_colsum of the result): one pass over dy instead of two
 template <typename T, int V>
-__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ dy, int rows, int cg, int ld, int LC,
-                                                         float* __restrict__ db, int accumulate, int use_atomic) {
+__global__ void __launch_bounds__(256) colsum_vec_kernel(T* __restrict__ dy, int rows, int cg, int ld, int LC,
+                                                         float* __restrict__ db, int accumulate, int use_atomic,
+                                                         const T* __restrict__ y = nullptr, int ldy = 0, int act = 0, float leak = 0.f) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ float sh[256 * V];
   const int LR = 256 / LC;
@@ -358,13 +361,28 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ d
 #pragma unroll
   for (int k = 0; k < V; k++) acc[k] = 0.f;
   if (cv < cg) {
-    const T* p = dy + (size_t)cv * V;
-#pragma unroll 4
-    for (int r = r0 + lr; r < r1; r += LR) {
-      float v[V];
-      ldv<T, V>(p + (size_t)r * ld, v);
+    T* p = dy + (size_t)cv * V;
+    if (y) {
+      const T* py = y + (size_t)cv * V;
+#pragma unroll 2
+      for (int r = r0 + lr; r < r1; r += LR) {
+        float v[V], yv[V];
+        ldv<T, V>(p + (size_t)r * ld, v);
+        ldv<T, V>(py + (size_t)r * ldy, yv);
 #pragma unroll
-      for (int k = 0; k < V; k++) acc[k] += v[k];
+        for (int k = 0; k < V; k++) v[k] = to_f(from_f<T>(__fmul_rn(v[k], act_bwd_from_y(yv[k], act, leak))));
+        stv<T, V>(p + (size_t)r * ld, v);
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] += v[k];
+      }
+    } else {
+#pragma unroll 4
+      for (int r = r0 + lr; r < r1; r += LR) {
+        float v[V];
+        ldv<T, V>(p + (size_t)r * ld, v);
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] += v[k];
+      }
     }
   }
 #pragma unroll
@@ -785,7 +803,24 @@ extern "C" int rcgan_cast(const void* src, int src_dtype, void* dst, int dst_dty
   return 0;
 }
 
+static int colsum_impl(void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream, const void* y, int ldy,
+                       int act, float leak);
 extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream) {
+  return colsum_impl(const_cast<void*>(dy), rows, c, ld, dtype, db, accumulate, stream, nullptr, 0, 0, 0.f);
+}
+extern "C" int rcgan_act_bwd_colsum(void* dy, const void* y, int rows, int c, int ld_dy, int ld_y, int dtype, int act, float leak,
+                                    float* db, int accumulate, void* stream) {
+  RCGAN_CHECK_ARG(dy && y && db, "act_bwd_colsum: null pointer");
+  const int w = vw(dtype);
+  const bool vec = c % w == 0 && ld_dy % w == 0 && ld_y % w == 0 && aligned16(dy) && aligned16(y) && rows >= 64;
+  if (!vec) {   // odd shapes: the two kernels it stands for
+    if (int e = rcgan_act_bwd(dy, y, dy, rows, c, ld_dy, ld_y, ld_dy, dtype, act, leak, 0, stream)) return e;
+    return rcgan_colsum(dy, rows, c, ld_dy, dtype, db, accumulate, stream);
+  }
+  return colsum_impl(dy, rows, c, ld_dy, dtype, db, accumulate, stream, y, ld_y, act, leak);
+}
+static int colsum_impl(void* dy, int rows, int c, int ld, int dtype, float* db, int accumulate, void* stream, const void* y, int ldy,
+                       int act, float leak) {
   RCGAN_CHECK_ARG(rows > 0 && c > 0 && ld >= c, "colsum: bad shape");
   cudaStream_t st = as_stream(stream);
   const int w = vw(dtype);
@@ -812,8 +847,8 @@ extern "C" int rcgan_colsum(const void* dy, int rows, int c, int ld, int dtype, 
   }
   if (vec) {
     dim3 grid(gx, gy);
-    if (dtype == RCGAN_F32) launch_pdl(colsum_vec_kernel<float, 4>, grid, 256, 0, st, (const float*)dy, rows, c / 4, ld, LC, db, accumulate, gy > 1);
-    else if (dtype == RCGAN_BF16) launch_pdl(colsum_vec_kernel<bf16, 8>, grid, 256, 0, st, (const bf16*)dy, rows, c / 8, ld, LC, db, accumulate, gy > 1);
+    if (dtype == RCGAN_F32) launch_pdl(colsum_vec_kernel<float, 4>, grid, 256, 0, st, (float*)dy, rows, c / 4, ld, LC, db, accumulate, gy > 1, (const float*)y, ldy, act, leak);
+    else if (dtype == RCGAN_BF16) launch_pdl(colsum_vec_kernel<bf16, 8>, grid, 256, 0, st, (bf16*)dy, rows, c / 8, ld, LC, db, accumulate, gy > 1, (const bf16*)y, ldy, act, leak);
     else { rcgan_set_error("bad dtype %d", dtype); return RCGAN_EBADSHAPE; }
   } else {
     dim3 grid(gx, gy), block(32, 8);

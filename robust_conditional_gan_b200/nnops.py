@@ -348,8 +348,14 @@ class ConvOp(Op):
             call('rcgan_upsample2_bwd', dy, gp(self.res), rn, rh, rw, self.res.c, self.res.grad_dtype, self.acc_r, st)
         elif nr and self.res is not None and not self.alias_r:
             call('rcgan_copy_acc', dy, gp(self.res), self.res.numel(), self.res.grad_dtype, self.acc_r, st)
+        bias_done = False
         if self.act != _C.ACT_NONE and not self.act_bwd_fused:
-            call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+            if nb and self.b is not None and y.dtype == y.grad_dtype:
+                # activation backward and the bias gradient's column sums in one pass over dL/dy
+                call('rcgan_act_bwd_colsum', dy, dp(y), y.rows, y.c, y.ld, y.ld, y.dtype, self.act, self.leak, gp(self.b), self.acc_b, st)
+                bias_done = True
+            else:
+                call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
@@ -371,7 +377,7 @@ class ConvOp(Op):
                 call('rcgan_conv2d_wgrad', self.gdesc, dp(self.patch), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
             else:
                 call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
-        if nb and self.b is not None:
+        if nb and self.b is not None and not bias_done:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 
 
@@ -445,8 +451,13 @@ class DeconvOp(Op):
         nx, nw, nb = self.need
         st = stream_ptr()
         y, dy = self.y, gp(self.y)
+        bias_done = False
         if self.act != _C.ACT_NONE and not self.act_bwd_fused:
-            call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+            if nb and self.b is not None and y.dtype == y.grad_dtype:
+                call('rcgan_act_bwd_colsum', dy, dp(y), y.rows, y.c, y.ld, y.ld, y.dtype, self.act, self.leak, gp(self.b), self.acc_b, st)
+                bias_done = True
+            else:
+                call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
         d, dyin = self.desc, dy
         if self.patch is not None and (nx or nw):
             call('rcgan_im2col', self.desc, dy, dp(self.patch), self.patch.ld, st)
@@ -456,7 +467,7 @@ class DeconvOp(Op):
                  0.0, st)
         if nw:
             call('rcgan_conv2d_wgrad', d, dyin, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
-        if nb and self.b is not None:
+        if nb and self.b is not None and not bias_done:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 
 

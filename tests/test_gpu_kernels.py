@@ -389,3 +389,23 @@ def test_wfold4_and_adjoint(lib, mode, cin, cout):
     assert relerr(dw.reshape(w.shape), wr.grad) < 1e-6
     call('rcgan_wfold4_bwd', gd.data_ptr(), dw.data_ptr(), cin, cout, mode, 1, st())
     assert relerr(dw.reshape(w.shape), 2 * wr.grad) < 1e-6
+
+
+@pytest.mark.parametrize('dtype', [_C.F32, _C.BF16])
+@pytest.mark.parametrize('rows,c,ld,act', [(4096, 128, 128, _C.ACT_RELU), (70000, 64, 64, _C.ACT_LRELU), (300, 24, 32, _C.ACT_TANH),
+                                            (50, 10, 16, _C.ACT_SIGMOID)])
+def test_act_bwd_colsum_equals_the_two_kernels(lib, rows, c, ld, act, dtype):
+    """rcgan_act_bwd_colsum == rcgan_act_bwd (in place) followed by rcgan_colsum, bit for bit on dy, to fp32 summation order on db"""
+    g = torch.Generator().manual_seed(rows)
+    td = TD[dtype]
+    dy = torch.randn(rows, ld, generator=g).to(td).cuda()
+    y = torch.randn(rows, ld, generator=g).to(td).cuda()
+    db0 = torch.randn(c, generator=g).cuda()
+    for acc in (0, 1):
+        a, b_ = dy.clone(), db0.clone()
+        call('rcgan_act_bwd', a.data_ptr(), y.data_ptr(), a.data_ptr(), rows, c, ld, ld, ld, dtype, act, 0.2, 0, st())
+        call('rcgan_colsum', a.data_ptr(), rows, c, ld, dtype, b_.data_ptr(), acc, st())
+        a2, b2 = dy.clone(), db0.clone()
+        call('rcgan_act_bwd_colsum', a2.data_ptr(), y.data_ptr(), rows, c, ld, ld, dtype, act, 0.2, b2.data_ptr(), acc, st())
+        assert torch.equal(a2, a)
+        assert relerr(b2, b_) < 1e-5
