@@ -297,12 +297,17 @@ def kernel_roofline(model, rows, pk):
     tot = sum(r['ms'] for r in rows)
     name = 'conv_tc %s n%d %dx%dx%d -> %dx%dx%d k%d s%d (%s %s)' % (form, d.n, d.h, d.w, d.cin, d.ho, d.wo, d.cout, d.kh, d.stride,
                                                                    prog.name, type(op).__name__)
-    traffic = None
+    # DRAM bytes per launch: not measurable inside the run (it needs the profiler) -- taken from the committed `ncu --set full`
+    # capture of this very kernel and shape; traffic_source names the file, null when there is no capture of the shape
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
     if os.path.exists(tp):
-        traffic = _json.load(open(tp)).get(name.split(' (')[0])
+        kt = _json.load(open(tp))
+        traffic = kt.get(name.split(' (')[0])
+        traffic_src = kt.get('_source', {}).get(name.split(' (')[0]) if traffic is not None else None
     return {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_burst'],
-            'traffic': traffic, 'peak_source': pk['src'] + ' bf16 burst (kernel timed alone)', 'kernel': name,
+            'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes': 2.0 * (d.n * d.h * d.w * d.cin + d.n * d.ho * d.wo * d.cout) + 2.0 * d.kh * d.kw * d.cin * d.cout,
+            'peak_source': pk['src'] + ' bf16 burst (kernel timed alone)', 'kernel': name,
             'launch_ms': ms / nl, 'flops_per_launch': flops / nl, 'launches_per_call': nl, 'conv_family_share_of_step': fam / tot}
 
 

@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
   }
 }
 
-template <typename TX, typename TY, int V>
-__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
+template <typename TX, typename TY, int V, bool FROM_X>
+__global__ void __launch_bounds__(256, 4) bn_bwd_partial_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
                                                              const TY* __restrict__ y, Geo g, const float* __restrict__ save,
                                                              int act, float leak, float* __restrict__ ws,
                                                              const float* __restrict__ scale, const float* __restrict__ offset,
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const TY* __restric
   for (int i = 0; i < V; i++) { s1[i] = 0.f; s2[i] = 0.f; mean[i] = 0.f; istd[i] = 0.f; ca[i] = 0.f; cb[i] = 0.f; }
   // relu / lrelu: the sign of the forward pre-activation a*x + b (same expression as bn_apply_kernel) IS the mask y > 0, so
   // the output tensor is not read back (2 of the 7 tensor passes of the backward)
-  const bool from_x = offset != nullptr && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU);
+  constexpr bool from_x = FROM_X;       // compile-time: the two forms keep separate (lean) register allocations
   if (cv < g.cg) {
 #pragma unroll
     for (int i = 0; i < V; i++) { mean[i] = save[cv * V + i]; istd[i] = save[g.c + cv * V + i]; }
@@ -409,8 +409,10 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(Geo g, float* __re
 }
 
 // dx = istd*(scale[label]*g - A - xhat*B) = c1*g + c2*(x - mean) + c3 with the coefficients in registers (see bn_apply_kernel)
-template <typename TX, typename TY, int V>
-__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
+// (4 blocks per SM: at 78 registers only 3 fit, and the 512 per-sample chunks of the largest generator norm then need a second,
+// 15 % full wave -- ncu: 224 us = 3.5 TB/s)
+template <typename TX, typename TY, int V, bool FROM_X>
+__global__ void __launch_bounds__(256, 4) bn_bwd_dx_kernel(const TY* __restrict__ dy, const TX* __restrict__ x,
                                                         const TY* __restrict__ y, TY* __restrict__ dx, Geo g,
                                                         const float* __restrict__ scale, const int* __restrict__ labels,
                                                         const float* __restrict__ save, const float* __restrict__ AB,
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const TY* __restrict__ d
   const int ch = cv * V;
   const size_t tab = (size_t)(labels ? labels[r0 / g.hw] : 0) * g.c + ch;
   float c1[V], c2[V], c3[V], mean[V], cb[V];
-  const bool from_x = offset != nullptr && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU);   // see bn_bwd_partial_kernel
+  constexpr bool from_x = FROM_X;   // see bn_bwd_partial_kernel
 #pragma unroll
   for (int k = 0; k < V; k++) {
     const float istd = save[g.c + ch + k];
@@ -576,7 +578,8 @@ static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, i
   RCGAN_CHECK_ARG(ws && ws_bytes >= ((size_t)2 * g.nchunk * c + 2 * c) * sizeof(float), "bn_bwd: workspace too small");
   dim3 grid(g.gx, g.nchunk);
   size_t shb = (size_t)2 * 256 * g.V * sizeof(float);
-  BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(bn_bwd_partial_kernel<TX, TY, VV>, grid, 256, shb, st, (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws, scale, offset, labels));
+  const bool from_x = offset != nullptr && (act == RCGAN_ACT_RELU || act == RCGAN_ACT_LRELU);
+  BN_DISPATCH(xdtype, ydtype, g.V, launch_pdl(from_x ? bn_bwd_partial_kernel<TX, TY, VV, true> : bn_bwd_partial_kernel<TX, TY, VV, false>, grid, 256, shb, st, (const TY*)dy, (const TX*)x, (const TY*)y, g, save, act, leak, (float*)ws, scale, offset, labels));
   RCGAN_LAUNCH_CHECK("bn_bwd_partial");
   launch_pdl(bn_bwd_finalize_kernel, ceil_div(c, 8), 256, 0, st, g, (float*)ws, scale, labels, n_labels, dscale, doffset,
                                                             accumulate_param);
@@ -584,7 +587,7 @@ static int bn_bwd_impl(const void* dy, const void* x, const void* y, void* dx, i
   const float* AB = (const float*)ws + (size_t)2 * g.nchunk * c;
   Geo ga = make_geo(samples, hw, c, labels != nullptr, xdtype == RCGAN_BF16 ? 8 : 4);
   ga.ldy = ldy;
-  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
+  BN_DISPATCH(xdtype, ydtype, ga.V, launch_pdl(from_x ? bn_bwd_dx_kernel<TX, TY, VV, true> : bn_bwd_dx_kernel<TX, TY, VV, false>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy, (const TX*)x, (const TY*)y, (TY*)dx, ga, scale, labels, save, AB, act,
                                         leak, accumulate_dx, offset));
   RCGAN_LAUNCH_CHECK("bn_bwd_dx");
   return 0;
@@ -620,7 +623,7 @@ extern "C" int rcgan_bn_infer_bwd(const void* dy, const void* y, int ldy, void* 
   if (e != cudaSuccess) { rcgan_set_error("bn_infer_bwd: memset failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
   Geo ga = make_geo(samples, hw, c, labels != nullptr, dtype == RCGAN_BF16 ? 8 : 4);
   ga.ldy = ldy;
-  BN_DISPATCH(dtype, dtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy,
+  BN_DISPATCH(dtype, dtype, ga.V, launch_pdl(bn_bwd_dx_kernel<TX, TY, VV, false>, dim3(ga.gx, ga.nchunk), 256, 0, st, (const TY*)dy,
                                              (const TX*)dy, (const TY*)y, (TY*)dx, ga, scale, labels, save, (const float*)ws, act,
                                              leak, accumulate_dx, (const float*)nullptr));
   RCGAN_LAUNCH_CHECK("bn_infer_bwd");

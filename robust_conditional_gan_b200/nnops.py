@@ -17,6 +17,7 @@ FUSE_ACT_BWD = os.environ.get('RCGAN_FUSE_ACT_BWD', '0') == '1'
 ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
 FUSE_RELU_OUT = os.environ.get('RCGAN_FUSE_RELU_OUT', '1') == '1'
 FUSE_BN_STATS = os.environ.get('RCGAN_FUSE_BN_STATS', '1') == '1'
+BN_MASK_FROM_X = os.environ.get('RCGAN_BN_MASK_FROM_X', '0') == '1'
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -522,6 +523,12 @@ class BatchNormOp(Op):
             # parameter gradients only: with a concat output dx cannot alias y.grad (different row stride)
             self.dx_dummy = torch.zeros(self.x.data.numel(), dtype=self.y.data.dtype, device=prog.device)
 
+    def _mask_offset(self):
+        """rcgan_bn_bwd can re-derive the relu mask from x (offset given) instead of reading y back: 5 instead of 7 tensor passes,
+        but measured SLOWER on B200 (tools/bn_bench.py, 512x32x32x256: 444 vs 412 us -- these kernels are issue-bound, not
+        bandwidth-bound, and the extra FMA costs more than the extra load): opt-in RCGAN_BN_MASK_FROM_X=1"""
+        return dp(self.offset) if BN_MASK_FROM_X else None
+
     def _lab(self, g):
         """labels of sample range g (int32 [n])"""
         return None if self.labels is None else dp(self.labels) + 4 * g * self.samples
@@ -574,7 +581,7 @@ class BatchNormOp(Op):
             dxp, accx = (gp(self.x), self.acc_x) if nx else (self.dx_dummy.data_ptr(), 0)
             call('rcgan_bn_bwd_cat', gp(self.y), dp(self.x), dp(self.y), self.y.ld, dxp, self.samples, self.hw, self.c, self.x.dtype,
                  self.y.dtype, dp(self.scale), dp(self.labels), self.n_labels, self.save[0].data_ptr(), self.act, self.leak, dsc, dof,
-                 accx, accp, prog.ws.ptr(), prog.ws.bytes, dp(self.offset), stream_ptr())
+                 accx, accp, prog.ws.ptr(), prog.ws.bytes, self._mask_offset(), stream_ptr())
             return
         xs, ys, gs = self.x.data.element_size(), self.y.data.element_size(), self.y.grad.element_size()
         for g in range(self.groups):
@@ -586,7 +593,7 @@ class BatchNormOp(Op):
             call('rcgan_bn_bwd', self._off(gp(self.y), g, gs), self._off(dp(self.x), g, xs), self._off(dp(self.y), g, ys), dxp,
                  self.samples, self.hw, self.c, self.x.dtype, self.y.dtype, dp(self.scale), self._lab(g), self.n_labels,
                  self.save[g].data_ptr(), self.act, self.leak, dsc, dof, accx, accp if g == 0 else 1, prog.ws.ptr(),
-                 prog.ws.bytes, dp(self.offset), stream_ptr())
+                 prog.ws.bytes, self._mask_offset(), stream_ptr())
 
 
 class ActOp(Op):

@@ -19,7 +19,10 @@ def main():
     dev = torch.device('cuda:0')
     st = torch.cuda.current_stream().cuda_stream
     lib = _C.load()
-    for (n, hw, c, nl) in SHAPES:
+    only = os.environ.get('BN_BENCH_ONLY')
+    for si, (n, hw, c, nl) in enumerate(SHAPES):
+        if only is not None and int(only) != si:
+            continue
         x = torch.randn(n * hw, c, device=dev).bfloat16()
         y = torch.empty_like(x)
         dy = torch.randn(n * hw, c, device=dev).bfloat16()
@@ -41,12 +44,17 @@ def main():
                 _C.call('rcgan_bn_fwd', x.data_ptr(), y.data_ptr(), n, hw, c, _C.BF16, _C.BF16, scale.data_ptr(), offset.data_ptr(), lp,
                         1e-5, _C.ACT_RELU, 0.0, 1, 0.9, mm.data_ptr(), mv.data_ptr(), save.data_ptr(), ws.data_ptr(), wsb, st)
 
-            def bwd():
-                _C.call('rcgan_bn_bwd', dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), n, hw, c, _C.BF16, _C.BF16,
+            def bwd():          # relu mask re-derived from x (5 tensor passes)
+                _C.call('rcgan_bn_bwd', dy.data_ptr(), x.data_ptr(), None, dx.data_ptr(), n, hw, c, _C.BF16, _C.BF16,
                         scale.data_ptr(), lp, L, save.data_ptr(), _C.ACT_RELU, 0.0, dscale.data_ptr(), doffset.data_ptr(), 0, 0,
                         ws.data_ptr(), wsb, offset.data_ptr(), st)
+
+            def bwd_y():        # relu mask read back from y (7 tensor passes)
+                _C.call('rcgan_bn_bwd', dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), n, hw, c, _C.BF16, _C.BF16,
+                        scale.data_ptr(), lp, L, save.data_ptr(), _C.ACT_RELU, 0.0, dscale.data_ptr(), doffset.data_ptr(), 0, 0,
+                        ws.data_ptr(), wsb, None, st)
             res = []
-            for fn in (fwd, bwd):
+            for fn in (fwd, bwd, bwd_y):
                 fn()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -57,7 +65,8 @@ def main():
                 res.append(e0.elapsed_time(e1) / 20 * 1e3)
             nbytes = n * hw * c * 2
             print(f'{(n, hw, c, nl)} statsV={v} fwd {res[0]:7.1f} us ({3 * nbytes / res[0] / 1e6:5.2f} TB/s of 3 passes)  '
-                  f'bwd {res[1]:7.1f} us ({7 * nbytes / res[1] / 1e6:5.2f} TB/s of 7 passes)', flush=True)
+                  f'bwd(mask from x) {res[1]:7.1f} us ({5 * nbytes / res[1] / 1e6:5.2f} TB/s of 5 passes)  '
+                  f'bwd(mask from y) {res[2]:7.1f} us ({7 * nbytes / res[2] / 1e6:5.2f} TB/s of 7 passes)', flush=True)
 
 
 if __name__ == '__main__':
