@@ -231,7 +231,7 @@ def op_profile(model, reps=5):
                 for _ in range(reps):
                     flush.zero_()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(); fn(prog); e1.record(); e1.synchronize()
+                    e0.record(); fn(prog); prog.join(); e1.record(); e1.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 ms = sorted(ts)[len(ts) // 2]
                 flops = 0

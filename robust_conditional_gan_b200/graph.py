@@ -18,6 +18,7 @@ import torch
 from . import _C
 from ._C import ConvDesc, call, ptr, stream_ptr
 
+SIDE_STREAM = __import__('os').environ.get('RCGAN_SIDE_STREAM', '1') == '1'   # A/B switch of Program.fork
 I32 = 100   # host-side dtype tag for integer label tensors (never passed to the library as an activation dtype)
 U8 = 101    # raw image bytes (CIFAR pixels)
 TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16, I32: torch.int32, U8: torch.uint8}
@@ -261,6 +262,7 @@ class Program:
         self._pack_args_own = None
         self._update_args = None
         self.after_backward = {}    # op index -> [callable]; index len(ops) = before the sweep starts
+        self._side, self._forked = None, False
         self.finalized = False
 
     def __enter__(self):
@@ -329,6 +331,27 @@ class Program:
         n, descs, ws, packs = self._pack_args if refresh_foreign else self._pack_args_own
         if n:
             call('rcgan_conv_wpack_batched', n, descs, ws, packs, stream_ptr())
+
+    def fork(self, fn):
+        """Run fn() -- launches that only READ what the current stream has produced so far and whose results nobody needs before
+        the optimizer -- on a side stream, concurrently with what the caller enqueues next (a bias gradient's column sums next to
+        the same layer's dgrad / wgrad: bandwidth-bound work in the shadow of tensor-bound work).  join() before anything may
+        overwrite what fn reads.  Captured into the step's CUDA graph as a fork / join."""
+        if not SIDE_STREAM:
+            fn()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        cur_s = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur_s)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._forked = True
+
+    def join(self):
+        if self._forked:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._forked = False
 
     def loss_slot(self, name):
         self.loss_names.append(name)
@@ -411,6 +434,7 @@ class Program:
             h()
         for op in reversed(self.ops):
             op.backward(self)
+            self.join()             # (ops that fork join themselves; this is the safety net before the hooks / the next op)
             for h in hooks.get(op.index, ()):
                 h()
 

@@ -357,6 +357,10 @@ class ConvOp(Op):
                 bias_done = True
             else:
                 call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        if nb and self.b is not None and not bias_done and torch.cuda.is_available():
+            # the bias gradient's column sums only read dL/dy: on the side stream, next to this layer's dgrad / wgrad
+            prog.fork(lambda: call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, stream_ptr()))
+            bias_done = True
         if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
@@ -459,6 +463,9 @@ class DeconvOp(Op):
                 bias_done = True
             else:
                 call('rcgan_act_bwd', dy, dp(y), dy, y.rows, y.c, y.ld, y.ld, y.ld, y.dtype, self.act, self.leak, 0, st)
+        if nb and self.b is not None and not bias_done:
+            prog.fork(lambda: call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, stream_ptr()))
+            bias_done = True
         d, dyin = self.desc, dy
         if self.patch is not None and (nx or nw):
             call('rcgan_im2col', self.desc, dy, dp(self.patch), self.patch.ld, st)
