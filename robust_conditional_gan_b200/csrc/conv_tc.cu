@@ -1324,6 +1324,15 @@ int run_tc(TcParams& p, const bf16* wbase, int kpad, int rows, int taps, int cha
   { const char* e = getenv("RCGAN_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap map, amap;
   const bool im2col = make_amap(&amap, p, channels, nimg);
+  if (!im2col && im2col_enabled()) {
+    // the cp.async gather is ~2x slower than the TMA im2col operand path: never take it silently (first occurrence per process)
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "rcgan_b200: conv %dx%d source, ld %d, %d rows: im2col tensor map not encodable -> cp.async gather path "
+                      "(about half the throughput); further occurrences are not reported\n", p.SH, p.SW, p.ld_src, p.M);
+    }
+  }
   // persistent big-tile kernel when it has at least ~3 tiles per SM to pipeline; below that the one-tile-per-CTA kernel
   // with two resident CTAs per SM fills the machine better
   const int pm = persist_mode();
