@@ -305,3 +305,50 @@ def test_bf16_error_is_the_storage_quantisation_gap(lib, alg):
     _calibrated(model.gen_params + model.c_params, lambda v: v.grad, tr.last['g_grads'], tr_e.last['g_grads'], alg + ' G')
 
 
+
+
+def test_bf16_storage_gap_at_a_trained_state(lib):
+    """The same calibrated comparison after 40 training iterations of the product itself (bf16, captured graphs): weights,
+    spectral-norm vectors and conditional-BN tables are no longer at their symmetric initial values, the hinge losses are partly
+    saturated.  The product's state is handed to the oracle (TF variable names) and ONE further D step and G step are compared."""
+    from oracle import nn as O
+    n = 4
+    flags = default_flags(algorithm='rcgan-u', alpha=0.5, perm_classifier=True, perm_multiplier=2.0, confuse_init=True, lr=2e-4)
+    ocfg = OC.default_config(algorithm='rcgan-u', alpha=0.5, perm_classifier=True, perm_multiplier=2.0, confuse_init=True, dim=128)
+    model = RCGANCifar(flags, tower_batch=n, precision='bf16', dim=128, use_cuda_graph=True)
+    model.store.load_state_dict(OC.init_params(ocfg, seed=1, dtype=torch.float64))
+    rs = np.random.RandomState(0)
+    for it in range(40):
+        bt = OC.synthetic_batch(n, seed=100 + it, dtype=torch.float32)
+        d = dict(all_real_data_int=bt['raw'], all_real_labels=bt['labels'], all_random_labels=bt['labels_random'],
+                 all_labels_biased=bt['labels_biased'], all_labels_inv_weights=bt['inv_weights'], noise=bt['noise'],
+                 dequant_noise=torch.as_tensor(rs.rand(n, 3072) / 128, dtype=torch.float32))
+        g = dict(noise=bt['noise_G'], all_random_labels_G=bt['labels_random_G'], all_labels_biased_G=bt['labels_biased_G'])
+        out = model.train_iteration(d, g)
+    assert all(np.isfinite(v) for v in out.values()), out
+    model.use_cuda_graph = False
+    P = {k: v.double().cpu() for k, v in model.store.state_dict().items()}
+    moved = max(float((P[k] - v).abs().max()) for k, v in OC.init_params(ocfg, seed=1, dtype=torch.float64).items() if k.endswith('Filters'))
+    assert moved > 1e-3                                              # it did train (Adam: ~lr per step per weight)
+    b = OC.synthetic_batch(n, seed=3, dtype=torch.float64)
+    tr = OC.Trainer({k: v.clone() for k, v in P.items()}, ocfg)
+    tr_e = OC.Trainer({k: v.clone() for k, v in P.items()}, ocfg)
+    feed_d(model, b); feed_g(model, b)
+    tr.d_step(b, 41)
+    with O.bf16_storage():
+        tr_e.d_step(b, 41)
+    model.d_step(41)
+    torch.cuda.synchronize()
+    got = model.d_prog.loss_dict(model.d_prog.losses.cpu())
+    assert abs(got['disc_real_l'] + got['disc_fake_l'] - float(tr_e.last['d']['disc_wgan'])) < 2e-3
+    _calibrated(model.disc_params, lambda v: v.grad, tr.last['d_grads'], tr_e.last['d_grads'], 'trained D')
+    model.store.load_state_dict({k: v.detach() for k, v in tr.P.items()})
+    tr_e.P = {k: v.detach().clone() for k, v in tr.P.items()}
+    tr.g_step(b, 41)
+    with O.bf16_storage():
+        tr_e.g_step(b, 41)
+    model.g_step(41)
+    torch.cuda.synchronize()
+    got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
+    assert abs(got['gen_wgan'] - float(tr_e.last['g']['gen_wgan'])) < 3e-3
+    _calibrated(model.gen_params + model.c_params, lambda v: v.grad, tr.last['g_grads'], tr_e.last['g_grads'], 'trained G')

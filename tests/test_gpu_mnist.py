@@ -352,3 +352,58 @@ def test_bf16_error_is_the_storage_quantisation_gap(lib, run):
     got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
     assert abs(got['g_loss'] - float(tr_e.last['g']['g_loss'])) < 2e-3
     calibrated(model.g_vars + model.c_vars, 'g_grads', run + ' G')
+
+
+def test_bf16_storage_gap_at_a_trained_state(lib):
+    """As test_bf16_error_is_the_storage_quantisation_gap, but after 30 training iterations of the product (RCGAN-U, bf16, captured
+    graphs): batch-norm tables, spectral-norm vectors, moving statistics and the learned confusion matrix have moved; the product's
+    state goes to the oracle by TF variable name and one further D step / G step is compared against the plain and the
+    storage-emulating oracle."""
+    from oracle import nn as O
+    B = 32
+    model, tr0, batch0 = build('rcganu', B, 'bf16', use_graph=True)
+    C = OS.one_coin_confusion(0.5)
+    for it in range(30):
+        bt = OM.synthetic_batch(B, seed=50 + it, dtype=torch.float32, C=C, cfg=tr0.cfg)
+        out = model.train_iteration(batch_images=bt['x'], batch_z=bt['z'], batch_labels_real=bt['y_real'], batch_labels_gen=bt['y_gen'],
+                                    batch_labels_fake=bt['y_fake'], batch_labels_real_weights=bt['y_real_weights'])
+    assert all(np.isfinite(v) for v in out.values()), out
+    model.use_cuda_graph = False
+    P = {k: v.double().cpu() for k, v in model.store.state_dict().items()}
+    assert float((P['confusion_logits'] - tr0.P['confusion_logits']).abs().max()) > 1e-3       # the confusion matrix is being learned
+    f32 = lambda d: {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+    tr = OM.Trainer({k: v.clone() for k, v in P.items()}, tr0.cfg, C)
+    tr_e = OM.Trainer(f32({k: v.clone() for k, v in P.items()}), tr0.cfg, C)
+    batch, batch_e = batch0, f32(batch0)
+    feed(model, batch)
+
+    def calibrated(vars_, key, label):
+        ratios = []
+        for v in vars_:
+            a, e = tr.last[key][v.name], tr_e.last[key][v.name]
+            if float(a.norm()) < 1e-9:
+                continue
+            g = v.grad.reshape(a.shape)
+            pa, ea = relerr(g, a), relerr(e, a)
+            ratios.append((pa + 1e-3) / (ea + 1e-3))
+            assert pa <= (2.0 if a.numel() >= 4096 else 4.0) * ea + 2e-3, (label, v.name, pa, ea)
+        assert sum(ratios) / len(ratios) < 1.5, (label, sum(ratios) / len(ratios))
+    tr.d_step(batch)
+    with O.bf16_storage():
+        tr_e.d_step(batch_e)
+    model.d_step()
+    torch.cuda.synchronize()
+    got = model.d_prog.loss_dict(model.d_prog.losses.cpu())
+    for k in ('d_loss_real', 'd_loss_fake'):
+        assert abs(got[k] - float(tr_e.last['d'][k])) < 3e-3, (k, got[k], tr_e.last['d'][k])
+    calibrated(model.d_vars, 'd_grads', 'trained D')
+    model.store.load_state_dict({k: v.detach() for k, v in tr.P.items()})
+    tr_e.P = f32({k: v.detach().clone() for k, v in tr.P.items()})
+    tr.g_step(batch)
+    with O.bf16_storage():
+        tr_e.g_step(batch_e)
+    model.g_step()
+    torch.cuda.synchronize()
+    got = model.g_prog.loss_dict(model.g_prog.losses.cpu())
+    assert abs(got['g_loss'] - float(tr_e.last['g']['g_loss'])) < 3e-3
+    calibrated(model.g_vars + model.c_vars, 'g_grads', 'trained G')
