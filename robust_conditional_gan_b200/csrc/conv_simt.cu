@@ -513,48 +513,61 @@ int wgrad_splits(const ConvP& p) {
 // Skinny linear layers (4 < N <= 16 outputs, e.g. the MNIST classifier 784 -> 10 at batch 1024, mnist/model.py:759-768):
 // a 256x16 tile grid would be 4 blocks.  One warp per row instead: lanes stride over K against the smem-resident
 // weights (row pitch 17 floats: conflict-free), 16 register accumulators, shuffle reduction, lane j writes output j.
+// K is walked in chunks of SKINNY_KC rows of the weight matrix staged in shared memory (the CIFAR permutation classifier is
+// 3072 -> 10, gan_resnet.py:458-466: its 209 KB of padded weights do not fit at once, and the generic 256x16 tile kernel ran it
+// on ONE or TWO blocks: 433 us per call, 2.6 ms per RCGAN-U iteration).  A block owns 8 rows (one per warp) per pass.
+constexpr int SKINNY_KC = 1024;
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) linear_skinny_kernel(ConvP p, const T* __restrict__ x, const float* __restrict__ wt,
                                                             TO* __restrict__ out) {
   pdl_sync();   // programmatic dependent launch: nothing of the previous kernel is touched before this
-  extern __shared__ float wsk[];   // [K][17]
-  for (int i = threadIdx.x; i < p.K * 16; i += 256) {
-    const int k = i >> 4, j = i & 15;
-    wsk[k * 17 + j] = j < p.N ? wt[(size_t)k * p.N + j] : 0.f;
-  }
-  __syncthreads();
+  extern __shared__ float wsk[];   // [min(K, SKINNY_KC)][17]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int m = blockIdx.x * 8 + warp; m < p.M; m += gridDim.x * 8) {
+  for (int m0 = blockIdx.x * 8; m0 < p.M; m0 += gridDim.x * 8) {
+    const int m = m0 + warp;
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) acc[j] = 0.f;
-    const T* xr = x + (size_t)m * p.ldx;
-    for (int k = lane; k < p.K; k += 32) {
-      const float xv = to_f(xr[k]);
-      const float* wr = wsk + k * 17;
+    for (int k0 = 0; k0 < p.K; k0 += SKINNY_KC) {
+      const int kc = min(SKINNY_KC, p.K - k0);
+      __syncthreads();           // the previous chunk (or pass) is consumed
+      for (int i = threadIdx.x; i < kc * 16; i += 256) {
+        const int k = i >> 4, j = i & 15;
+        wsk[k * 17 + j] = j < p.N ? wt[(size_t)(k0 + k) * p.N + j] : 0.f;
+      }
+      __syncthreads();
+      if (m < p.M) {
+        const T* xr = x + (size_t)m * p.ldx + k0;
+        for (int k = lane; k < kc; k += 32) {
+          const float xv = to_f(xr[k]);
+          const float* wr = wsk + k * 17;
 #pragma unroll
-      for (int j = 0; j < 16; j++) acc[j] = fmaf(xv, wr[j], acc[j]);
+          for (int j = 0; j < 16; j++) acc[j] = fmaf(xv, wr[j], acc[j]);
+        }
+      }
     }
-    float v = 0.f;
+    if (m < p.M) {
+      float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const float sj = warp_sum(acc[j]);
-      if (lane == j) v = sj;
-    }
-    if (lane < p.N) {
-      if (p.bias) v += p.bias[lane];
-      out[(size_t)m * p.ldy + lane] = from_f<TO>(act_fwd(v, p.act, p.leak));
+      for (int j = 0; j < 16; j++) {
+        const float sj = warp_sum(acc[j]);
+        if (lane == j) v = sj;
+      }
+      if (lane < p.N) {
+        if (p.bias) v += p.bias[lane];
+        out[(size_t)m * p.ldy + lane] = from_f<TO>(act_fwd(v, p.act, p.leak));
+      }
     }
   }
 }
 
 template <typename T, typename TO>
 bool launch_skinny(const ConvP& p, const void* x, const float* w, void* out, cudaStream_t st) {
-  const size_t shb = (size_t)p.K * 17 * sizeof(float);
-  if (p.kh != 1 || p.kw != 1 || p.stride != 1 || p.N <= 4 || p.N > 16 || p.M < 256 || shb > 96 * 1024) return false;
+  const size_t shb = (size_t)(p.K < SKINNY_KC ? p.K : SKINNY_KC) * 17 * sizeof(float);
+  if (p.kh != 1 || p.kw != 1 || p.stride != 1 || p.N <= 4 || p.N > 16 || p.M < 256) return false;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(linear_skinny_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(linear_skinny_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_KC * 17 * (int)sizeof(float));
     attr_done = true;
   }
   int grid = ceil_div(p.M, 8);

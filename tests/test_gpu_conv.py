@@ -27,6 +27,8 @@ SHAPES = [
     (33, 1, 1, 64, 1, 1, 1, 0, 0),       # d_h4_lin
     (300, 1, 1, 784, 10, 1, 1, 0, 0),    # classifier at a batch that takes the warp-per-row skinny kernel
     (257, 1, 1, 100, 16, 1, 1, 4, 0),    # skinny kernel, N = 16, padded rows
+    (512, 1, 1, 3072, 10, 1, 1, 0, 0),   # CIFAR permutation classifier (gan_resnet.py:458-466): skinny kernel, 3 chunks of K
+    (259, 1, 1, 2100, 12, 1, 1, 4, 0),   # skinny kernel, ragged last K chunk, ragged last row group
 ]
 
 
