@@ -165,6 +165,81 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a 2-cluster on one TPC run ONE M = 256 UMMA; each stages its own 128 A rows and its
+// own half of the B (weight) columns, the tensor cores of both SMs read both halves.  Per SM that is 4 KB (A) + N/2 x 32 B (B)
+// of shared-memory operand reads per K = 16 step instead of 4 KB + N x 32 B, and half the weight bytes through TMA.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier of THIS CTA that threads of the peer CTA arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (it > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once all prior MMAs of this thread retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// TMA loads of a CTA pair: the transaction bytes are counted on the LEADER's (rank 0) barrier -- the peer bit (bit 24) of the
+// shared::cluster barrier address is cleared, as CUTLASS's SM100_TMA_2SM_LOAD does
+constexpr uint32_t PAIR_PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & PAIR_PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                        unsigned short off_w, unsigned short off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar & PAIR_PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 template <int BN, int ST> struct Cfg {
   static constexpr int STAGES = ST;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -180,7 +255,7 @@ template <int BN, int ST> struct Cfg {
 template <int BN, int AVAIL, typename TO, int U = 4>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, uint32_t tmem_base, int warp, int lane, int m0,
                                             int n0, uint32_t tempty_bar = 0, int bn_lim = BN, float* st_acc = nullptr,
-                                            int* st_cnt = nullptr) {
+                                            int* st_cnt = nullptr, bool tempty_cluster = false) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   constexpr int PITCH = BN * (int)sizeof(TO) + 16;
   static_assert(4 * 32 * PITCH + 2048 <= AVAIL, "staging must fit the drained pipeline buffers");
@@ -261,7 +336,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, uint8_t* smem, ui
   if (tempty_bar) {
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty_bar);
+    if (lane == 0) {
+      if (tempty_cluster) mbar_arrive_cluster(tempty_bar);     // CTA pair: the leader's barrier, a shared::cluster address
+      else mbar_arrive(tempty_bar);
+    }
   }
   __syncwarp();
   if (p.dbg & 16) return;
@@ -785,6 +863,209 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair persistent kernel
+// The persistent kernel above with cta_group::2: a cluster of two CTAs (one TPC) owns a (2 x MT x 128) x bn tile.  CTA r of the pair
+// stages rows [m0 + r*MT*128, +MT*128) of A and columns [n0 + r*bn/2, +bn/2) of B; the leader's (rank 0) elected thread issues
+// M = 256 UMMAs that read both CTAs' shared memory and write 128 accumulator lanes into each CTA's TMEM; every CTA drains its own
+// lanes with the same epilogue as above.  Barriers: full[s] lives on the leader (both CTAs' TMA bytes are counted there), the
+// commit that frees a stage / publishes an accumulator is multicast to both CTAs, tempty[a] lives on the leader and collects
+// the 8 epilogue warps of the pair.
+template <int BN, int MT, int ST, typename TO>
+struct PairCfg {
+  static constexpr int A_BYTES = MT * BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the weight tile
+  static constexpr int PITCH = BN * (int)sizeof(TO) + 16;
+  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 2048;
+  static constexpr int SMEM = ST * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM <= 227 * 1024, "pair conv tile does not fit shared memory");
+  static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
+};
+
+template <int BN, int MT, int ST, typename TO, bool MULTI>
+__global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_constant__ TcMulti mp,
+                                                              const __grid_constant__ CUtensorMap wmap,
+                                                              const __grid_constant__ TcMaps amaps) {
+  using C = PairCfg<BN, MT, ST, TO>;
+  constexpr int TM = MT * BM;          // rows per CTA; the pair's tile has 2 * TM
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic shared window starts at the same offset in both CTAs of the pair, so every carved address below is the same
+  // shared::cta offset in both (the UMMA descriptors, the multicast commits and tcgen05.alloc rely on that)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + ST * C::A_BYTES;
+  uint8_t* epi = smB + ST * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::EPI_BYTES);
+  uint64_t* full = bars;               // [ST] leader: 1 arrival (expect_tx) + both CTAs' TMA bytes
+  uint64_t* empty = bars + ST;         // [ST] each CTA: 1 arrival (multicast tcgen05.commit)
+  uint64_t* tfull = bars + 2 * ST;     // [2]  each CTA: accumulator ready (multicast tcgen05.commit)
+  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  leader: accumulator drained (4 epilogue warps of each CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const TcParams& p0 = mp.p[0];
+  const int bn = p0.bn_eff;                              // N-tile width: multiple of 32, <= BN
+  const int n_tiles_n = (p0.N + bn - 1) / bn;
+  const int n_tiles = mp.tile_start[mp.nprob];
+  auto locate = [&](int tile, int& q) {
+    q = 0;
+    if (!MULTI) return tile;
+    while (q + 1 < mp.nprob && tile >= mp.tile_start[q + 1]) q++;
+    return tile - mp.tile_start[q];
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; s++) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(smem_u32(&tfull[a]), 1);
+      mbar_init(smem_u32(&tempty[a]), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 2 * MT * BN);   // the same warp of both CTAs, same destination offset
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+      for (int q = 0; q < mp.nprob; q++) asm volatile("prefetch.tensormap [%0];" ::"l"(&amaps.a[q]) : "memory");
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();      // the peer's barriers are initialised before anything (TMA bytes, commits, arrives) can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp < 4) {
+    // =========================================================== epilogue warps (both CTAs, own 128 x MT rows)
+    int ti = 0;
+    float st_acc[16];
+    int st_cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) st_acc[j] = 0.f;
+    const bool stats = sizeof(TO) == 2 && p0.colstats != nullptr;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0), tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
+    for (int tile = pair; tile < n_tiles; tile += npairs, ti++) {
+      const int a = ti & 1;
+      int q;
+      const int lt = locate(tile, q);
+      const TcParams& p = mp.p[q];
+      const int m0 = (lt / n_tiles_n) * (2 * TM) + (int)rank * TM, n0 = (lt % n_tiles_n) * bn;
+      mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < MT; j++)
+        tc_epilogue<BN, C::EPI_BYTES, TO, 4>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
+                                             j == MT - 1 ? (a ? tempty_leader1 : tempty_leader0) : 0u, bn, stats ? st_acc : nullptr, &st_cnt, true);
+    }
+    if (stats) {
+      float* S = reinterpret_cast<float*>(epi);
+      int* Cn = reinterpret_cast<int*>(S + 2 * BN);
+      const int tid = warp * 32 + lane, lpr = bn / 8;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = tid; i < 2 * BN + 1; i += 128) S[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int col0 = (lane % lpr) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { atomicAdd(&S[col0 + j], st_acc[j]); atomicAdd(&S[BN + col0 + j], st_acc[8 + j]); }
+      atomicAdd(Cn, st_cnt);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p0.colstats + (size_t)blockIdx.x * 2 * p0.N;
+      for (int i = tid; i < p0.N; i += 128) { dst[i] = S[i]; dst[p0.N + i] = S[BN + i]; }
+      float* counts = p0.colstats + (size_t)RCGAN_NUM_SMS * 2 * p0.N;
+      if (tid == 0) {
+        counts[blockIdx.x] = (float)(*Cn / lpr);
+        for (int j = blockIdx.x + gridDim.x; j < RCGAN_NUM_SMS; j += gridDim.x) counts[j] = 0.f;
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================================================== TMA producer (both CTAs: own A rows, own half of B)
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int hb = bn >> 1;
+      for (int tile = pair; tile < n_tiles; tile += npairs) {
+        int q;
+        const int lt = locate(tile, q);
+        const TcParams& p = mp.p[q];
+        const CUtensorMap* amap = &amaps.a[q];
+        const int nkb = p.ntaps * p.kb_per_tap;
+        const int mpair = (lt / n_tiles_n) * (2 * TM), n0 = (lt % n_tiles_n) * bn;
+        const int m0 = mpair + (int)rank * TM;
+        int im_w[MT], im_h[MT], im_n[MT];
+        int nsub = 0, nsub_pair = 0;         // sub-tiles with rows < M: of this CTA, of both CTAs
+#pragma unroll
+        for (int j = 0; j < MT; j++) {
+          const int mj = m0 + j * BM;
+          if (mj < p.M) nsub = j + 1;
+          const int mb = mj % p.MW, mr = mj / p.MW;
+          im_w[j] = p.im_w_lo + mb * p.im_sw; im_h[j] = p.im_h_lo + (mr % p.MH) * p.im_sh; im_n[j] = mr / p.MH;
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * MT; j++)
+          if (mpair + j * BM < p.M) nsub_pair++;
+        const uint32_t tx = (uint32_t)(bn * BK * 2 + nsub_pair * (BM * BK * 2));
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % ST;
+          mbar_wait(smem_u32(&empty[s]), ((it / ST) & 1) ^ 1);
+          const int tap = kb / p.kb_per_tap;
+          const int k0 = (kb - tap * p.kb_per_tap) * BK;
+          if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full[s]), tx);
+#pragma unroll
+          for (int j = 0; j < MT; j++)
+            if (j < nsub)
+              tma_load_im2col_4d_pair(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)), amap, smem_u32(&full[s]), k0, im_w[j],
+                                      im_h[j], im_n[j], p.toffw[tap], p.toffh[tap]);
+          tma_load_3d_pair(smem_u32(smB + s * C::B_BYTES), &wmap, smem_u32(&full[s]), k0, n0 + (int)rank * hb, p.twi[tap]);
+        }
+      }
+    }
+  } else {
+    // =========================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, bn);
+      uint32_t it = 0;
+      int ti = 0;
+      for (int tile = pair; tile < n_tiles; tile += npairs, ti++) {
+        const int a = ti & 1;
+        int q;
+        locate(tile, q);
+        const TcParams& p = mp.p[q];
+        const int nkb = p.ntaps * p.kb_per_tap;
+        mbar_wait_cluster(smem_u32(&tempty[a]), ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
+        for (int kb = 0; kb < nkb; kb++, it++) {
+          const int s = it % ST;
+          mbar_wait(smem_u32(&full[s]), (it / ST) & 1);
+          tc_fence_after();
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + s * C::B_BYTES));
+#pragma unroll
+          for (int j = 0; j < MT; j++) {
+            const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + s * C::A_BYTES + j * (BM * BK * 2)));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_bf16_pair(tacc + (uint32_t)(j * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(smem_u32(&empty[s]));
+        }
+        umma_commit_pair(smem_u32(&tfull[a]));
+      }
+    }
+  }
+  // neither CTA may leave (or free its TMEM) while the other can still read its shared memory / write its accumulator lanes
+  tc_fence_before();
+  __syncthreads();         // reconverges the single-lane roles before the .aligned cluster barrier
+  cluster_sync_all();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * MT * BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[tap][ci][co] = sum over output pixels m of x[pix(m, tap)][ci] * dy[m][co]: the contraction runs over PIXELS, which
 // is the strided dimension of both NHWC operands, so both tiles are MN-major for the UMMA (a_major = b_major = 1):
@@ -1297,6 +1578,46 @@ int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, 
   return 0;
 }
 
+template <int BN, int MT, int ST, typename TO>
+int launch_tc_pair(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, cudaStream_t st) {
+  using C = PairCfg<BN, MT, ST, TO>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<BN, MT, ST, TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_pair_kernel<BN, MT, ST, TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) { rcgan_set_error("conv_tc_pair: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+    attr_done = true;
+  }
+  const int bn = mp.p[0].bn_eff, n_tiles_n = (mp.p[0].N + bn - 1) / bn;
+  mp.tile_start[0] = 0;
+  for (int q = 0; q < mp.nprob; q++)
+    mp.tile_start[q + 1] = mp.tile_start[q] + ((mp.p[q].M + 2 * MT * BM - 1) / (2 * MT * BM)) * n_tiles_n;
+  const int n_tiles = mp.tile_start[mp.nprob];
+  const int npairs = n_tiles < RCGAN_NUM_SMS / 2 ? n_tiles : RCGAN_NUM_SMS / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = rcgan_pdl_enabled() ? 2 : 1;
+  if (mp.nprob > 1) cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BN, MT, ST, TO, true>, mp, map, amaps);
+  else cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BN, MT, ST, TO, false>, mp, map, amaps);
+  RCGAN_LAUNCH_CHECK("conv_tc_pair");
+  rcgan_set_conv_variant("conv_tc_pair<%d,%d,%d,%s,multi=%d>", BN, MT, ST, sizeof(TO) == 4 ? "f32" : "bf16", mp.nprob > 1 ? 1 : 0);
+  return 0;
+}
+
+// RCGAN_TC_PAIR: 0 = persistent launches stay on the one-CTA (cta_group::1) kernel, 1 (default) = CTA pairs for the 256-wide
+// tiles, 2 = CTA pairs wherever the N tile is a multiple of 32
+int pair_mode() {
+  const char* e = getenv("RCGAN_TC_PAIR");
+  return e ? atoi(e) : 1;
+}
+
 // RCGAN_TC_PERSIST=0 selects the one-tile-per-CTA kernel everywhere (A/B comparisons); =2 forces the persistent kernel
 int persist_mode() {
   const char* e = getenv("RCGAN_TC_PERSIST");
@@ -1313,6 +1634,14 @@ int run_tc_persist(TcMulti& mp, const TcMaps& amaps, const bf16* wbase, int kpad
   long tiles256 = 0;
   for (int q = 0; q < mp.nprob; q++) { mp.p[q].bn_eff = bn_eff; tiles256 += (long)((mp.p[q].M + 255) / 256) * ((p.N + bn_eff - 1) / bn_eff); }
   CUtensorMap map;
+  if (bn_eff % 32 == 0 && (pair_mode() >= 2 || (pair_mode() == 1 && wide))) {
+    // CTA pairs: each CTA loads half of the weight tile's columns
+    if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn_eff / 2)) return e;
+    if (wide) return launch_tc_pair<256, 1, 4, bf16>(mp, map, amaps, st);
+    if (tiles256 >= 2 * RCGAN_NUM_SMS)
+      return p.out_f32 ? launch_tc_pair<128, 2, 3, float>(mp, map, amaps, st) : launch_tc_pair<128, 2, 4, bf16>(mp, map, amaps, st);
+    return p.out_f32 ? launch_tc_pair<128, 1, 5, float>(mp, map, amaps, st) : launch_tc_pair<128, 1, 6, bf16>(mp, map, amaps, st);
+  }
   if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn_eff)) return e;
   if (wide) return launch_tc_persist<256, 1, 3, bf16>(mp, map, amaps, st);
   if (tiles256 >= 2 * RCGAN_NUM_SMS)     // enough work for 256-row tiles (one B tile feeds two MMAs)

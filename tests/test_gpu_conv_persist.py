@@ -18,6 +18,35 @@ pytestmark = pytest.mark.gpu
 TOL_OUT = {_C.BF16: 6e-3, _C.F32: 2e-5}
 NAME = {_C.BF16: 'bf16', _C.F32: 'f32'}
 
+# Every case runs twice: on the CTA-pair kernel (cta_group::2, the default wherever the N tile is a multiple of 32) and, with
+# RCGAN_TC_PAIR=0, on the one-CTA persistent kernel it replaces.  The variant strings in the tables name the one-CTA kernel;
+# expect() maps them to the pair kernel's instantiation (conv_tc.cu run_tc_persist).
+PAIR_OF = {'conv_tc_persist<256,1,3,bf16': 'conv_tc_pair<256,1,4,bf16', 'conv_tc_persist<128,2,3,bf16': 'conv_tc_pair<128,2,4,bf16',
+           'conv_tc_persist<128,2,3,f32': 'conv_tc_pair<128,2,3,f32', 'conv_tc_persist<128,1,5,bf16': 'conv_tc_pair<128,1,6,bf16',
+           'conv_tc_persist<128,1,4,f32': 'conv_tc_pair<128,1,5,f32'}
+
+
+@pytest.fixture(autouse=True, params=['pair', 'solo'])
+def pair(request, monkeypatch):
+    monkeypatch.setenv('RCGAN_TC_PAIR', '1' if request.param == 'pair' else '0')
+    return request.param == 'pair'
+
+
+def expect(variant, ncols, pair, odt=_C.BF16):
+    """the variant string of the kernel that must have run: `variant` itself, or its CTA-pair counterpart"""
+    if variant is None or not pair or not variant.startswith('conv_tc_persist<'):
+        return variant
+    cap = 256 if (ncols > 128 and odt == _C.BF16) else 128
+    bn_eff = cap if ncols >= cap else (ncols + 15) // 16 * 16
+    if bn_eff % 32:
+        return variant
+    head, tail = variant.rsplit(',', 1)
+    return PAIR_OF[head] + ',' + tail
+
+
+def persistent(v):
+    return v.startswith('conv_tc_persist<') or v.startswith('conv_tc_pair<')
+
 
 def make(shape, seed=0, wscale=0.05):
     n, h, w, cin, cout, k, s, px, py = shape
@@ -68,7 +97,7 @@ FPROP = [
 
 
 @pytest.mark.parametrize('shape,odt,variant', FPROP)
-def test_persistent_fprop(lib, shape, odt, variant):
+def test_persistent_fprop(lib, shape, odt, variant, pair):
     d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
     n, cout, s = shape[0], shape[4], shape[6]
     pack, wd = pack_for(lib, d, wt)
@@ -76,7 +105,7 @@ def test_persistent_fprop(lib, shape, odt, variant):
     y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=TD[odt])
     call('rcgan_conv2d_fprop', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y.data_ptr(), odt, _C.ACT_LRELU, 0.2, st())
     torch.cuda.synchronize()
-    assert _C.last_conv_variant() == variant
+    assert _C.last_conv_variant() == expect(variant, cout, pair, odt)
     ref32 = O.lrelu(O.conv2d(x, wt, s) + b)
     check(y[..., :cout].float().cpu(), ref32, lambda i: O.lrelu(O.conv2d(x[i].double(), wt.double(), s) + b.double()), n, TOL_OUT[odt])
     if ldy > cout:
@@ -96,7 +125,7 @@ DGRAD = [
 
 
 @pytest.mark.parametrize('shape,odt,variant', DGRAD)
-def test_persistent_dgrad_and_deconv(lib, shape, odt, variant):
+def test_persistent_dgrad_and_deconv(lib, shape, odt, variant, pair):
     d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
     n, h, w, cin, cout, k, s = shape[:7]
     pack, wd = pack_for(lib, d, wt)
@@ -111,6 +140,7 @@ def test_persistent_dgrad_and_deconv(lib, shape, odt, variant):
     dx = torch.zeros(n, h, w, ldx, device='cuda', dtype=TD[odt])
     call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, dx.data_ptr(), odt, _C.ACT_NONE, 0.0, 0, st())
     torch.cuda.synchronize()
+    variant = expect(variant, cin, pair, odt)
     assert _C.last_conv_variant() == variant
     check(dx[..., :cin].float().cpu(), g32, g64, n, TOL_OUT[odt])
     # accumulate=1: += onto a buffer that already holds a gradient (bf16: one more rounding)
@@ -148,7 +178,7 @@ def test_forced_persistent_small_shapes(lib, shape, monkeypatch):
         y = torch.full((n, ho, wo, ldy), 7.0, device='cuda', dtype=TD[odt])
         call('rcgan_conv2d_fprop', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y.data_ptr(), odt, _C.ACT_LRELU, 0.2, st())
         torch.cuda.synchronize()
-        assert _C.last_conv_variant().startswith('conv_tc_persist<'), _C.last_conv_variant()
+        assert persistent(_C.last_conv_variant()), _C.last_conv_variant()
         assert relerr(y[..., :cout].float(), ref) < TOL_OUT[odt]
         if ldy > cout:
             assert float((y[..., cout:].float() - 7.0).abs().max()) == 0.0
@@ -158,7 +188,7 @@ def test_forced_persistent_small_shapes(lib, shape, monkeypatch):
     for acc in (0, 1):
         call('rcgan_conv2d_dgrad', d, dyd.data_ptr(), wd.data_ptr(), pack.data_ptr(), None, dx.data_ptr(), _C.F32, _C.ACT_NONE, 0.0, acc, st())
         torch.cuda.synchronize()
-        assert _C.last_conv_variant().startswith('conv_tc_persist<'), _C.last_conv_variant()
+        assert persistent(_C.last_conv_variant()), _C.last_conv_variant()
         assert relerr(dx[..., :cin], (1 + acc) * xr.grad) < 2e-5
 
 
@@ -175,7 +205,7 @@ def test_small_shapes_take_the_one_tile_kernel(lib):
 @pytest.mark.parametrize('shape,variant', [((600, 8, 8, 128, 128, 3, 1, 0, 0), 'conv_tc<128,3,im2col=1>'),
                                            ((1800, 8, 8, 128, 128, 3, 1, 0, 0), 'conv_tc_persist<128,2,3,bf16,multi=0>'),
                                            ((64, 32, 32, 256, 256, 3, 1, 0, 0), 'conv_tc_persist<256,1,3,bf16,multi=0>')])
-def test_fused_residual_in_both_kernels(lib, shape, variant):
+def test_fused_residual_in_both_kernels(lib, shape, variant, pair):
     """rcgan_conv2d_fprop_res (ResidualBlock's shortcut add, gan_resnet.py:328) is bit-identical to fprop + rcgan_add in the
     one-tile kernel and in both persistent tile shapes"""
     d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
@@ -187,7 +217,7 @@ def test_fused_residual_in_both_kernels(lib, shape, variant):
     y = torch.zeros(n, ho, wo, cout, device='cuda', dtype=torch.bfloat16)
     call('rcgan_conv2d_fprop_res', d, xd.data_ptr(), wd.data_ptr(), pack.data_ptr(), bd.data_ptr(), resd.data_ptr(), y.data_ptr(), _C.BF16,
          _C.ACT_NONE, 0.0, st())
-    assert _C.last_conv_variant() == variant
+    assert _C.last_conv_variant() == expect(variant, cout, pair)
     ref = O.conv2d(x, wt, shape[6]) + b + res.float()
     assert relerr(y.float().cpu(), ref) < 6e-3
     y2 = torch.zeros_like(y)
@@ -199,7 +229,7 @@ def test_fused_residual_in_both_kernels(lib, shape, variant):
 @pytest.mark.parametrize('n,h,w,cin,cout,variant', [(64, 32, 32, 256, 256, 'conv_tc_persist<256,1,3,bf16,multi=1>'),
                                                     (130, 16, 16, 256, 128, 'conv_tc_persist<128,1,5,bf16,multi=1>'),
                                                     (300, 32, 32, 64, 96, 'conv_tc_persist<128,2,3,bf16,multi=1>')])
-def test_persistent_upsample_conv(lib, n, h, w, cin, cout, variant):
+def test_persistent_upsample_conv(lib, n, h, w, cin, cout, variant, pair):
     """rcgan_upconv2d_fprop at the benchmark's G.Block sizes: 4 parity problems in one persistent launch vs the oracle's
     3x3 conv of the nearest-neighbour upsampled input (gan_resnet.py:259-272)"""
     g = torch.Generator().manual_seed(n + h)
@@ -215,7 +245,7 @@ def test_persistent_upsample_conv(lib, n, h, w, cin, cout, variant):
     y = torch.zeros(n, h, w, cout, device='cuda', dtype=torch.bfloat16)
     call('rcgan_upconv2d_fprop', d, xd.data_ptr(), pack.data_ptr(), bdev.data_ptr(), y.data_ptr(), _C.BF16, _C.ACT_RELU, 0.0, st())
     torch.cuda.synchronize()
-    assert _C.last_conv_variant() == variant
+    assert _C.last_conv_variant() == expect(variant, cout, pair)
     up = xs.float().repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
     ref = torch.relu(O.conv2d(up, wt, 1) + b)
     assert relerr(y.float().cpu(), ref) < 1e-2            # the folded taps are pre-summed in fp32, then rounded to bf16 once more
@@ -256,7 +286,7 @@ EX_SHAPES = [((600, 8, 8, 128, 128, 3, 1, 0, 0), 'conv_tc<128,3,im2col=1>'),
 
 @pytest.mark.parametrize('shape,variant', EX_SHAPES)
 @pytest.mark.parametrize('act', [_C.ACT_RELU, _C.ACT_LRELU])
-def test_dgrad_with_fused_activation_backward(lib, shape, variant, act):
+def test_dgrad_with_fused_activation_backward(lib, shape, variant, act, pair):
     """rcgan_conv2d_dgrad_ex(mask): dx (=|+=) act'(mask) * dgrad -- bit-identical to rcgan_conv2d_dgrad followed by rcgan_act_bwd
     (the `nonlinearity` in front of a conv, gan_resnet.py:318-325, differentiated in the producing dgrad's epilogue)"""
     d, x, wt, b, dy, xd, dyd, (ho, wo, ldx, ldy) = make(shape)
@@ -277,7 +307,7 @@ def test_dgrad_with_fused_activation_backward(lib, shape, variant, act):
         call('rcgan_conv2d_dgrad_ex', d, dyd.data_ptr(), pack.data_ptr(), None, got.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, acc,
              ctypes.byref(ep), st())
         torch.cuda.synchronize()
-        assert variant is None or _C.last_conv_variant() == variant
+        assert variant is None or _C.last_conv_variant() == expect(variant, cin, pair)
         assert torch.equal(got[..., :cin], ref[..., :cin])
     # and against the oracle: relu'(mask) * conv2d gradient
     xr = x.clone().requires_grad_(True)
@@ -290,7 +320,7 @@ def test_dgrad_with_fused_activation_backward(lib, shape, variant, act):
 
 @pytest.mark.parametrize('shape,variant', [s for s in EX_SHAPES if s[0][6] == 1])
 @pytest.mark.parametrize('res_up', [0, 1])
-def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, variant, res_up):
+def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, variant, res_up, pair):
     """rcgan_conv2d_fprop_ex(res, res_up, out2): y = conv + bias + [upsample2](res), out2 = relu(y) -- ResidualBlock's
     `shortcut + output` with UpsampleConv_1x1's shortcut still at the small resolution (gan_resnet.py:259-272, 305-328) and the
     next block's `nonlinearity(inputs)`; bit-identical to fprop, upsample, add, relu as separate kernels"""
@@ -313,7 +343,7 @@ def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, vari
     ep = _C.ConvEpilogue(res=res.data_ptr(), res_up=res_up, ld_res=ldy, out2=y2.data_ptr(), out2_act=_C.ACT_RELU)
     call('rcgan_conv2d_fprop_ex', d, xd.data_ptr(), pack.data_ptr(), bd.data_ptr(), y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, ctypes.byref(ep), st())
     torch.cuda.synchronize()
-    assert variant is None or _C.last_conv_variant() == variant
+    assert variant is None or _C.last_conv_variant() == expect(variant, cout, pair)
     assert torch.equal(y[..., :cout], ref[..., :cout])
     assert torch.equal(y2[..., :cout], torch.relu(ref[..., :cout]))
     if ldy > cout:
@@ -323,7 +353,7 @@ def test_fprop_with_fused_residual_upsampling_and_second_output(lib, shape, vari
 @pytest.mark.parametrize('shape,kind', [((64, 32, 32, 256, 256, 3, 1, 0, 0), 'fprop'), ((5, 16, 16, 128, 128, 3, 1, 0, 0), 'fprop'),
                                         ((300, 8, 8, 64, 64, 3, 1, 0, 0), 'fprop'), ((130, 16, 16, 256, 256, 4, 2, 0, 0), 'deconv'),
                                         ((3, 8, 8, 128, 256, 4, 2, 0, 0), 'deconv')])
-def test_epilogue_column_statistics(lib, shape, kind):
+def test_epilogue_column_statistics(lib, shape, kind, pair):
     """rcgan_conv_epilogue.colstats: per-CTA partial sums / sums of squares / row counts of the STORED bf16 output, merged here on
     the host, equal the moments of the tensor (what the following conditional batch norm needs: normalization.py:38-41);
     rcgan_bn_fwd_prestats on them == rcgan_bn_fwd with its own statistics pass.  The persistent kernel is forced for small shapes."""
@@ -344,7 +374,7 @@ def test_epilogue_column_statistics(lib, shape, kind):
         call('rcgan_conv2d_dgrad_ex', d, dyd.data_ptr(), pack.data_ptr(), keep(dev(bias)), y.data_ptr(), _C.BF16, _C.ACT_NONE, 0.0, 0,
              ctypes.byref(ep), st())
     torch.cuda.synchronize()
-    assert _C.last_conv_variant().startswith('conv_tc_persist<')
+    assert _C.last_conv_variant().startswith('conv_tc_pair<' if pair else 'conv_tc_persist<')
     P = 148
     sums = parts[:P * 2 * N].reshape(P, 2, N).double().cpu()
     counts = parts[P * 2 * N:].double().cpu()

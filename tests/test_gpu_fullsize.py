@@ -75,8 +75,9 @@ def test_mnist_rcganu_b1024_step_matches_oracle(lib):
         assert c > 0.95 and e < 0.35, (v.name, e, c)
     log = _C.conv_variant_log()
     print('variants', sorted(log)); print('worst', sorted(worst, reverse=True)[:6])
-    assert any(v.startswith('conv_tc_persist<128,2,3,bf16,multi=1>') for v in log), log       # g_h2 / d_h1 dgrad: the roofline kernel
-    assert any(v.startswith('conv_tc_persist<') and 'multi=0' in v for v in log), log
+    # g_h2 / d_h1 dgrad, the roofline kernel: the CTA-pair kernel, or the one-CTA persistent kernel under RCGAN_TC_PAIR=0
+    assert any(v.startswith(('conv_tc_pair<128,2,4,bf16,multi=1>', 'conv_tc_persist<128,2,3,bf16,multi=1>')) for v in log), log
+    assert any(v.startswith(('conv_tc_pair<', 'conv_tc_persist<')) and 'multi=0' in v for v in log), log
     assert any(v.startswith('wgrad_tc<') for v in log), log
 
 
@@ -112,6 +113,7 @@ def test_cifar_rcgan_b256_steps_match_oracle(lib):
     glog = _C.conv_variant_log()
     print('D step variants', sorted(dlog)); print('G step variants', sorted(glog))
     for log in (dlog, glog):
-        assert any(v.startswith('conv_tc_persist<256,1,3,bf16') for v in log), log             # the 256-channel generator convs
-        assert any(v.startswith('conv_tc_persist<128,2,3,bf16') for v in log), log             # the 128-channel discriminator convs
+        # the 256-channel generator convs and the 128-channel discriminator convs: CTA-pair kernels (one-CTA under RCGAN_TC_PAIR=0)
+        assert any(v.startswith(('conv_tc_pair<256,1,4,bf16', 'conv_tc_persist<256,1,3,bf16')) for v in log), log
+        assert any(v.startswith(('conv_tc_pair<128,2,4,bf16', 'conv_tc_persist<128,2,3,bf16')) for v in log), log
         assert any(v.startswith('wgrad_tc<128') for v in log), log

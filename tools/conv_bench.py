@@ -62,6 +62,7 @@ def main():
         for var in variants:
             os.environ['RCGAN_TC_PERSIST'] = var.split(':')[0]
             os.environ['RCGAN_TC_DBG'] = var.split(':')[1] if ':' in var else '0'
+            os.environ['RCGAN_TC_PAIR'] = var.split(':')[2] if var.count(':') >= 2 else '1'      # PERSIST:DBG:PAIR
             ts = []
             for it in range(6):
                 flush.zero_()
@@ -115,7 +116,7 @@ def main():
                 refw = torch.einsum('nhwc,nhwd->cd', x.float(), dy.float()) if k == 1 else None
                 if refw is not None:
                     print('   wgrad relerr', float((dw[0, 0] - refw).abs().max() / refw.abs().max()))
-            print(f'{shp} var={var} cold {min(ts[1:])*1e3:8.1f} us  warm {warm*1e3:8.1f} us  {fl/warm/1e9:7.1f} TF/s  maxdiff_vs_var0 {err:.3g}', flush=True)
+            print(f'{shp} var={var} [{_C.last_conv_variant()}] cold {min(ts[1:])*1e3:8.1f} us  warm {warm*1e3:8.1f} us  {fl/warm/1e9:7.1f} TF/s  maxdiff_vs_var0 {err:.3g}', flush=True)
 
 
 if __name__ == '__main__':
