@@ -184,7 +184,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the waiter only needs this warp's
+  // tcgen05.ld's to have completed, which tcgen05.wait::ld + fence::before_thread_sync in program order guarantee; a
+  // .release.cluster here costs a MEMBAR per tile (8 % of the epilogue warps' samples in ncu)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait on a barrier of THIS CTA that threads of the peer CTA arrive on
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   using C = Cfg<BN, ST>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a provable __shared__ pointer (LDS/STS, not generic LD/ST)
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * C::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * C::B_BYTES);
@@ -670,12 +673,44 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 // and TMEM allocation / barrier init / descriptor prefetch are paid once per SM instead of once per tile.
 // (Measured on the one-tile-per-CTA kernel above at 256x32x32x128 3x3: 89 us, of which 45 us were per-CTA prologue +
 // handshake skeleton and 18 us the exposed epilogue.)   TMA im2col operand only.
+// The persistent kernels run 10 warps: 0-3 and 6-9 are two epilogue groups (warp w reads TMEM lanes 32*(w%4)..+31, the hardware's
+// rule; group 0 owns the left half of the tile's columns, group 1 the right half), warp 4 is the TMA producer, warp 5 issues
+// the MMAs.  With one group a 128x256 tile took ~7.7 us to drain (ncu: the four warps, one per scheduler, spend it on exposed
+// instruction latency), longer than the main loop of the K = 1024 transposed convs and of every conv with a fused epilogue.
+constexpr int EPI_GROUPS = 2;
+constexpr int PERSIST_THREADS = 64 + 128 * EPI_GROUPS;
+
+template <int BN>
+__device__ __forceinline__ void epilogue_stats_flush(const TcParams& p0, uint8_t* epi, const float* st_acc, int st_cnt, int quarter,
+                                                     int eg, int lane, int bn) {
+  constexpr int NT = 128 * EPI_GROUPS;
+  float* S = reinterpret_cast<float*>(epi);
+  int* Cn = reinterpret_cast<int*>(S + 2 * BN);
+  const int tid = (eg * 4 + quarter) * 32 + lane, hb = bn >> 1, lpr = hb / 8;      // a lane owns 8 columns of its group's half
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  for (int i = tid; i < 2 * BN + 1; i += NT) S[i] = 0.f;
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  const int col0 = eg * hb + (lane % lpr) * 8;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { atomicAdd(&S[col0 + j], st_acc[j]); atomicAdd(&S[BN + col0 + j], st_acc[8 + j]); }
+  atomicAdd(Cn, st_cnt);
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  float* dst = p0.colstats + (size_t)blockIdx.x * 2 * p0.N;
+  for (int i = tid; i < p0.N; i += NT) { dst[i] = S[i]; dst[p0.N + i] = S[BN + i]; }
+  float* counts = p0.colstats + (size_t)RCGAN_NUM_SMS * 2 * p0.N;
+  if (tid == 0) {
+    counts[blockIdx.x] = (float)(*Cn / (bn / 8));       // st_cnt counts 16-byte pieces: bn / 8 per stored row
+    for (int j = blockIdx.x + gridDim.x; j < RCGAN_NUM_SMS; j += gridDim.x) counts[j] = 0.f;
+  }
+}
+
 template <int BN, int MT, int ST, typename TO>
 struct PCfg {
   static constexpr int A_BYTES = MT * BM * BK * 2;     // MT stacked 128-row sub-tiles share one B tile
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int PITCH = BN * (int)sizeof(TO) + 16;
-  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 2048;
+  // two groups of 4 epilogue warps, each draining one half of the tile's columns through its own staging region
+  static constexpr int EPI_GROUP_BYTES = 4 * 32 * ((BN / 2) * (int)sizeof(TO) + 16) + 2048;
+  static constexpr int EPI_BYTES = EPI_GROUPS * EPI_GROUP_BYTES;
   static constexpr int SMEM = ST * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "persistent conv tile does not fit shared memory");
   static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
@@ -685,13 +720,13 @@ struct PCfg {
 // the tile shapes are chosen for flops per staged byte: 128x256 (N >= 256) and 256x128 (N <= 128) both move 48 KB per
 // 4.2 MFLOP K block, against 32 KB per 2.1 MFLOP for 128x128.
 template <int BN, int MT, int ST, typename TO, bool MULTI>
-__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ TcMulti mp,
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) conv_tc_persist_kernel(const __grid_constant__ TcMulti mp,
                                                                  const __grid_constant__ CUtensorMap wmap,
                                                                  const __grid_constant__ TcMaps amaps) {
   using C = PCfg<BN, MT, ST, TO>;
   constexpr int TM = MT * BM;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a provable __shared__ pointer (LDS/STS, not generic LD/ST)
   uint8_t* smA = smem;
   uint8_t* smB = smem + ST * C::A_BYTES;
   uint8_t* epi = smB + ST * C::B_BYTES;
@@ -699,7 +734,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   uint64_t* full = bars;               // [ST] 1 arrival (expect_tx) + TMA bytes
   uint64_t* empty = bars + ST;         // [ST] 1 arrival (tcgen05.commit)
   uint64_t* tfull = bars + 2 * ST;     // [2]  accumulator ready (tcgen05.commit)
-  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  accumulator drained (4 epilogue warps)
+  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  accumulator drained (4 * EPI_GROUPS epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -723,7 +758,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(smem_u32(&tfull[a]), 1);
-      mbar_init(smem_u32(&tempty[a]), 4);
+      mbar_init(smem_u32(&tempty[a]), 4 * EPI_GROUPS);
     }
     fence_barrier_init();
   }
@@ -740,8 +775,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // PDL: the prologue above overlapped the previous kernel's tail; its results are touched only from here on
 
-  if (warp < 4) {
-    // =========================================================== epilogue warps
+  if (warp < 4 || warp >= 6) {
+    // =========================================================== epilogue warps: group eg drains columns [eg * hb, +hb) of the tile
+    const int quarter = warp & 3, eg = warp >= 6 ? 1 : 0, hb = bn >> 1;
+    uint8_t* my_epi = epi + eg * C::EPI_GROUP_BYTES;
     int ti = 0;
     float st_acc[16];
     int st_cnt = 0;
@@ -753,36 +790,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       int q;
       const int lt = locate(tile, q);
       const TcParams& p = mp.p[q];
-      const int m0 = (lt / n_tiles_n) * TM, n0 = (lt % n_tiles_n) * bn;
+      const int m0 = (lt / n_tiles_n) * TM, n0 = (lt % n_tiles_n) * bn + eg * hb;
       mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < MT; j++)
-        tc_epilogue<BN, C::EPI_BYTES, TO, 4>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
-                                          j == MT - 1 ? smem_u32(&tempty[a]) : 0u, bn, stats ? st_acc : nullptr, &st_cnt);
+        tc_epilogue<BN / 2, C::EPI_GROUP_BYTES, TO, 4>(p, my_epi, tmem_base + (uint32_t)((a * MT + j) * BN + eg * hb), quarter, lane,
+                                                       m0 + j * BM, n0, j == MT - 1 ? smem_u32(&tempty[a]) : 0u, hb,
+                                                       stats ? st_acc : nullptr, &st_cnt);
     }
-    if (stats) {
-      // this CTA's partial (count, column sums, column sums of squares): lanes -> shared atomics -> one row of p0.colstats
-      // layout: [RCGAN_NUM_SMS][2][N] floats, then [RCGAN_NUM_SMS] row counts; CTAs that do not exist leave count 0
-      float* S = reinterpret_cast<float*>(epi);
-      int* Cn = reinterpret_cast<int*>(S + 2 * BN);
-      const int tid = warp * 32 + lane, lpr = bn / 8;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = tid; i < 2 * BN + 1; i += 128) S[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int col0 = (lane % lpr) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; j++) { atomicAdd(&S[col0 + j], st_acc[j]); atomicAdd(&S[BN + col0 + j], st_acc[8 + j]); }
-      atomicAdd(Cn, st_cnt);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* dst = p0.colstats + (size_t)blockIdx.x * 2 * p0.N;
-      for (int i = tid; i < p0.N; i += 128) { dst[i] = S[i]; dst[p0.N + i] = S[BN + i]; }
-      float* counts = p0.colstats + (size_t)RCGAN_NUM_SMS * 2 * p0.N;
-      if (tid == 0) {
-        counts[blockIdx.x] = (float)(*Cn / lpr);
-        for (int j = blockIdx.x + gridDim.x; j < RCGAN_NUM_SMS; j += gridDim.x) counts[j] = 0.f;
-      }
-    }
+    if (stats) epilogue_stats_flush<BN>(p0, epi, st_acc, st_cnt, quarter, eg, lane, bn);
     tc_fence_before();
   } else if (warp == 4) {
     // =========================================================== TMA producer
@@ -874,15 +891,15 @@ template <int BN, int MT, int ST, typename TO>
 struct PairCfg {
   static constexpr int A_BYTES = MT * BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the weight tile
-  static constexpr int PITCH = BN * (int)sizeof(TO) + 16;
-  static constexpr int EPI_BYTES = 4 * 32 * PITCH + 2048;
+  static constexpr int EPI_GROUP_BYTES = 4 * 32 * ((BN / 2) * (int)sizeof(TO) + 16) + 2048;
+  static constexpr int EPI_BYTES = EPI_GROUPS * EPI_GROUP_BYTES;
   static constexpr int SMEM = ST * (A_BYTES + B_BYTES) + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM <= 227 * 1024, "pair conv tile does not fit shared memory");
   static_assert(2 * MT * BN <= 512, "double-buffered accumulators must fit TMEM");
 };
 
 template <int BN, int MT, int ST, typename TO, bool MULTI>
-__global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_constant__ TcMulti mp,
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) conv_tc_pair_kernel(const __grid_constant__ TcMulti mp,
                                                               const __grid_constant__ CUtensorMap wmap,
                                                               const __grid_constant__ TcMaps amaps) {
   using C = PairCfg<BN, MT, ST, TO>;
@@ -890,7 +907,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   // the dynamic shared window starts at the same offset in both CTAs of the pair, so every carved address below is the same
   // shared::cta offset in both (the UMMA descriptors, the multicast commits and tcgen05.alloc rely on that)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a provable __shared__ pointer (LDS/STS, not generic LD/ST)
   uint8_t* smA = smem;
   uint8_t* smB = smem + ST * C::A_BYTES;
   uint8_t* epi = smB + ST * C::B_BYTES;
@@ -898,7 +915,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_const
   uint64_t* full = bars;               // [ST] leader: 1 arrival (expect_tx) + both CTAs' TMA bytes
   uint64_t* empty = bars + ST;         // [ST] each CTA: 1 arrival (multicast tcgen05.commit)
   uint64_t* tfull = bars + 2 * ST;     // [2]  each CTA: accumulator ready (multicast tcgen05.commit)
-  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  leader: accumulator drained (4 epilogue warps of each CTA)
+  uint64_t* tempty = bars + 2 * ST + 2;   // [2]  leader: accumulator drained (4 * EPI_GROUPS epilogue warps of each CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -922,7 +939,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_const
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(smem_u32(&tfull[a]), 1);
-      mbar_init(smem_u32(&tempty[a]), 8);
+      mbar_init(smem_u32(&tempty[a]), 2 * 4 * EPI_GROUPS);
     }
     fence_barrier_init();
   }
@@ -939,8 +956,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();
 
-  if (warp < 4) {
-    // =========================================================== epilogue warps (both CTAs, own 128 x MT rows)
+  if (warp < 4 || warp >= 6) {
+    // =========================================================== epilogue warps (both CTAs, own 128 x MT rows; two column groups)
+    const int quarter = warp & 3, eg = warp >= 6 ? 1 : 0, hb = bn >> 1;
+    uint8_t* my_epi = epi + eg * C::EPI_GROUP_BYTES;
     int ti = 0;
     float st_acc[16];
     int st_cnt = 0;
@@ -953,34 +972,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pair_kernel(const __grid_const
       int q;
       const int lt = locate(tile, q);
       const TcParams& p = mp.p[q];
-      const int m0 = (lt / n_tiles_n) * (2 * TM) + (int)rank * TM, n0 = (lt % n_tiles_n) * bn;
+      const int m0 = (lt / n_tiles_n) * (2 * TM) + (int)rank * TM, n0 = (lt % n_tiles_n) * bn + eg * hb;
       mbar_wait(smem_u32(&tfull[a]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < MT; j++)
-        tc_epilogue<BN, C::EPI_BYTES, TO, 4>(p, epi, tmem_base + (uint32_t)((a * MT + j) * BN), warp, lane, m0 + j * BM, n0,
-                                             j == MT - 1 ? (a ? tempty_leader1 : tempty_leader0) : 0u, bn, stats ? st_acc : nullptr, &st_cnt, true);
+        tc_epilogue<BN / 2, C::EPI_GROUP_BYTES, TO, 4>(p, my_epi, tmem_base + (uint32_t)((a * MT + j) * BN + eg * hb), quarter, lane,
+                                                       m0 + j * BM, n0, j == MT - 1 ? (a ? tempty_leader1 : tempty_leader0) : 0u, hb,
+                                                       stats ? st_acc : nullptr, &st_cnt, true);
     }
-    if (stats) {
-      float* S = reinterpret_cast<float*>(epi);
-      int* Cn = reinterpret_cast<int*>(S + 2 * BN);
-      const int tid = warp * 32 + lane, lpr = bn / 8;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = tid; i < 2 * BN + 1; i += 128) S[i] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int col0 = (lane % lpr) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; j++) { atomicAdd(&S[col0 + j], st_acc[j]); atomicAdd(&S[BN + col0 + j], st_acc[8 + j]); }
-      atomicAdd(Cn, st_cnt);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* dst = p0.colstats + (size_t)blockIdx.x * 2 * p0.N;
-      for (int i = tid; i < p0.N; i += 128) { dst[i] = S[i]; dst[p0.N + i] = S[BN + i]; }
-      float* counts = p0.colstats + (size_t)RCGAN_NUM_SMS * 2 * p0.N;
-      if (tid == 0) {
-        counts[blockIdx.x] = (float)(*Cn / lpr);
-        for (int j = blockIdx.x + gridDim.x; j < RCGAN_NUM_SMS; j += gridDim.x) counts[j] = 0.f;
-      }
-    }
+    if (stats) epilogue_stats_flush<BN>(p0, epi, st_acc, st_cnt, quarter, eg, lane, bn);
     tc_fence_before();
   } else if (warp == 4) {
     // =========================================================== TMA producer (both CTAs: own A rows, own half of B)
@@ -1117,7 +1118,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   using C = WgCfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; stays a provable __shared__ pointer (LDS/STS, not generic LD/ST)
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * C::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * C::B_BYTES);
@@ -1571,8 +1572,8 @@ int launch_tc_persist(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, 
     mp.tile_start[q + 1] = mp.tile_start[q] + ((mp.p[q].M + MT * BM - 1) / (MT * BM)) * n_tiles_n;
   const int n_tiles = mp.tile_start[mp.nprob];
   const int grid = n_tiles < RCGAN_NUM_SMS ? n_tiles : RCGAN_NUM_SMS;
-  if (mp.nprob > 1) launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, true>, grid, 192, C::SMEM, st, mp, map, amaps);
-  else launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, false>, grid, 192, C::SMEM, st, mp, map, amaps);
+  if (mp.nprob > 1) launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, true>, grid, PERSIST_THREADS, C::SMEM, st, mp, map, amaps);
+  else launch_pdl(conv_tc_persist_kernel<BN, MT, ST, TO, false>, grid, PERSIST_THREADS, C::SMEM, st, mp, map, amaps);
   RCGAN_LAUNCH_CHECK("conv_tc_persist");
   rcgan_set_conv_variant("conv_tc_persist<%d,%d,%d,%s,multi=%d>", BN, MT, ST, sizeof(TO) == 4 ? "f32" : "bf16", mp.nprob > 1 ? 1 : 0);
   return 0;
@@ -1596,7 +1597,7 @@ int launch_tc_pair(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, cud
   const int n_tiles = mp.tile_start[mp.nprob];
   const int npairs = n_tiles < RCGAN_NUM_SMS / 2 ? n_tiles : RCGAN_NUM_SMS / 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+  cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(PERSIST_THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
