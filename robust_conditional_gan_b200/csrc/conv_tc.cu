@@ -1103,6 +1103,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & PAIR_PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 template <int BN> struct WgCfg {
   static constexpr int STAGES = BN == 64 ? 4 : 3;
   static constexpr int UNIT_BYTES = 128 * 128;                 // 128 pixel rows x 128 B
@@ -1319,6 +1326,163 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// wgrad on a CTA pair (cta_group::2): the pair's tile is 4 units (256 accumulator rows) x BN output channels.  CTA r stages
+// its own two units of x (TMA im2col) and its half of the dy columns; the leader issues M = 256 UMMAs.  Per staged byte that
+// is twice the flops of the one-CTA 128 x 128 tile (BN = 256: 64 KB per 8 x (256 x 256 x 16) MMAs and CTA, against 64 KB per
+// 8 x (128 x 128 x 16)), and the operand stream from L2 is what bounds this kernel.  TMA im2col operand only.
+template <int BN> struct WgPairCfg {
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int UNIT_BYTES = 128 * 128;
+  static constexpr int A_BYTES = 2 * UNIT_BYTES;
+  static constexpr int B_BYTES = (BN / 128) * UNIT_BYTES;      // this CTA's BN/2 columns of dy, 64 per box
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "wgrad pair tile does not fit shared memory");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_pair_kernel(const __grid_constant__ WgParams p,
+                                                               const __grid_constant__ CUtensorMap dymap,
+                                                               const __grid_constant__ CUtensorMap xmap) {
+  using C = WgPairCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * C::B_BYTES);
+  uint64_t* full = bars;                  // leader: 1 arrival (expect_tx) + both CTAs' TMA bytes
+  uint64_t* empty = bars + STAGES;        // each CTA: multicast tcgen05.commit
+  uint64_t* accum_full = bars + 2 * STAGES;   // each CTA: multicast tcgen05.commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int u0 = (blockIdx.x >> 1) * 4 + (int)rank * 2;     // this CTA's two units
+  const int n0 = blockIdx.y * BN;
+  const int kb_beg = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_beg + p.kb_per_split);
+  const int nkb = kb_end - kb_beg;                           // >= 1 by the host's split choice
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    mbar_init(smem_u32(accum_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc_pair(smem_u32(tmem_slot), BN);
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&dymap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
+
+  if (warp < 4) {
+    // ---- epilogue: this CTA's 128 accumulator rows (two units x 64 channels) x BN columns, staged per warp and reduced
+    // into dW one whole row piece per lane (red.global.add.v4.f32), as in the one-CTA kernel
+    if (nkb > 0) {
+      mbar_wait(smem_u32(accum_full), 0);
+      tc_fence_after();
+      constexpr int PITCH = BN * 4 + 16;
+      static_assert(4 * 32 * PITCH <= STAGES * (C::A_BYTES + C::B_BYTES), "staging must fit the drained pipeline buffers");
+      uint8_t* slab = smem + warp * (32 * PITCH);
+      const int ncols = min(BN, p.cout - n0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (c0 >= ncols) continue;
+        uint4* dst = reinterpret_cast<uint4*>(slab + lane * PITCH + c0 * 4);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      __syncwarp();
+      const int u = u0 + (warp >> 1);
+      if (u < p.units) {
+        const int tap = u / p.cblks;
+        const int ci0 = (u - tap * p.cblks) * 64 + (warp & 1) * 32;
+        float* obase = p.dw + ((size_t)tap * p.cin + ci0) * p.cout + n0;
+        const int nrows = min(32, p.cin - ci0);
+        const bool vec = (ncols % 4 == 0) && (p.cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+        if (vec) {
+          const int lpr = ncols / 4;
+          for (int idx = lane; idx < nrows * lpr; idx += 32) {
+            const int row = idx / lpr, piece = idx - row * lpr;
+            const float4 q = *reinterpret_cast<const float4*>(slab + row * PITCH + piece * 16);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(obase + (size_t)row * p.cout + piece * 4), "f"(q.x),
+                         "f"(q.y), "f"(q.z), "f"(q.w)
+                         : "memory");
+          }
+        } else {
+          for (int row = 0; row < nrows; row++) {
+            const float* srow = reinterpret_cast<const float*>(slab + row * PITCH);
+            for (int c = lane; c < ncols; c += 32) atomicAdd(obase + (size_t)row * p.cout + c, srow[c]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      int utap[2], uc0[2];
+      bool uok[2];
+      for (int j = 0; j < 2; j++) {
+        const int u = u0 + j;
+        uok[j] = u < p.units;
+        const int uu = uok[j] ? u : 0;
+        utap[j] = uu / p.cblks;
+        uc0[j] = (uu - utap[j] * p.cblks) * 64;
+      }
+      for (int kk = 0; kk < nkb; kk++) {
+        const int s = kk % STAGES;
+        mbar_wait(smem_u32(&empty[s]), ((kk / STAGES) & 1) ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full[s]), 2 * (C::A_BYTES + C::B_BYTES));
+        const long mpix = (long)(kb_beg + kk) * 128;
+        const int n = (int)(mpix / p.HW), pi = (int)(mpix - (long)n * p.HW);
+        const int oy = pi / p.WO, ox = pi - oy * p.WO;
+#pragma unroll
+        for (int j = 0; j < 2; j++)      // a unit past the end of the filter loads channel block `cin` (out of bounds -> zeros)
+          tma_load_im2col_4d_pair(smem_u32(smA + s * C::A_BYTES + j * C::UNIT_BYTES), &xmap, smem_u32(&full[s]),
+                                  uok[j] ? uc0[j] : p.cblks * 64, ox * p.stride - p.pad_l, oy * p.stride - p.pad_t, n,
+                                  (unsigned short)(utap[j] % p.kw), (unsigned short)(utap[j] / p.kw));
+#pragma unroll
+        for (int j = 0; j < BN / 128; j++)
+          tma_load_2d_pair(smem_u32(smB + s * C::B_BYTES + j * C::UNIT_BYTES), &dymap, smem_u32(&full[s]),
+                           n0 + (int)rank * (BN / 2) + j * 64, (kb_beg + kk) * 128);
+      }
+    }
+  } else {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      for (int kk = 0; kk < nkb; kk++) {
+        const int s = kk % STAGES;
+        mbar_wait(smem_u32(&full[s]), (kk / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = umma_desc_mnmajor_sw128(smem_u32(smA + s * C::A_BYTES), C::UNIT_BYTES);
+        const uint64_t db = umma_desc_mnmajor_sw128(smem_u32(smB + s * C::B_BYTES), C::UNIT_BYTES);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; k++) umma_bf16_pair(tmem_base, da + 128 * k, db + 128 * k, idesc, (kk | k) != 0);
+        umma_commit_pair(smem_u32(&empty[s]));
+      }
+      if (nkb > 0) umma_commit_pair(smem_u32(accum_full));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, BN);
   }
 }
 
@@ -1940,6 +2104,29 @@ static int launch_wgrad_tc(const WgParams& p, const CUtensorMap& map, const CUte
   return 0;
 }
 
+template <int BN>
+static int launch_wgrad_tc_pair(const WgParams& p, const CUtensorMap& map, const CUtensorMap& xmap, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgPairCfg<BN>::SMEM);
+    if (e != cudaSuccess) { rcgan_set_error("wgrad_tc_pair: smem opt-in failed: %s", cudaGetErrorString(e)); return RCGAN_ECUDA; }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = WgPairCfg<BN>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = rcgan_pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, wgrad_tc_pair_kernel<BN>, p, map, xmap);
+  RCGAN_LAUNCH_CHECK("wgrad_tc_pair");
+  rcgan_set_conv_variant("wgrad_tc_pair<%d>", BN);
+  return 0;
+}
+
 // dw (=|+=) x^T dy on the tensor cores.  dw must be zero-initialised by the caller path when !accumulate.
 int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, cudaStream_t st,
                    int* handled) {
@@ -1984,7 +2171,32 @@ int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, floa
   ap.src = p.x; ap.SH = d->h; ap.SW = d->w; ap.ld_src = d->ldx; ap.MH = d->ho; ap.MW = d->wo;
   ap.im_w_lo = -d->pad_l; ap.im_h_lo = -d->pad_t; ap.im_sw = d->stride; ap.im_sh = d->stride;
   CUtensorMap xmap;
-  if (make_amap(&xmap, ap, d->cin, d->n)) {
+  const bool im2col = make_amap(&xmap, ap, d->cin, d->n);
+  // CTA pairs for 256-multiple cout (measured 512x32x32 256->256 k3: 580 -> 398 us, 1.07 -> 1.56 PFLOP/s; with 128 output channels
+  // the pair tile stages 48 KB per 8 MMAs against 64 KB and came out even or slower: 43.6 -> 48.0 us at 512x16x16 128->128 k3;
+  // RCGAN_TC_PAIR=2 takes that path too)
+  if (im2col && p.units >= 4 && ((pair_mode() >= 1 && d->cout % 256 == 0) || (pair_mode() >= 2 && d->cout % 128 == 0))) {
+    // 4 units x (256 | 128) channels per pair; split K so that the pairs fill the 74 TPCs in whole waves
+    const int pbn = d->cout % 256 == 0 ? 256 : 128;
+    const int ptiles = ((p.units + 3) / 4) * (d->cout / pbn);
+    long best = -1;
+    int best_s = 1;
+    for (int sp = 1; sp <= max_splits && sp <= 4 * RCGAN_NUM_SMS; sp++) {
+      const int per = (p.kb_total + sp - 1) / sp;
+      const int real = (p.kb_total + per - 1) / per;
+      const long waves = ((long)ptiles * real + RCGAN_NUM_SMS / 2 - 1) / (RCGAN_NUM_SMS / 2);
+      const long cost = waves * (per + 6);               // + ~6 K blocks of prologue / epilogue per CTA
+      if (best < 0 || cost < best) { best = cost; best_s = sp; }
+    }
+    p.kb_per_split = (p.kb_total + best_s - 1) / best_s;
+    const int psplits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    dim3 pgrid(2 * ((p.units + 3) / 4), d->cout / pbn, psplits);
+    if (int e = (pbn == 256 ? launch_wgrad_tc_pair<256>(p, map, xmap, pgrid, st) : launch_wgrad_tc_pair<128>(p, map, xmap, pgrid, st)))
+      return e;
+    *handled = 1;
+    return 0;
+  }
+  if (im2col) {
     if (int e = (bn == 64 ? launch_wgrad_tc<64, true>(p, map, xmap, grid, st) : launch_wgrad_tc<128, true>(p, map, xmap, grid, st)))
       return e;
   } else {

@@ -18,6 +18,8 @@ ALIAS_RESIDUAL = os.environ.get('RCGAN_ALIAS_RESIDUAL', '1') == '1'
 FUSE_RELU_OUT = os.environ.get('RCGAN_FUSE_RELU_OUT', '1') == '1'
 FUSE_BN_STATS = os.environ.get('RCGAN_FUSE_BN_STATS', '1') == '1'
 BN_MASK_FROM_X = os.environ.get('RCGAN_BN_MASK_FROM_X', '0') == '1'
+# a conv's filter gradient on the side stream, next to its input gradient (both only read dL/dy; joined at the end of the op)
+FORK_WGRAD = os.environ.get('RCGAN_FORK_WGRAD', '1') == '1'
 
 ACT = {None: _C.ACT_NONE, 'none': _C.ACT_NONE, 'relu': _C.ACT_RELU, 'lrelu': _C.ACT_LRELU, 'sigmoid': _C.ACT_SIGMOID,
        'tanh': _C.ACT_TANH}
@@ -364,6 +366,15 @@ class ConvOp(Op):
         if self.tpatch is not None and (nx or nw) and not (nx and self.acc_x):
             self._backward_transposed(prog, nx, nw, dy, st)
             nx = nw = False
+        def wgrad():
+            s = stream_ptr()
+            if self.patch is not None:
+                call('rcgan_conv2d_wgrad', self.gdesc, dp(self.patch), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, s)
+            else:
+                call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, s)
+        if nw and nx and FORK_WGRAD and torch.cuda.is_available():
+            prog.fork(wgrad)            # wgrad || dgrad: independent outputs, the small layers do not fill the machine alone
+            nw = False
         if nx:
             if self.dx_mask is not None:
                 call('rcgan_conv2d_dgrad_ex', self.desc, dy, pp(self.pack), None, gp(self.dx_target), self.x.grad_dtype, _C.ACT_NONE,
@@ -378,10 +389,7 @@ class ConvOp(Op):
                 call('rcgan_conv2d_dgrad', self.desc, dy, dp(self.w), None if self.patch is not None else pp(self.pack), None,
                      gp(self.x), self.x.grad_dtype, _C.ACT_NONE, 0.0, self.acc_x, st)
         if nw:
-            if self.patch is not None:
-                call('rcgan_conv2d_wgrad', self.gdesc, dp(self.patch), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
-            else:
-                call('rcgan_conv2d_wgrad', self.desc, dp(self.x), dy, gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+            wgrad()
         if nb and self.b is not None and not bias_done:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 
@@ -470,11 +478,15 @@ class DeconvOp(Op):
         if self.patch is not None and (nx or nw):
             call('rcgan_im2col', self.desc, dy, dp(self.patch), self.patch.ld, st)
             d, dyin = self.gdesc, dp(self.patch)
+        wgrad = lambda: call('rcgan_conv2d_wgrad', d, dyin, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, stream_ptr())
+        if nw and nx and FORK_WGRAD and torch.cuda.is_available():
+            prog.fork(wgrad)
+            nw = False
         if nx:
             call('rcgan_conv2d_fprop', d, dyin, dp(self.w), pp(self.pack), None, gp(self.x), self.x.grad_dtype, _C.ACT_NONE,
                  0.0, st)
         if nw:
-            call('rcgan_conv2d_wgrad', d, dyin, dp(self.x), gp(self.w), self.acc_w, prog.ws.ptr(), prog.ws.bytes, st)
+            wgrad()
         if nb and self.b is not None and not bias_done:
             call('rcgan_colsum', dy, y.rows, y.c, y.ld, y.grad_dtype, gp(self.b), self.acc_b, st)
 

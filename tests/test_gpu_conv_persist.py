@@ -253,9 +253,11 @@ def test_persistent_upsample_conv(lib, n, h, w, cin, cout, variant, pair):
 
 
 @pytest.mark.parametrize('shape,variant', [((128, 32, 32, 256, 256, 3, 1, 0, 0), 'wgrad_tc<128,im2col=1>'),
+                                           ((512, 16, 16, 128, 128, 3, 1, 0, 0), 'wgrad_tc<128,im2col=1>'),     # 18 units: the last pair's peer CTA is empty
+                                           ((300, 32, 32, 128, 128, 4, 2, 0, 0), 'wgrad_tc<128,im2col=1>'),     # folded ConvMeanPool, ragged pixel count
                                            ((1024, 14, 14, 128, 138, 5, 2, 0, 6), 'wgrad_tc<128,im2col=1>'),
                                            ((2048, 7, 7, 64, 64, 5, 2, 0, 0), 'wgrad_tc<64,im2col=1>')])
-def test_wgrad_at_benchmark_sizes(lib, shape, variant):
+def test_wgrad_at_benchmark_sizes(lib, shape, variant, pair):
     """the tcgen05 wgrad at the benchmarks' contraction lengths (K = n*ho*wo up to 131072 pixels, many split-K slices)"""
     d, x, wt, b, dy, xd, dyd, _ = make(shape)
     s = shape[6]
@@ -266,6 +268,8 @@ def test_wgrad_at_benchmark_sizes(lib, shape, variant):
     dw = torch.full(wt.shape, 3.0, device='cuda')
     call('rcgan_conv2d_wgrad', d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), nb, st())
     torch.cuda.synchronize()
+    if pair and shape[4] % 128 == 0:        # the CTA-pair wgrad: 4 units x 256 (cout % 256 == 0) or 128 channels
+        variant = 'wgrad_tc_pair<%d>' % (256 if shape[4] % 256 == 0 else 128)
     assert _C.last_conv_variant() == variant
     assert relerr(dw.cpu(), wr.grad) < 8e-5               # fp32 reference over K ~ 1e5 pixels carries its own ~2e-5
     # fp64 on a slice of the output channels (wgrad cost is linear in cout)

@@ -1,0 +1,12 @@
+# A/B runs of bench.py under environment switches (debug helper): usage  bash tools/ab_flags.sh
+run() { name=$1; shift; env "$@" timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-secondary --no-op-profile > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; python -c "
+import json,sys
+try:
+    d=json.loads([l for l in open('gpurun_out/ab_$name.json') if l.startswith('{')][-1]); print('$name', round(d['ms_per_step'],3), round(d['value']), d['gpu_launches'])
+except Exception as e: print('$name FAILED', e)
+"; }
+run base X=1
+run nofork RCGAN_FORK_WGRAD=0
+run pair0 RCGAN_TC_PAIR=0
+run pair0_nofork RCGAN_TC_PAIR=0 RCGAN_FORK_WGRAD=0
+run pair2 RCGAN_TC_PAIR=2
