@@ -1776,8 +1776,9 @@ int launch_tc_pair(TcMulti& mp, const CUtensorMap& map, const TcMaps& amaps, cud
   return 0;
 }
 
-// RCGAN_TC_PAIR: 0 = persistent launches stay on the one-CTA (cta_group::1) kernel, 1 (default) = CTA pairs for the 256-wide
-// tiles, 2 = CTA pairs wherever the N tile is a multiple of 32
+// RCGAN_TC_PAIR: 0 = persistent launches stay on the one-CTA (cta_group::1) kernel, 1 = CTA pairs for the 256-wide tiles
+// (and wgrad with cout % 256 == 0), 2 = CTA pairs wherever the N tile is a multiple of 32 (wgrad: cout % 128 == 0),
+// 3 = fprop / dgrad as 2, wgrad as 1
 int pair_mode() {
   const char* e = getenv("RCGAN_TC_PAIR");
   return e ? atoi(e) : 1;
@@ -1799,7 +1800,7 @@ int run_tc_persist(TcMulti& mp, const TcMaps& amaps, const bf16* wbase, int kpad
   long tiles256 = 0;
   for (int q = 0; q < mp.nprob; q++) { mp.p[q].bn_eff = bn_eff; tiles256 += (long)((mp.p[q].M + 255) / 256) * ((p.N + bn_eff - 1) / bn_eff); }
   CUtensorMap map;
-  if (bn_eff % 32 == 0 && (pair_mode() >= 2 || (pair_mode() == 1 && wide))) {
+  if (bn_eff % 32 == 0 && (pair_mode() >= 2 || (pair_mode() == 1 && wide))) {   // 3: as 2 here
     // CTA pairs: each CTA loads half of the weight tile's columns
     if (int e = make_wmap(&map, wbase, kpad, rows, taps, bn_eff / 2)) return e;
     if (wide) return launch_tc_pair<256, 1, 4, bf16>(mp, map, amaps, st);
@@ -2175,7 +2176,7 @@ int rcgan_tc_wgrad(const rcgan_conv_desc* d, const void* x, const void* dy, floa
   // CTA pairs for 256-multiple cout (measured 512x32x32 256->256 k3: 580 -> 398 us, 1.07 -> 1.56 PFLOP/s; with 128 output channels
   // the pair tile stages 48 KB per 8 MMAs against 64 KB and came out even or slower: 43.6 -> 48.0 us at 512x16x16 128->128 k3;
   // RCGAN_TC_PAIR=2 takes that path too)
-  if (im2col && p.units >= 4 && ((pair_mode() >= 1 && d->cout % 256 == 0) || (pair_mode() >= 2 && d->cout % 128 == 0))) {
+  if (im2col && p.units >= 4 && ((pair_mode() >= 1 && d->cout % 256 == 0) || (pair_mode() == 2 && d->cout % 128 == 0))) {
     // 4 units x (256 | 128) channels per pair; split K so that the pairs fill the 74 TPCs in whole waves
     const int pbn = d->cout % 256 == 0 ? 256 : 128;
     const int ptiles = ((p.units + 3) / 4) * (d->cout / pbn);

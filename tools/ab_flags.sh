@@ -5,8 +5,8 @@ try:
     d=json.loads([l for l in open('gpurun_out/ab_$name.json') if l.startswith('{')][-1]); print('$name', round(d['ms_per_step'],3), round(d['value']), d['gpu_launches'])
 except Exception as e: print('$name FAILED', e)
 "; }
-run base X=1
-run nofork RCGAN_FORK_WGRAD=0
-run pair0 RCGAN_TC_PAIR=0
-run pair0_nofork RCGAN_TC_PAIR=0 RCGAN_FORK_WGRAD=0
+run pair1 RCGAN_TC_PAIR=1
 run pair2 RCGAN_TC_PAIR=2
+run pair3 RCGAN_TC_PAIR=3
+run pair1b RCGAN_TC_PAIR=1
+run pair3b RCGAN_TC_PAIR=3
