@@ -19,6 +19,10 @@ from . import _C
 from ._C import ConvDesc, call, ptr, stream_ptr
 
 SIDE_STREAM = __import__('os').environ.get('RCGAN_SIDE_STREAM', '1') == '1'   # A/B switch of Program.fork
+# derived (spectral-normed / folded) conv weights: their gradient buffers are zeroed by ONE kernel at the start of the backward
+# sweep and every wgrad accumulates, instead of one cudaMemset node in front of each wgrad (a memset node is a full dependency:
+# the wgrad behind it loses its programmatic-dependent-launch overlap)
+PREZERO_WGRAD = __import__('os').environ.get('RCGAN_PREZERO_WGRAD', '1') == '1'
 I32 = 100   # host-side dtype tag for integer label tensors (never passed to the library as an activation dtype)
 U8 = 101    # raw image bytes (CIFAR pixels)
 TORCH_DTYPE = {_C.F32: torch.float32, _C.BF16: torch.bfloat16, I32: torch.int32, U8: torch.uint8}
@@ -231,6 +235,15 @@ class Op:
         t.base.grad_written = True
         return acc
 
+    def claim_wgrad(self, prog, t):
+        """claim() for a conv filter gradient: the first writer of a derived weight's gradient registers the buffer for the
+        program's batched zeroing and accumulates (see PREZERO_WGRAD)"""
+        if PREZERO_WGRAD and not t.is_variable and not t.base.grad_written:
+            prog.prezero.append(t.base)
+            t.base.grad_written = True
+            return 1
+        return self.claim(t)
+
     def plan_bwd(self, prog):
         pass
 
@@ -261,6 +274,8 @@ class Program:
         self._pack_args = None
         self._pack_args_own = None
         self._update_args = None
+        self.prezero = []           # tensors whose gradient buffer is zeroed at the start of the backward sweep (claim_wgrad)
+        self._prezero_args = None
         self.after_backward = {}    # op index -> [callable]; index len(ops) = before the sweep starts
         self._side, self._forked = None, False
         self.finalized = False
@@ -365,6 +380,7 @@ class Program:
         """wrt: iterable of Variables this program differentiates with respect to."""
         wrt = set(id(v) for v in wrt)
         self.wrt = wrt
+        self.prezero, self._prezero_args = [], None
         for t in self.tensors:
             t.needs_grad = False
             t.grad_written = False
@@ -430,6 +446,16 @@ class Program:
         backward sits at the first normalised weight, i.e. after everything that feeds it).  after_backward[i]: callables run once
         op i's backward is enqueued -- the data-parallel reducer launches a gradient bucket there (parallel.GradReducer)."""
         hooks = self.after_backward
+        if self.prezero:
+            if self._prezero_args is None:
+                import ctypes
+                n = len(self.prezero)
+                numels = [t._grad.numel() for t in self.prezero]
+                assert all(t._grad.dtype == torch.float32 for t in self.prezero)
+                self._zero_src = torch.zeros(max(numels), dtype=torch.float32, device=self.device)
+                PA, LA = ctypes.c_void_p * n, ctypes.c_long * n
+                self._prezero_args = (n, PA(*[self._zero_src.data_ptr()] * n), PA(*[t._grad.data_ptr() for t in self.prezero]), LA(*numels))
+            call('rcgan_copy_batched', *self._prezero_args, stream_ptr())
         for h in hooks.get(len(self.ops), ()):
             h()
         for op in reversed(self.ops):

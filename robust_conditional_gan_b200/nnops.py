@@ -276,7 +276,7 @@ class ConvOp(Op):
         self.acc_x = self.claim(self.dx_target) if nx else 0
         if self.dx_mask is not None:
             self.dx_ep = _C.ConvEpilogue(mask=dp(self.x), mask_act=self.dx_mask[0], mask_leak=self.dx_mask[1])
-        self.acc_w = self.claim(self.w) if nw else 0
+        self.acc_w = self.claim_wgrad(prog, self.w) if nw else 0
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
     def _backward_transposed(self, prog, nx, nw, dy, st):
@@ -440,7 +440,7 @@ class DeconvOp(Op):
         nx, nw, nb = self.need
         self.acc_x = self.claim(self.x) if nx else 0
         assert self.acc_x == 0, 'deconv input gradient must have a single writer'
-        self.acc_w = self.claim(self.w) if nw else 0
+        self.acc_w = self.claim_wgrad(prog, self.w) if nw else 0
         self.acc_b = self.claim(self.b) if (nb and self.b is not None) else 0
 
     def forward(self, prog):

@@ -174,3 +174,23 @@ def test_spectral_norm_ops_batch_only_parameters():
         w2 = CastOp(a.wbar, _C.F32).y                              # a W produced by another op is not available up front
         b = SpectralNormOp(w2, v['u'], update=False)
     assert a.batched and not b.batched
+
+
+def test_derived_weight_gradients_are_zeroed_once_per_sweep_and_accumulated():
+    """A spectral-normed filter's gradient buffer belongs to the program, not to the parameter arena: its first writer (the conv's
+    wgrad) registers it for the one batched zeroing at the start of the backward sweep and accumulates, so no memset node sits in
+    front of each wgrad; a plain parameter's gradient keeps accumulating into the arena."""
+    st, v = store_with(W=(3, 3, 64, 64), u=(1, 64), w_plain=(3, 3, 64, 64))
+    p = Program('t', DEV, _C.BF16)
+    with p:
+        x = p.input('x', [2, 8, 8, 64], _C.BF16)
+        sn = SpectralNormOp(v['W'], v['u'])
+        c1 = ConvOp(x, sn.wbar, None)
+        c2 = ConvOp(c1.y, sn.wbar, None)           # the same normalised filter used twice: the second wgrad accumulates too
+        c3 = ConvOp(c2.y, v['w_plain'], None)
+        MeanHWOp(c3.y)
+    st.finalize()
+    p.finalize([v['W'], v['w_plain']])
+    assert [t is sn.wbar.base for t in p.prezero] == [True]
+    assert c1.acc_w == 1 and c2.acc_w == 1 and c3.acc_w == 1
+    assert sn.wbar.base.grad_written
