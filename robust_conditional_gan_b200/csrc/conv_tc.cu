@@ -6,14 +6,22 @@
 // useful flops are issued) and the tf.matmul linears (1x1, h=w=1).
 //
 //   GEMM view:  D[128 pixels x BN channels] += A[128 x 64] * B[BN x 64]^T   per K block (one filter tap x 64 channels)
-//   A (activations): gathered by 4 producer warps with 16-byte cp.async (zero-fill for the SAME-padding halo and the
-//       channel tail) straight into the UMMA canonical K-major SWIZZLE_128B layout, then fence.proxy.async + mbarrier
+//   A (activations): TMA im2col (cp.async.bulk.tensor.4d...im2col: 128 pixels x 64 channels per load, the SAME-padding halo
+//       and the channel tail zero-filled by the bounding box) into the UMMA canonical K-major SWIZZLE_128B layout; when the
+//       im2col map is not encodable, 4 producer warps gather the same layout with 16-byte cp.async (one-tile kernel only)
 //   B (weights)    : TMA 3-D tiled load (cp.async.bulk.tensor, SWIZZLE_128B) from the packed bf16 weight copy
 //   MMA            : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per K block,
 //                    accumulator in TMEM; tcgen05.commit releases the smem stage / signals the epilogue
-//   epilogue       : the 4 producer warps read TMEM with tcgen05.ld.32x32b, add bias, apply the activation and store
-//                    bf16 or fp32 NHWC rows (optionally accumulating: dgrad into a gradient that already has a writer)
-// 3-4 stage mbarrier ring, <= 96 KB smem per CTA so two CTAs share an SM (one CTA's epilogue overlaps the other's MMAs).
+//   epilogue       : 4 warps (8 in the persistent kernels) read TMEM with tcgen05.ld.32x32b, add bias, apply the activation,
+//                    stage whole rows in shared memory and store bf16 or fp32 NHWC rows (optionally accumulating, adding a
+//                    residual, masking with an activation derivative, emitting a second relu output / column statistics)
+// Three kernels share these operands and the epilogue:
+//   conv_tc_kernel         one 128 x BN tile per CTA, 3-4 stage ring, <= 96 KB smem so two CTAs share an SM (one CTA's epilogue
+//                          overlaps the other's MMAs): small problems
+//   conv_tc_persist_kernel one CTA per SM loops over tiles; accumulators double buffered in TMEM; 10 warps (two epilogue groups)
+//   conv_tc_pair_kernel    the persistent kernel on a CTA pair: tcgen05.mma.cta_group::2 (M = 256 over two SMs), each CTA stages
+//                          half of the weight tile; default for the 256-wide tiles
+// and the filter gradient runs as wgrad_tc_kernel (one 128 x 128 tile per CTA, split-K) or wgrad_tc_pair_kernel (256 x 256 per pair).
 #include <cuda.h>
 
 #include "common.cuh"
