@@ -195,3 +195,93 @@ def test_resampling_folds_into_a_4x4_stride2_filter():
         ga, = torch.autograd.grad(a.square().sum(), w)
         gb, = torch.autograd.grad(b.square().sum(), w)
         assert float((ga - gb).abs().max()) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ more identities
+# (floating-point parity is unpinned -- TensorFlow 1.5 cannot run here -- so the oracle is anchored on algebraic identities
+# that hold for the reference's formulas and would break under the usual restatement mistakes)
+def test_sigmoid_ce_is_the_stable_form_of_the_textbook_loss():
+    """tf.nn.sigmoid_cross_entropy_with_logits (mnist/model.py:139-147): max(x,0) - x z + log(1 + exp(-|x|)) equals
+    -z log s(x) - (1-z) log(1 - s(x)) and stays finite where the textbook form overflows"""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, generator=g, dtype=torch.float64) * 6
+    z = torch.rand(1000, generator=g, dtype=torch.float64)
+    s = torch.sigmoid(x)
+    assert torch.allclose(O.sigmoid_ce(x, z), -z * torch.log(s) - (1 - z) * torch.log1p(-s), atol=1e-10)
+    big = torch.tensor([-800.0, 800.0], dtype=torch.float64)
+    out = O.sigmoid_ce(big, torch.tensor([1.0, 0.0], dtype=torch.float64))
+    assert torch.isfinite(out).all() and torch.allclose(out, torch.tensor([800.0, 800.0], dtype=torch.float64))
+
+
+def test_hinge_losses_and_their_subgradients():
+    """mnist/model.py:135-138, gan_resnet.py:604-606: d_real = relu(1 - x), d_fake = relu(1 + x), g = -x"""
+    dr, df, gl = O.gan_loss_fns('hinge')
+    x = torch.tensor([-2.0, -1.0, 0.0, 0.5, 1.0, 3.0], dtype=torch.float64, requires_grad=True)
+    assert torch.equal(dr(x).detach(), torch.tensor([3.0, 2.0, 1.0, 0.5, 0.0, 0.0], dtype=torch.float64))
+    assert torch.equal(df(x).detach(), torch.tensor([0.0, 0.0, 1.0, 1.5, 2.0, 4.0], dtype=torch.float64))
+    (gx,) = torch.autograd.grad(dr(x).sum() + df(x).sum() + gl(x).sum(), x)
+    # d/dx: -[x<1] + [x>-1] - 1 (torch's relu has subgradient 0 at the kink, like TF's)
+    assert torch.equal(gx, torch.tensor([-2.0, -2.0, -1.0, -1.0, 0.0, 0.0], dtype=torch.float64))
+
+
+def test_conditional_batchnorm_with_one_label_is_plain_batchnorm():
+    """normalization.py:27-59 against mnist/ops.py:30-44: same moments (axes 0,1,2, biased variance); with a single label the
+    gathered scale / offset rows are gamma / beta"""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(6, 5, 5, 8, generator=g, dtype=torch.float64) * 2 + 1
+    gamma, beta = torch.rand(8, generator=g, dtype=torch.float64) + 0.5, torch.randn(8, generator=g, dtype=torch.float64)
+    y_plain, mean, var = O.batch_norm_train(x, gamma, beta)
+    labels = torch.zeros(6, dtype=torch.long)
+    y_cond = O.cond_batchnorm(x, labels, beta[None].repeat(3, 1), gamma[None].repeat(3, 1))
+    assert torch.allclose(y_plain, y_cond, atol=1e-12)
+    # and the statistics are per BATCH, not per label: permuting which samples carry which label leaves (y - offset) / scale alone
+    lab = torch.tensor([0, 1, 2, 0, 1, 2])
+    off, sc = torch.randn(3, 8, generator=g, dtype=torch.float64), torch.rand(3, 8, generator=g, dtype=torch.float64) + 0.5
+    xhat = (O.cond_batchnorm(x, lab, off, sc) - off[lab][:, None, None, :]) / sc[lab][:, None, None, :]
+    assert torch.allclose(xhat, (x - mean) * torch.rsqrt(var + 1e-5), atol=1e-12)
+
+
+def test_power_iteration_converges_to_the_largest_singular_value():
+    """mnist/sn.py:17-75: repeated from the returned u, sigma -> ||W||_2 and W_bar has spectral norm 1; ONE iteration from a random
+    u (what a training step does) underestimates it"""
+    g = torch.Generator().manual_seed(2)
+    W = torch.randn(3, 3, 16, 24, generator=g, dtype=torch.float64)
+    u = torch.randn(1, 24, generator=g, dtype=torch.float64)
+    top = torch.linalg.svdvals(W.reshape(-1, 24))[0]
+    _, _, s1 = O.spectral_normed_weight(W, u)
+    assert float(s1) < float(top)
+    for _ in range(200):
+        Wbar, u, sigma = O.spectral_normed_weight(W, u)
+    assert abs(float(sigma) - float(top)) < 1e-8 * float(top)
+    assert abs(float(torch.linalg.svdvals(Wbar.reshape(-1, 24))[0]) - 1.0) < 1e-8
+
+
+def test_one_by_one_conv_is_the_linear_layer_and_concat_broadcasts_labels():
+    """ops.linear (mnist/ops.py:97-113) == conv2d with a 1x1 filter on a 1x1 image; conv_cond_concat (mnist/ops.py:46-51)"""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(7, 20, generator=g, dtype=torch.float64)
+    w = torch.randn(20, 9, generator=g, dtype=torch.float64)
+    assert torch.allclose(O.conv2d(x.reshape(7, 1, 1, 20), w.reshape(1, 1, 20, 9), 1).reshape(7, 9), x @ w, atol=1e-12)
+    img = torch.randn(7, 4, 4, 3, generator=g, dtype=torch.float64)
+    y = torch.eye(10, dtype=torch.float64)[torch.arange(7) % 10]
+    cat = O.conv_cond_concat(img, y)
+    assert cat.shape == (7, 4, 4, 13) and torch.equal(cat[..., :3], img)
+    assert all(torch.equal(cat[i, r, c, 3:], y[i]) for i in range(7) for r in range(4) for c in range(4))
+
+
+def test_tf_adam_first_step_is_lr_times_sign_and_max_norm_clips():
+    """tf.train.AdamOptimizer at t = 1: the step is lr * g / (|g| + eps') ~ lr * sign(g) whatever |g| is (>> eps');
+    the max-norm constrained variables (mnist/ops.py:101-111) are clipped to [-1, 1] AFTER the update"""
+    P = {'a': torch.tensor([0.5, -0.5, 0.999, -0.2], dtype=torch.float64)}
+    opt = O.TFAdam(['a'], lr=2e-3, beta1=0.5, clip=['a'])
+    gr = {'a': torch.tensor([3.0, -1e-3, -40.0, 7.0], dtype=torch.float64)}
+    before = P['a'].clone()
+    opt.step(P, gr)
+    step = before - P['a']
+    # exactly lr * g / (|g| + eps / sqrt(1 - beta2)): TF's epsilon sits OUTSIDE the bias correction, so at t = 1 it is 31.6x larger
+    # relative to |g| than torch.optim.Adam's -- visible at |g| = 1e-3 (3.2e-4 relative), invisible at |g| = 3
+    eps_eff = 1e-8 / (1 - 0.999) ** 0.5
+    want = 2e-3 * gr['a'] / (gr['a'].abs() + eps_eff)
+    assert torch.allclose(step[[0, 1, 3]], want[[0, 1, 3]], rtol=1e-12)
+    assert abs(float(step[1]) / -2e-3 - 1) > 3e-4 and abs(float(step[0]) / 2e-3 - 1) < 2e-7
+    assert float(P['a'][2]) == 1.0                      # 0.999 + 0.002 clipped
